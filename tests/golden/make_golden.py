@@ -1,0 +1,249 @@
+"""Generate the golden fixtures in this directory by RUNNING THE REFERENCE ITSELF.
+
+Run in the build container only (it imports /root/reference read-only; nothing is copied):
+
+    python tests/golden/make_golden.py
+
+The GPU box has no /root/reference, so tests read the committed ``*.npz`` files instead.
+Weights are closed-form (oracle.kit_oracle.deterministic_state_dict) so fixtures stay small.
+"""
+import os
+import random
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+sys.path.insert(0, REF)
+for _stub in ("h5py", "matplotlib", "matplotlib.pyplot", "wandb", "tqdm"):   # imported, never used here
+    try:
+        __import__(_stub)
+    except Exception:
+        sys.modules[_stub] = types.ModuleType(_stub)
+
+import model as ref_model                      # noqa: E402  /root/reference/model.py
+import euclidean_loss as ref_loss              # noqa: E402
+import augmentation as ref_aug                 # noqa: E402
+import dataloader as ref_dl                    # noqa: E402
+from oracle import kit_oracle as ko            # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def ref_forward_unbatched(m, x, xf, x_mask, y_mask, K):
+    """Exactly the A1_train.py:117-124 call for one sequence; K != 54 through the fc_final hook
+     because model.py:167 hard-codes 54."""
+    T = x.shape[0]
+    src_mask = m.get_mask(x_mask, T, "repeat-inc")
+    tgt_mask = m.get_mask(y_mask, T, "repeat-inc")
+    cap = {}
+    h = m.fc_final.register_forward_hook(lambda mod, i, o: cap.__setitem__("o", o))
+    try:
+        out = m(x, xf, src_pad_mask=x_mask.unsqueeze(0), tgt_pad_mask=y_mask.unsqueeze(0),
+                src_mask=src_mask, tgt_mask=tgt_mask)
+    except RuntimeError:
+        out = None
+    finally:
+        h.remove()
+    hooked = cap["o"].reshape(T, K, 2)
+    if K == 54:
+        assert out is not None and torch.equal(out, hooked)
+    return hooked
+
+
+def completer_case(name, K, H, L, NH, T, B, seed, grads_full):
+    sd = ko.deterministic_state_dict(2 * K, H, L)
+    m = ref_model.KeypointCompleter(input_size=2 * K, hidden_dim=H, num_layers=L, num_heads=NH)
+    missing = m.load_state_dict(sd, strict=True)
+    inputs, gt, mask = ko.synthetic_batch(B, T, K, seed=seed)
+    preds, losses_mse, losses_euc_eval = [], [], []
+    m.zero_grad()
+    total = 0.0
+    for b in range(B):
+        x = inputs[b, :-1]
+        xf = inputs[b, 1:]
+        xm = mask[b, :-1].clone()
+        ym = mask[b, 1:].clone()
+        pred = ref_forward_unbatched(m, x, xf, xm, ym, K)
+        preds.append(pred.detach())
+        loss = torch.nn.MSELoss()(pred, gt[b])                       # A1_train.py:254,128
+        losses_mse.append(loss.detach())
+        total = total + loss / B                                      # batched mean == mean of means
+        blended = pred * ym[:, None, None] + gt[b] * (1 - ym)[:, None, None]     # A1_train.py:184
+        losses_euc_eval.append(ref_loss.EuclideanLoss()(blended, gt[b]).detach())
+    total.backward()
+    out = {
+        "K": K, "H": H, "L": L, "NH": NH, "T": T, "B": B, "seed": seed,
+        "inputs": inputs.numpy(), "gt": gt.numpy(), "mask": mask.numpy(),
+        "pred": torch.stack(preds).numpy(),
+        "loss_mse": torch.stack(losses_mse).numpy(),
+        "loss_euclid_eval": torch.stack(losses_euc_eval).numpy(),
+        "loss_euclid_train": np.array([ref_loss.EuclideanLoss()(p, g).item()
+                                       for p, g in zip(preds, gt)], dtype=np.float32),
+    }
+    names = [n for n, _ in m.named_parameters()]
+    out["grad_names"] = np.array(names)
+    out["grad_norms"] = np.array([p.grad.norm().item() for _, p in m.named_parameters()], dtype=np.float64)
+    for n, p in m.named_parameters():
+        if n in grads_full:
+            out["grad::" + n] = p.grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "pred", out["pred"].shape, "loss", out["loss_mse"])
+
+
+def get_mask_case():
+    m = ref_model.KeypointCompleter(input_size=108, hidden_dim=16, num_layers=1, num_heads=2)
+    rs = np.random.RandomState(3)
+    out = {}
+    for n, T in enumerate([1, 2, 7, 16, 33]):
+        fm = torch.from_numpy((rs.uniform(size=T) < 0.4).astype(np.float32))
+        out[f"mask{n}"] = fm.numpy()
+        for typ in ["triangle", "repeat", "repeat-inc", "all"]:
+            if T == 1 and typ in ("repeat", "repeat-inc"):
+                continue            # reference squeeze() collapses [1,1] to a scalar
+            out[f"{typ}{n}"] = m.get_mask(fm, T, typ).numpy()
+    np.savez_compressed(os.path.join(HERE, "get_mask.npz"), **out)
+
+
+def normalize_case():
+    rs = np.random.RandomState(5)
+    out = {}
+    body = {"pose_left_shoulder": 5, "pose_right_shoulder": 6, "pose_right_eye": 2}
+    for n, (T, K) in enumerate([(9, 12), (24, 54), (40, 71)]):
+        d = rs.uniform(0.05, 0.95, size=(T, K, 2)).astype(np.float32)
+        d[rs.uniform(size=(T, K)) < 0.08] = 0.0
+        # shoulders missing at the start (frames stay untouched), later (box carried forward)
+        d[0, 5, 0] = 0.0
+        d[1, 6] = 0.0
+        d[T // 2, 5] = 0.0
+        d[T // 2 + 1, 6, 0] = 0.0
+        out[f"in{n}"] = d.copy()
+        out[f"out{n}"] = ref_dl.normalize_pose(d.copy(), body)
+    out["ids"] = np.array([5, 6, 2])
+    np.savez_compressed(os.path.join(HERE, "normalize_pose.npz"), **out)
+
+
+class _Tape:
+    """Records what the reference draws from ``random`` so tests can replay the parameters."""
+    def __init__(self, seed):
+        self.r = random.Random(seed)
+        self.uniform_draws, self.random_draws = [], []
+
+    def uniform(self, a, b):
+        v = self.r.uniform(a, b)
+        self.uniform_draws.append(v)
+        return v
+
+    def random(self):
+        v = self.r.random()
+        self.random_draws.append(v)
+        return v
+
+
+def augment_case():
+    K, T = 54, 10
+    pose = list(range(0, 12))
+    lh = list(range(12, 33))
+    rh = list(range(33, 54))
+    ids = {"pose": pose, "left_hand": lh, "rigth_hand": rh}
+    body = {"pose_chest_middle_up": 0, "pose_left_shoulder": 5, "pose_left_elbow": 7, "pose_left_wrist": 9,
+            "pose_right_shoulder": 6, "pose_right_elbow": 8, "pose_right_wrist": 10}
+    aug = ref_aug.augmentation(ids, body)
+    rs = np.random.RandomState(11)
+    base = rs.uniform(0.05, 0.95, size=(T, K, 2)).astype(np.float32)
+    base[rs.uniform(size=(T, K)) < 0.1] = 0.0
+    out = {"base": base, "pose": np.array(pose), "left_hand": np.array(lh), "right_hand": np.array(rh),
+           "arm_chains": np.array(aug.ARM_IDENTIFIERS_ORDER)}
+    real_uniform, real_random = ref_aug.random.uniform, ref_aug.random.random
+    try:
+        for n in range(3):
+            tape = _Tape(100 + n)
+            ref_aug.random.uniform, ref_aug.random.random = tape.uniform, tape.random
+            out[f"rotate{n}"] = aug.augment_rotate(torch.from_numpy(base.copy()), (-15, 15)).numpy()
+            out[f"rotate{n}_u"] = np.array(tape.uniform_draws)
+            tape = _Tape(200 + n)
+            ref_aug.random.uniform, ref_aug.random.random = tape.uniform, tape.random
+            out[f"squeeze{n}"] = aug.augment_shear(torch.from_numpy(base.copy()), "squeeze", (-0.15, 0.15)).numpy()
+            out[f"squeeze{n}_u"] = np.array(tape.uniform_draws)
+            tape = _Tape(300 + n)
+            ref_aug.random.uniform, ref_aug.random.random = tape.uniform, tape.random
+            out[f"persp{n}"] = aug.augment_shear(torch.from_numpy(base.copy()), "perspective", (-0.15, 0.15)).numpy()
+            out[f"persp{n}_u"] = np.array(tape.uniform_draws)
+            out[f"persp{n}_r"] = np.array(tape.random_draws)
+            tape = _Tape(400 + n)
+            ref_aug.random.uniform, ref_aug.random.random = tape.uniform, tape.random
+            out[f"arm{n}"] = aug.augment_arm_joint_rotate(torch.from_numpy(base.copy()), 0.5, (-15, 15)).numpy()
+            out[f"arm{n}_u"] = np.array(tape.uniform_draws)
+            out[f"arm{n}_r"] = np.array(tape.random_draws)
+    finally:
+        ref_aug.random.uniform, ref_aug.random.random = real_uniform, real_random
+    np.savez_compressed(os.path.join(HERE, "augmentation.npz"), **out)
+
+
+def missing_case():
+    cwd = os.getcwd()
+    os.chdir(REF)                      # put_missing_frames opens ./dataset_config.json
+    out = {}
+    try:
+        n = 0
+        for T in (20, 64, 131):
+            for ds in ("AUTSL", "AEC", "PUCP_PSL_DGI305"):
+                seed = 1000 + n
+                random.seed(seed)
+                np.random.seed(seed)
+                video = torch.arange(T, dtype=torch.float32).view(T, 1, 1).repeat(1, 3, 2).clone()
+                v2, mask = ref_dl.put_missing_frames(video, False, ds)
+                v3, m3 = ref_dl.add_sos(v2, mask)
+                out[f"src{n}"] = v2[:, 0, 0].numpy().astype(np.int32)
+                out[f"mask{n}"] = mask.numpy()
+                out[f"sos_video{n}"] = v3.numpy()
+                out[f"sos_mask{n}"] = m3.numpy()
+                out[f"meta{n}"] = np.array([T, seed])
+                out[f"ds{n}"] = np.array(ds)
+                n += 1
+        # random-missing mode
+        random.seed(77)
+        video = (1 + torch.arange(30, dtype=torch.float32)).view(30, 1, 1).repeat(1, 2, 2).clone()
+        v2, mask = ref_dl.put_missing_frames(video, True, "AUTSL")
+        out["rand_video"] = v2.numpy()
+        out["rand_mask"] = mask.numpy()
+        out["count"] = np.array(n)
+    finally:
+        os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "missing_frames.npz"), **out)
+
+
+def loss_case():
+    rs = np.random.RandomState(9)
+    o = torch.from_numpy(rs.normal(size=(3, 17, 71, 2)).astype(np.float32))
+    t = torch.from_numpy(rs.normal(size=(3, 17, 71, 2)).astype(np.float32))
+    out = {"o": o.numpy(), "t": t.numpy(),
+           "euclid": ref_loss.EuclideanLoss()(o, t).numpy(),
+           "mse": torch.nn.MSELoss()(o, t).numpy(),
+           "euclid_dist": ref_loss.EuclideanDistanceLoss()(o[0], t[0]).numpy()}
+    np.savez_compressed(os.path.join(HERE, "loss.npz"), **out)
+
+
+if __name__ == "__main__":
+    get_mask_case()
+    normalize_case()
+    augment_case()
+    missing_case()
+    loss_case()
+    small_full = ["learned_input_positional_encoder", "input_embedding.bias", "fc_final.weight", "fc_final.bias",
+                  "transformer.encoder.layers.0.self_attn.in_proj_bias",
+                  "transformer.decoder.layers.1.multihead_attn.out_proj.weight",
+                  "transformer.decoder.layers.0.norm2.weight", "swiGlu_decoded.fc2.bias",
+                  "filled_embedding.weight", "transformer.encoder.layers.1.linear1.bias"]
+    completer_case("completer_small_k54", K=54, H=64, L=2, NH=4, T=12, B=3, seed=42, grads_full=small_full)
+    completer_case("completer_small_k71", K=71, H=64, L=2, NH=4, T=12, B=3, seed=43, grads_full=small_full)
+    completer_case("completer_default_k54", K=54, H=256, L=6, NH=8, T=16, B=2, seed=44,
+                   grads_full=["fc_final.bias", "learned_filled_positional_encoder",
+                               "transformer.encoder.layers.0.norm1.weight",
+                               "transformer.decoder.layers.5.self_attn.in_proj_bias"])
+    print("done")
