@@ -1,0 +1,742 @@
+// The KeypointCompleter step engine: parameter-arena layout, activation workspace, and the
+// forward (model.py:100-170) / backward call sequences over the kernels of this library.
+// Everything is enqueued on the caller's stream; no allocation, no synchronisation.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "attention.cuh"
+#include "gemm_sm100.cuh"
+#include "rowops.cuh"
+
+namespace kit {
+
+struct LinearW {
+  int64_t w = -1, b = -1;  // fp32 arena offsets (floats)
+  int rows = 0, cols = 0;  // W is [rows, cols] (out_features, in_features)
+  int64_t wb = -1, wbT = -1;  // bf16 arena offsets (elements); wbT = W^T [cols, ldT]
+  int ld = 0, ldT = 0;
+  bool need_T = true;
+};
+struct LNW { int64_t g = -1, b = -1; };
+struct AttnW { LinearW in, out; };
+struct EncW { AttnW sa; LinearW l1, l2; LNW n1, n2; };
+struct DecW { AttnW sa, ca; LinearW l1, l2; LNW n1, n2, n3; };
+struct SwiW { LinearW fc12, fc3; };
+
+struct Entry {
+  std::string name;
+  int64_t offset, numel, rows, cols;
+  int is_buffer;
+};
+
+struct Layout {
+  KitModelConfig cfg;
+  std::vector<Entry> entries;
+  int64_t trainable = 0, total = 0;
+  int64_t wb_elems = 0;
+  std::vector<std::pair<int64_t, int64_t>> buckets;  // in backward completion order
+  int64_t learned_i, learned_f, pe_i, pe_f;
+  LinearW emb_i, emb_f, fc_final;
+  SwiW swi_i, swi_f, swi_d;
+  std::vector<EncW> enc;
+  std::vector<DecW> dec;
+  LNW enc_norm, dec_norm;
+  std::vector<WeightDesc> wdescs;
+};
+
+static int64_t up8(int64_t x) { return round_up(x, 8); }
+
+struct LayoutBuilder {
+  Layout& L;
+  int64_t cur = 0, wcur = 0;
+  explicit LayoutBuilder(Layout& l) : L(l) {}
+  int64_t add(const std::string& name, int64_t rows, int64_t cols, int is_buffer = 0) {
+    const int64_t off = cur;
+    L.entries.push_back({name, off, rows * cols, rows, cols, is_buffer});
+    cur = up8(cur + rows * cols);
+    return off;
+  }
+  void add_wb(LinearW& w) {
+    w.ld = (int)up8(w.cols);
+    w.wb = wcur;
+    wcur = round_up(wcur + (int64_t)w.rows * w.ld, 64);
+    if (w.need_T) {
+      w.ldT = (int)up8(w.rows);
+      w.wbT = wcur;
+      wcur = round_up(wcur + (int64_t)w.cols * w.ldT, 64);
+    }
+    WeightDesc d;
+    d.src_off = w.w; d.rows = w.rows; d.cols = w.cols;
+    d.dst_off = w.wb; d.dst_ld = w.ld; d.rows_pad = w.rows; d.cols_pad = w.ld;
+    d.dstT_off = w.wbT; d.dstT_ld = w.ldT;
+    L.wdescs.push_back(d);
+  }
+  // weight and bias registered under the reference's names
+  void linear(LinearW& w, const std::string& prefix, int rows, int cols, bool need_T = true) {
+    w.rows = rows; w.cols = cols; w.need_T = need_T;
+    w.w = add(prefix + ".weight", rows, cols);
+  }
+  void linear_bias(LinearW& w, const std::string& prefix) { w.b = add(prefix + ".bias", 1, w.rows); }
+  void ln(LNW& n, const std::string& prefix, int H) {
+    n.g = add(prefix + ".weight", 1, H);
+    n.b = add(prefix + ".bias", 1, H);
+  }
+  // SwiGLU: fc1 | fc2 stored back to back so they run as ONE [2H,H] GEMM
+  void swiglu(SwiW& s, const std::string& prefix, int H) {
+    s.fc12.rows = 2 * H; s.fc12.cols = H; s.fc12.need_T = true;
+    s.fc12.w = add(prefix + ".fc1.weight", H, H);
+    add(prefix + ".fc2.weight", H, H);
+    s.fc12.b = add(prefix + ".fc1.bias", 1, H);
+    add(prefix + ".fc2.bias", 1, H);
+    linear(s.fc3, prefix + ".fc3", H, H);
+    linear_bias(s.fc3, prefix + ".fc3");
+  }
+  void attn(AttnW& a, const std::string& prefix, int H) {
+    a.in.rows = 3 * H; a.in.cols = H;
+    a.in.w = add(prefix + ".in_proj_weight", 3 * H, H);
+    a.in.b = add(prefix + ".in_proj_bias", 1, 3 * H);
+    linear(a.out, prefix + ".out_proj", H, H);
+    linear_bias(a.out, prefix + ".out_proj");
+  }
+};
+
+static int build_layout(const KitModelConfig* c, Layout& L) {
+  KIT_REQUIRE(c != nullptr, "null model config");
+  KIT_REQUIRE(c->hidden > 0 && c->hidden % 64 == 0 && c->hidden <= 1024, "hidden %d unsupported (multiple of 64, <= 1024)", c->hidden);
+  KIT_REQUIRE(c->heads > 0 && c->hidden % c->heads == 0, "hidden %d not divisible by heads %d", c->hidden, c->heads);
+  const int d = c->hidden / c->heads;
+  KIT_REQUIRE(d == 16 || d == 32 || d == 64, "head dim %d unsupported (16, 32, 64)", d);
+  KIT_REQUIRE(c->input_size > 0 && c->input_size % 2 == 0, "input_size must be 2*K");
+  KIT_REQUIRE(c->layers > 0 && c->ff > 0 && c->ff % 8 == 0 && c->max_len > 0, "bad layers/ff/max_len");
+  L.cfg = *c;
+  const int H = c->hidden, IN = c->input_size, FF = c->ff;
+  LayoutBuilder lb(L);
+  // ---- group E: embeddings, learned PEs, the two pre-transformer SwiGLUs (last bucket of backward)
+  L.learned_i = lb.add("learned_input_positional_encoder", 1, H);
+  L.learned_f = lb.add("learned_filled_positional_encoder", 1, H);
+  lb.linear(L.emb_i, "input_embedding", H, IN, false);
+  lb.linear_bias(L.emb_i, "input_embedding");
+  lb.linear(L.emb_f, "filled_embedding", H, IN, false);
+  lb.linear_bias(L.emb_f, "filled_embedding");
+  lb.swiglu(L.swi_i, "swiGlu_input_prev", H);
+  lb.swiglu(L.swi_f, "swiGlu_filled_prev", H);
+  const int64_t end_group_e = lb.cur;
+  L.enc.resize(c->layers);
+  L.dec.resize(c->layers);
+  std::vector<int64_t> enc_begin(c->layers), dec_begin(c->layers);
+  for (int l = 0; l < c->layers; ++l) {
+    enc_begin[l] = lb.cur;
+    const std::string p = "transformer.encoder.layers." + std::to_string(l);
+    EncW& e = L.enc[l];
+    lb.attn(e.sa, p + ".self_attn", H);
+    lb.linear(e.l1, p + ".linear1", FF, H); lb.linear_bias(e.l1, p + ".linear1");
+    lb.linear(e.l2, p + ".linear2", H, FF); lb.linear_bias(e.l2, p + ".linear2");
+    lb.ln(e.n1, p + ".norm1", H);
+    lb.ln(e.n2, p + ".norm2", H);
+  }
+  lb.ln(L.enc_norm, "transformer.encoder.norm", H);
+  const int64_t end_enc = lb.cur;
+  for (int l = 0; l < c->layers; ++l) {
+    dec_begin[l] = lb.cur;
+    const std::string p = "transformer.decoder.layers." + std::to_string(l);
+    DecW& e = L.dec[l];
+    lb.attn(e.sa, p + ".self_attn", H);
+    lb.attn(e.ca, p + ".multihead_attn", H);
+    lb.linear(e.l1, p + ".linear1", FF, H); lb.linear_bias(e.l1, p + ".linear1");
+    lb.linear(e.l2, p + ".linear2", H, FF); lb.linear_bias(e.l2, p + ".linear2");
+    lb.ln(e.n1, p + ".norm1", H);
+    lb.ln(e.n2, p + ".norm2", H);
+    lb.ln(e.n3, p + ".norm3", H);
+  }
+  lb.ln(L.dec_norm, "transformer.decoder.norm", H);
+  lb.swiglu(L.swi_d, "swiGlu_decoded", H);
+  lb.linear(L.fc_final, "fc_final", IN, H);
+  lb.linear_bias(L.fc_final, "fc_final");
+  L.trainable = lb.cur;
+  L.pe_i = lb.add("trig_input_positional_encoder.pos_encoding", c->max_len, H, 1);
+  L.pe_f = lb.add("trig_filled_positional_encoder.pos_encoding", c->max_len, H, 1);
+  L.total = lb.cur;
+  (void)end_group_e;
+  // buckets in the order backward completes them
+  const int half = c->layers / 2;
+  L.buckets.clear();
+  if (half > 0) {
+    L.buckets.push_back({dec_begin[half], L.trainable});
+    L.buckets.push_back({dec_begin[0], dec_begin[half]});
+    L.buckets.push_back({enc_begin[half], end_enc});
+    L.buckets.push_back({0, enc_begin[half]});
+  } else {
+    L.buckets.push_back({dec_begin[0], L.trainable});
+    L.buckets.push_back({0, dec_begin[0]});
+  }
+  // bf16 GEMM operands
+  lb.add_wb(L.emb_i); lb.add_wb(L.emb_f);
+  lb.add_wb(L.swi_i.fc12); lb.add_wb(L.swi_i.fc3);
+  lb.add_wb(L.swi_f.fc12); lb.add_wb(L.swi_f.fc3);
+  for (int l = 0; l < c->layers; ++l) {
+    EncW& e = L.enc[l];
+    lb.add_wb(e.sa.in); lb.add_wb(e.sa.out); lb.add_wb(e.l1); lb.add_wb(e.l2);
+  }
+  for (int l = 0; l < c->layers; ++l) {
+    DecW& e = L.dec[l];
+    lb.add_wb(e.sa.in); lb.add_wb(e.sa.out); lb.add_wb(e.ca.in); lb.add_wb(e.ca.out); lb.add_wb(e.l1); lb.add_wb(e.l2);
+  }
+  lb.add_wb(L.swi_d.fc12); lb.add_wb(L.swi_d.fc3);
+  lb.add_wb(L.fc_final);
+  L.wb_elems = lb.wcur;
+  return KIT_OK;
+}
+
+// ---------------------------------------------------------------- engine
+struct Buf {
+  int64_t off;  // bytes into the workspace
+  int64_t elems;
+  int esize;
+  int64_t ld;
+};
+
+struct EncAct { bf16 *qkv, *ao, *s1, *x1, *z, *hh, *s2, *x2; float *lse, *st1, *st2; };
+struct DecAct { bf16 *qkv, *ao, *s1, *y1, *qc, *kvc, *aoc, *s2, *y2, *z, *hh, *s3, *y3; float *lse, *lsec, *st1, *st2, *st3; };
+
+}  // namespace kit
+
+using namespace kit;
+
+struct KitEngine {
+  Layout L;
+  int B = 0, T = 0;
+  int64_t M = 0;
+  int K2p = 0;
+  std::map<std::string, Buf> bufs;
+  int64_t ws_bytes = 0;
+  float* params = nullptr;
+  float* grads = nullptr;
+  uint8_t* ws = nullptr;
+  bool bound = false, weights_fresh = false;
+  std::vector<GemmPlan> fwd_plans, bwd_plans;
+  size_t cursor = 0;
+  std::vector<GemmPlan>* active = nullptr;
+  int64_t launches = 0;
+  cudaStream_t st = nullptr;
+  // saved masks (backward reuses the forward's)
+  KitAttnMask enc_mask{}, dec_mask{};
+  // resolved pointers
+  bf16* wb = nullptr;
+  WeightDesc* wdesc_dev = nullptr;
+  int* tile_prefix_dev = nullptr;
+  int total_tiles = 0;
+  bf16 *xe, *xd, *ei_raw, *ei, *si12, *sig, *x0, *ef_raw, *ef, *sf12, *sfg, *y0;
+  bf16 *mem, *dec_out, *sd12, *sdg, *sd, *zf, *sf, *dp;
+  float *st_encn, *st_decn;
+  std::vector<EncAct> ea;
+  std::vector<DecAct> da;
+  bf16 *g0, *g1, *g2, *g3, *gmem, *gff, *gqkv, *gkv, *g2h;
+
+  int64_t alloc(const std::string& name, int64_t elems, int esize, int64_t ld) {
+    Buf b{ws_bytes, elems, esize, ld};
+    bufs[name] = b;
+    ws_bytes = round_up(ws_bytes + elems * esize, 256);
+    return b.off;
+  }
+};
+
+namespace kit {
+
+template <typename T>
+static T* wsptr(KitEngine* e, const std::string& name) {
+  return reinterpret_cast<T*>(e->ws + e->bufs.at(name).off);
+}
+
+static void plan_workspace(KitEngine* e) {
+  const Layout& L = e->L;
+  const int64_t M = e->M;
+  const int H = L.cfg.hidden, FF = L.cfg.ff, NH = L.cfg.heads;
+  const int64_t lse_n = (int64_t)e->B * NH * e->T;
+  e->alloc("wb", L.wb_elems, 2, 0);
+  e->alloc("wdesc", (int64_t)L.wdescs.size() * sizeof(WeightDesc), 1, 0);
+  e->alloc("tile_prefix", (int64_t)L.wdescs.size() * 4 + 4, 1, 0);
+  e->alloc("xe", M * e->K2p, 2, e->K2p);
+  e->alloc("xd", M * e->K2p, 2, e->K2p);
+  for (const char* n : {"ei_raw", "ei", "sig", "x0", "ef_raw", "ef", "sfg", "y0", "mem", "dec_out", "sdg", "sd", "zf", "sf"})
+    e->alloc(n, M * H, 2, H);
+  for (const char* n : {"si12", "sf12", "sd12"}) e->alloc(n, M * 2 * H, 2, 2 * H);
+  e->alloc("dp", M * e->K2p, 2, e->K2p);
+  e->alloc("st_encn", 2 * M, 4, 0);
+  e->alloc("st_decn", 2 * M, 4, 0);
+  for (int l = 0; l < L.cfg.layers; ++l) {
+    const std::string p = "enc" + std::to_string(l) + ".";
+    e->alloc(p + "qkv", M * 3 * H, 2, 3 * H);
+    for (const char* n : {"ao", "s1", "x1", "s2", "x2"}) e->alloc(p + n, M * H, 2, H);
+    e->alloc(p + "z", M * FF, 2, FF);
+    e->alloc(p + "hh", M * FF, 2, FF);
+    e->alloc(p + "lse", lse_n, 4, 0);
+    e->alloc(p + "st1", 2 * M, 4, 0);
+    e->alloc(p + "st2", 2 * M, 4, 0);
+  }
+  for (int l = 0; l < L.cfg.layers; ++l) {
+    const std::string p = "dec" + std::to_string(l) + ".";
+    e->alloc(p + "qkv", M * 3 * H, 2, 3 * H);
+    e->alloc(p + "kvc", M * 2 * H, 2, 2 * H);
+    for (const char* n : {"ao", "s1", "y1", "qc", "aoc", "s2", "y2", "s3", "y3"}) e->alloc(p + n, M * H, 2, H);
+    e->alloc(p + "z", M * FF, 2, FF);
+    e->alloc(p + "hh", M * FF, 2, FF);
+    e->alloc(p + "lse", lse_n, 4, 0);
+    e->alloc(p + "lsec", lse_n, 4, 0);
+    for (const char* n : {"st1", "st2", "st3"}) e->alloc(p + n, 2 * M, 4, 0);
+  }
+  // backward scratch
+  for (const char* n : {"g0", "g1", "g2", "g3", "gmem"}) e->alloc(n, M * H, 2, H);
+  e->alloc("gff", M * FF, 2, FF);
+  e->alloc("gqkv", M * 3 * H, 2, 3 * H);
+  e->alloc("gkv", M * 2 * H, 2, 2 * H);
+  e->alloc("g2h", M * 2 * H, 2, 2 * H);
+}
+
+static void resolve_pointers(KitEngine* e) {
+  const Layout& L = e->L;
+  e->wb = wsptr<bf16>(e, "wb");
+  e->wdesc_dev = wsptr<WeightDesc>(e, "wdesc");
+  e->tile_prefix_dev = wsptr<int>(e, "tile_prefix");
+#define KIT_P(n) e->n = wsptr<bf16>(e, #n)
+  KIT_P(xe); KIT_P(xd); KIT_P(ei_raw); KIT_P(ei); KIT_P(si12); KIT_P(sig); KIT_P(x0); KIT_P(ef_raw); KIT_P(ef);
+  KIT_P(sf12); KIT_P(sfg); KIT_P(y0); KIT_P(mem); KIT_P(dec_out); KIT_P(sd12); KIT_P(sdg); KIT_P(sd); KIT_P(zf); KIT_P(sf);
+  KIT_P(dp); KIT_P(g0); KIT_P(g1); KIT_P(g2); KIT_P(g3); KIT_P(gmem); KIT_P(gff); KIT_P(gqkv); KIT_P(gkv); KIT_P(g2h);
+#undef KIT_P
+  e->st_encn = wsptr<float>(e, "st_encn");
+  e->st_decn = wsptr<float>(e, "st_decn");
+  e->ea.resize(L.cfg.layers);
+  e->da.resize(L.cfg.layers);
+  for (int l = 0; l < L.cfg.layers; ++l) {
+    const std::string p = "enc" + std::to_string(l) + ".";
+    EncAct& a = e->ea[l];
+    a.qkv = wsptr<bf16>(e, p + "qkv"); a.ao = wsptr<bf16>(e, p + "ao"); a.s1 = wsptr<bf16>(e, p + "s1");
+    a.x1 = wsptr<bf16>(e, p + "x1"); a.z = wsptr<bf16>(e, p + "z"); a.hh = wsptr<bf16>(e, p + "hh");
+    a.s2 = wsptr<bf16>(e, p + "s2"); a.x2 = wsptr<bf16>(e, p + "x2");
+    a.lse = wsptr<float>(e, p + "lse"); a.st1 = wsptr<float>(e, p + "st1"); a.st2 = wsptr<float>(e, p + "st2");
+    const std::string q = "dec" + std::to_string(l) + ".";
+    DecAct& d = e->da[l];
+    d.qkv = wsptr<bf16>(e, q + "qkv"); d.ao = wsptr<bf16>(e, q + "ao"); d.s1 = wsptr<bf16>(e, q + "s1");
+    d.y1 = wsptr<bf16>(e, q + "y1"); d.qc = wsptr<bf16>(e, q + "qc"); d.kvc = wsptr<bf16>(e, q + "kvc");
+    d.aoc = wsptr<bf16>(e, q + "aoc"); d.s2 = wsptr<bf16>(e, q + "s2"); d.y2 = wsptr<bf16>(e, q + "y2");
+    d.z = wsptr<bf16>(e, q + "z"); d.hh = wsptr<bf16>(e, q + "hh"); d.s3 = wsptr<bf16>(e, q + "s3");
+    d.y3 = wsptr<bf16>(e, q + "y3");
+    d.lse = wsptr<float>(e, q + "lse"); d.lsec = wsptr<float>(e, q + "lsec");
+    d.st1 = wsptr<float>(e, q + "st1"); d.st2 = wsptr<float>(e, q + "st2"); d.st3 = wsptr<float>(e, q + "st3");
+  }
+}
+
+// GEMM through the per-engine plan cache (tensor maps are built once per call site).
+static int eg(KitEngine* e, int mode, const bf16* A, int64_t lda, const bf16* Bm, int64_t ldb, void* C, int64_t ldc, int M,
+              int N, int K, const float* bias, const bf16* addend, int64_t ld_add, int out_kind, int act, bf16* aux,
+              int64_t ld_aux) {
+  std::vector<GemmPlan>& plans = *e->active;
+  if (e->cursor >= plans.size()) {
+    GemmPlan p;
+    int rc = gemm_plan(&p, mode, A, lda, Bm, ldb, C, ldc, M, N, K, bias, addend, ld_add, out_kind, act, aux, ld_aux,
+                       mode == 1 ? 0 : 1);
+    if (rc) return rc;
+    plans.push_back(p);
+  }
+  GemmPlan& p = plans[e->cursor++];
+  p.p.C = C;  // the only pointer that may change between calls (pred / grads are caller memory)
+  e->launches++;
+  return gemm_launch(&p, e->st);
+}
+#define KIT_TRY(x)      \
+  do {                  \
+    int _rc = (x);      \
+    if (_rc) return _rc; \
+  } while (0)
+
+// y = x W^T + b (+ addend)
+static int linear_fwd(KitEngine* e, const bf16* x, int64_t ldx, const LinearW& w, int row0, int nrows, bf16* y, int64_t ldy,
+                      const bf16* addend, int64_t ld_add, int act = ACT_NONE, bf16* aux = nullptr, int64_t ld_aux = 0) {
+  return eg(e, 0, x, ldx, e->wb + w.wb + (int64_t)row0 * w.ld, w.ld, y, ldy, (int)e->M, nrows, w.cols,
+            e->params + w.b + row0, addend, ld_add, OUT_BF16, act, aux, ld_aux);
+}
+// dx = dy W[row0:row0+nrows, :] (+ addend)   (B operand = rows of W^T restricted to those columns)
+static int linear_dgrad(KitEngine* e, const bf16* dy, int64_t ld_dy, const LinearW& w, int row0, int nrows, bf16* dx,
+                        int64_t ld_dx, const bf16* addend, int64_t ld_add, int act = ACT_NONE, bf16* aux = nullptr,
+                        int64_t ld_aux = 0) {
+  return eg(e, 0, dy, ld_dy, e->wb + w.wbT + row0, w.ldT, dx, ld_dx, (int)e->M, w.cols, nrows, nullptr, addend, ld_add,
+            OUT_BF16, act, aux, ld_aux);
+}
+// dW[row0:row0+nrows, :] += dy^T x ; db[row0:...] += colsum(dy)
+static int linear_wgrad(KitEngine* e, const bf16* dy, int64_t ld_dy, const bf16* x, int64_t ldx, const LinearW& w, int row0,
+                        int nrows) {
+  KIT_TRY(eg(e, 1, dy, ld_dy, x, ldx, e->grads + w.w + (int64_t)row0 * w.cols, w.cols, nrows, w.cols, (int)e->M, nullptr,
+             nullptr, 0, OUT_F32_ATOMIC, ACT_NONE, nullptr, 0));
+  e->launches++;
+  return colsum(dy, ld_dy, e->grads + w.b + row0, e->M, (int)up8(nrows), e->st);
+}
+
+static int swiglu_fwd(KitEngine* e, const bf16* x, const SwiW& s, bf16* x12, bf16* g, bf16* out) {
+  const int H = e->L.cfg.hidden;
+  KIT_TRY(linear_fwd(e, x, H, s.fc12, 0, 2 * H, x12, 2 * H, nullptr, 0));
+  e->launches++;
+  KIT_TRY(swiglu_gate_fwd(x12, g, e->M, H, e->st));
+  return linear_fwd(e, g, H, s.fc3, 0, H, out, H, nullptr, 0);
+}
+// dout -> dx (into dx_out); uses g2h / a scratch [M,H]
+static int swiglu_bwd(KitEngine* e, const bf16* dout, const bf16* x, const SwiW& s, const bf16* x12, const bf16* g,
+                      bf16* scratch, bf16* dx_out) {
+  const int H = e->L.cfg.hidden;
+  KIT_TRY(linear_wgrad(e, dout, H, g, H, s.fc3, 0, H));
+  KIT_TRY(linear_dgrad(e, dout, H, s.fc3, 0, H, scratch, H, nullptr, 0));
+  e->launches++;
+  KIT_TRY(swiglu_gate_bwd(scratch, x12, e->g2h, e->M, H, e->st));
+  KIT_TRY(linear_wgrad(e, e->g2h, 2 * H, x, H, s.fc12, 0, 2 * H));
+  return linear_dgrad(e, e->g2h, 2 * H, s.fc12, 0, 2 * H, dx_out, H, nullptr, 0);
+}
+
+static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const float* x_dec, int64_t xds,
+                          const KitAttnMask* em, const KitAttnMask* dm, int zero_masked, float* pred) {
+  const Layout& L = e->L;
+  const int H = L.cfg.hidden, NH = L.cfg.heads, d = H / NH, IN = L.cfg.input_size, FF = L.cfg.ff;
+  const int B = e->B, T = e->T;
+  const int64_t M = e->M;
+  e->active = &e->fwd_plans;
+  e->cursor = 0;
+  e->launches = 0;
+  e->enc_mask = em ? *em : KitAttnMask{};
+  e->dec_mask = dm ? *dm : KitAttnMask{};
+  const float* zm = (zero_masked && em) ? em->frame_mask : nullptr;
+  KIT_REQUIRE(!zero_masked || zm != nullptr, "zero_masked_enc needs enc_mask.frame_mask");
+  e->launches += 2;
+  KIT_TRY(pack_frames(x_enc, xes, B, T, IN, zm, em ? em->frame_mask_stride : 0, e->xe, e->K2p, e->st));
+  KIT_TRY(pack_frames(x_dec, xds, B, T, IN, nullptr, 0, e->xd, e->K2p, e->st));
+  // model.py:120-137 (embedding, token norm, PE, SwiGLU) for both branches
+  KIT_TRY(eg(e, 0, e->xe, e->K2p, e->wb + L.emb_i.wb, L.emb_i.ld, e->ei_raw, H, (int)M, H, e->K2p, e->params + L.emb_i.b,
+             nullptr, 0, OUT_BF16, ACT_NONE, nullptr, 0));
+  KIT_TRY(eg(e, 0, e->xd, e->K2p, e->wb + L.emb_f.wb, L.emb_f.ld, e->ef_raw, H, (int)M, H, e->K2p, e->params + L.emb_f.b,
+             nullptr, 0, OUT_BF16, ACT_NONE, nullptr, 0));
+  e->launches += 2;
+  KIT_TRY(embed_post_fwd(e->ei_raw, e->params + L.pe_i, e->params + L.learned_i, e->ei, M, H, T, e->st));
+  KIT_TRY(embed_post_fwd(e->ef_raw, e->params + L.pe_f, e->params + L.learned_f, e->ef, M, H, T, e->st));
+  KIT_TRY(swiglu_fwd(e, e->ei, L.swi_i, e->si12, e->sig, e->x0));
+  KIT_TRY(swiglu_fwd(e, e->ef, L.swi_f, e->sf12, e->sfg, e->y0));
+  // encoder (torch/nn/modules/transformer.py:956 post-norm layers + final norm :137)
+  const bf16* x = e->x0;
+  for (int l = 0; l < L.cfg.layers; ++l) {
+    const EncW& w = L.enc[l];
+    EncAct& a = e->ea[l];
+    KIT_TRY(linear_fwd(e, x, H, w.sa.in, 0, 3 * H, a.qkv, 3 * H, nullptr, 0));
+    e->launches++;
+    KIT_TRY(attention_fwd(a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, a.lse, B, NH, T, T, d, &e->enc_mask, e->st));
+    KIT_TRY(linear_fwd(e, a.ao, H, w.sa.out, 0, H, a.s1, H, x, H));
+    e->launches++;
+    KIT_TRY(add_ln_fwd(a.s1, nullptr, e->params + w.n1.g, e->params + w.n1.b, nullptr, a.x1, a.st1, a.st1 + M, M, H, e->st));
+    KIT_TRY(linear_fwd(e, a.x1, H, w.l1, 0, FF, a.hh, FF, nullptr, 0, ACT_GELU, a.z, FF));
+    KIT_TRY(linear_fwd(e, a.hh, FF, w.l2, 0, H, a.s2, H, a.x1, H));
+    e->launches++;
+    KIT_TRY(add_ln_fwd(a.s2, nullptr, e->params + w.n2.g, e->params + w.n2.b, nullptr, a.x2, a.st2, a.st2 + M, M, H, e->st));
+    x = a.x2;
+  }
+  e->launches++;
+  KIT_TRY(add_ln_fwd(x, nullptr, e->params + L.enc_norm.g, e->params + L.enc_norm.b, nullptr, e->mem, e->st_encn,
+                     e->st_encn + M, M, H, e->st));
+  // decoder (transformer.py:1147-1153 + final norm :163); cross-attention is unmasked
+  const bf16* y = e->y0;
+  for (int l = 0; l < L.cfg.layers; ++l) {
+    const DecW& w = L.dec[l];
+    DecAct& a = e->da[l];
+    KIT_TRY(linear_fwd(e, y, H, w.sa.in, 0, 3 * H, a.qkv, 3 * H, nullptr, 0));
+    e->launches++;
+    KIT_TRY(attention_fwd(a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, a.lse, B, NH, T, T, d, &e->dec_mask, e->st));
+    KIT_TRY(linear_fwd(e, a.ao, H, w.sa.out, 0, H, a.s1, H, y, H));
+    e->launches++;
+    KIT_TRY(add_ln_fwd(a.s1, nullptr, e->params + w.n1.g, e->params + w.n1.b, nullptr, a.y1, a.st1, a.st1 + M, M, H, e->st));
+    KIT_TRY(linear_fwd(e, a.y1, H, w.ca.in, 0, H, a.qc, H, nullptr, 0));
+    KIT_TRY(linear_fwd(e, e->mem, H, w.ca.in, H, 2 * H, a.kvc, 2 * H, nullptr, 0));
+    e->launches++;
+    KIT_TRY(attention_fwd(a.qc, H, a.kvc, 2 * H, a.kvc + H, 2 * H, a.aoc, H, a.lsec, B, NH, T, T, d, nullptr, e->st));
+    KIT_TRY(linear_fwd(e, a.aoc, H, w.ca.out, 0, H, a.s2, H, a.y1, H));
+    e->launches++;
+    KIT_TRY(add_ln_fwd(a.s2, nullptr, e->params + w.n2.g, e->params + w.n2.b, nullptr, a.y2, a.st2, a.st2 + M, M, H, e->st));
+    KIT_TRY(linear_fwd(e, a.y2, H, w.l1, 0, FF, a.hh, FF, nullptr, 0, ACT_GELU, a.z, FF));
+    KIT_TRY(linear_fwd(e, a.hh, FF, w.l2, 0, H, a.s3, H, a.y2, H));
+    e->launches++;
+    KIT_TRY(add_ln_fwd(a.s3, nullptr, e->params + w.n3.g, e->params + w.n3.b, nullptr, a.y3, a.st3, a.st3 + M, M, H, e->st));
+    y = a.y3;
+  }
+  e->launches++;
+  KIT_TRY(add_ln_fwd(y, nullptr, e->params + L.dec_norm.g, e->params + L.dec_norm.b, nullptr, e->dec_out, e->st_decn,
+                     e->st_decn + M, M, H, e->st));
+  // model.py:147-155 output head
+  KIT_TRY(swiglu_fwd(e, e->dec_out, L.swi_d, e->sd12, e->sdg, e->sd));
+  e->launches++;
+  KIT_TRY(final_norm_silu_fwd(e->sd, e->ef_raw, e->zf, e->sf, M, H, e->st));
+  KIT_TRY(eg(e, 0, e->sf, H, e->wb + L.fc_final.wb, L.fc_final.ld, pred, IN, (int)M, IN, H, e->params + L.fc_final.b, nullptr,
+             0, OUT_F32, ACT_NONE, nullptr, 0));
+  return KIT_OK;
+}
+
+static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback cb, void* user) {
+  const Layout& L = e->L;
+  const int H = L.cfg.hidden, NH = L.cfg.heads, d = H / NH, IN = L.cfg.input_size, FF = L.cfg.ff;
+  const int B = e->B, T = e->T;
+  const int64_t M = e->M;
+  const int nl = L.cfg.layers, half = nl / 2;
+  e->active = &e->bwd_plans;
+  e->cursor = 0;
+  e->launches = 0;
+  int bucket = 0;
+  auto done = [&]() {
+    if (cb) cb(bucket, user);
+    ++bucket;
+  };
+  // ---- output head
+  e->launches++;
+  KIT_TRY(cast_pad(dpred, M, IN, IN, e->dp, e->K2p, e->st));
+  KIT_TRY(linear_wgrad(e, e->dp, e->K2p, e->sf, H, L.fc_final, 0, IN));
+  KIT_TRY(eg(e, 0, e->dp, e->K2p, e->wb + L.fc_final.wbT, L.fc_final.ldT, e->g0, H, (int)M, H, e->K2p, nullptr, nullptr, 0,
+             OUT_BF16, ACT_NONE, nullptr, 0));
+  e->launches++;
+  KIT_TRY(final_norm_silu_bwd(e->g0, e->zf, e->g3, M, H, e->st));  // g3 = d(zf): kept for the embedding residual
+  KIT_TRY(swiglu_bwd(e, e->g3, e->dec_out, L.swi_d, e->sd12, e->sdg, e->g0, e->g1));  // g1 = d dec_out
+  e->launches++;
+  KIT_TRY(ln_bwd(e->g1, e->da[nl - 1].y3, e->st_decn, e->st_decn + M, e->params + L.dec_norm.g, nullptr, e->g0,
+                 e->grads + L.dec_norm.g, e->grads + L.dec_norm.b, M, H, e->st));
+  bf16* dy = e->g0;  // gradient w.r.t. the current layer's output
+  bool mem_grad_started = false;
+  for (int l = nl - 1; l >= 0; --l) {
+    const DecW& w = L.dec[l];
+    DecAct& a = e->da[l];
+    const bf16* y_in = (l == 0) ? e->y0 : e->da[l - 1].y3;
+    // FFN block
+    e->launches++;
+    KIT_TRY(ln_bwd(dy, a.s3, a.st3, a.st3 + M, e->params + w.n3.g, nullptr, e->g1, e->grads + w.n3.g, e->grads + w.n3.b, M, H, e->st));
+    KIT_TRY(linear_wgrad(e, e->g1, H, a.hh, FF, w.l2, 0, H));
+    KIT_TRY(linear_dgrad(e, e->g1, H, w.l2, 0, H, e->gff, FF, nullptr, 0, ACT_GELU_BWD, a.z, FF));
+    KIT_TRY(linear_wgrad(e, e->gff, FF, a.y2, H, w.l1, 0, FF));
+    KIT_TRY(linear_dgrad(e, e->gff, FF, w.l1, 0, FF, e->g2, H, e->g1, H));  // g2 = d y2
+    // cross-attention block
+    e->launches++;
+    KIT_TRY(ln_bwd(e->g2, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1, e->grads + w.n2.g, e->grads + w.n2.b, M, H, e->st));
+    KIT_TRY(linear_wgrad(e, e->g1, H, a.aoc, H, w.ca.out, 0, H));
+    KIT_TRY(linear_dgrad(e, e->g1, H, w.ca.out, 0, H, e->g2, H, nullptr, 0));  // g2 = d aoc
+    e->launches += 2;
+    KIT_TRY(attention_bwd(a.qc, H, a.kvc, 2 * H, a.kvc + H, 2 * H, a.aoc, H, e->g2, H, a.lsec, e->gqkv, H, e->gkv, 2 * H,
+                          e->gkv + H, 2 * H, B, NH, T, T, d, nullptr, e->st));  // gqkv used as [M,H] dq
+    KIT_TRY(linear_wgrad(e, e->gqkv, H, a.y1, H, w.ca.in, 0, H));
+    KIT_TRY(linear_wgrad(e, e->gkv, 2 * H, e->mem, H, w.ca.in, H, 2 * H));
+    KIT_TRY(linear_dgrad(e, e->gkv, 2 * H, w.ca.in, H, 2 * H, e->gmem, H, mem_grad_started ? e->gmem : nullptr, H));
+    mem_grad_started = true;
+    KIT_TRY(linear_dgrad(e, e->gqkv, H, w.ca.in, 0, H, e->g2, H, e->g1, H));  // g2 = d y1
+    // self-attention block
+    e->launches++;
+    KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1, e->grads + w.n1.g, e->grads + w.n1.b, M, H, e->st));
+    KIT_TRY(linear_wgrad(e, e->g1, H, a.ao, H, w.sa.out, 0, H));
+    KIT_TRY(linear_dgrad(e, e->g1, H, w.sa.out, 0, H, e->g2, H, nullptr, 0));  // g2 = d ao
+    e->launches += 2;
+    KIT_TRY(attention_bwd(a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, e->g2, H, a.lse, e->gqkv, 3 * H,
+                          e->gqkv + H, 3 * H, e->gqkv + 2 * H, 3 * H, B, NH, T, T, d, &e->dec_mask, e->st));
+    KIT_TRY(linear_wgrad(e, e->gqkv, 3 * H, y_in, H, w.sa.in, 0, 3 * H));
+    KIT_TRY(linear_dgrad(e, e->gqkv, 3 * H, w.sa.in, 0, 3 * H, e->g0, H, e->g1, H));  // g0 = d y_in
+    dy = e->g0;
+    if (half > 0 && l == half) done();
+  }
+  done();  // decoder finished (bucket 1, or bucket 0 for a 1-layer model)
+  // filled branch: SwiGLU, token-norm/PE, embedding  (g3 = residual gradient from the head)
+  KIT_TRY(swiglu_bwd(e, dy, e->ef, L.swi_f, e->sf12, e->sfg, e->g1, e->g2));  // g2 = d ef
+  e->launches++;
+  KIT_TRY(embed_post_bwd(e->g2, e->ef_raw, e->g3, e->g1, e->grads + L.learned_f, M, H, e->st));  // g1 = d ef_raw
+  KIT_TRY(eg(e, 1, e->g1, H, e->xd, e->K2p, e->grads + L.emb_f.w, IN, H, IN, (int)M, nullptr, nullptr, 0, OUT_F32_ATOMIC,
+             ACT_NONE, nullptr, 0));
+  e->launches++;
+  KIT_TRY(colsum(e->g1, H, e->grads + L.emb_f.b, M, H, e->st));
+  // ---- encoder
+  e->launches++;
+  KIT_TRY(ln_bwd(e->gmem, e->ea[nl - 1].x2, e->st_encn, e->st_encn + M, e->params + L.enc_norm.g, nullptr, e->g0,
+                 e->grads + L.enc_norm.g, e->grads + L.enc_norm.b, M, H, e->st));
+  bf16* dx = e->g0;
+  for (int l = nl - 1; l >= 0; --l) {
+    const EncW& w = L.enc[l];
+    EncAct& a = e->ea[l];
+    const bf16* x_in = (l == 0) ? e->x0 : e->ea[l - 1].x2;
+    e->launches++;
+    KIT_TRY(ln_bwd(dx, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1, e->grads + w.n2.g, e->grads + w.n2.b, M, H, e->st));
+    KIT_TRY(linear_wgrad(e, e->g1, H, a.hh, FF, w.l2, 0, H));
+    KIT_TRY(linear_dgrad(e, e->g1, H, w.l2, 0, H, e->gff, FF, nullptr, 0, ACT_GELU_BWD, a.z, FF));
+    KIT_TRY(linear_wgrad(e, e->gff, FF, a.x1, H, w.l1, 0, FF));
+    KIT_TRY(linear_dgrad(e, e->gff, FF, w.l1, 0, FF, e->g2, H, e->g1, H));  // g2 = d x1
+    e->launches++;
+    KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1, e->grads + w.n1.g, e->grads + w.n1.b, M, H, e->st));
+    KIT_TRY(linear_wgrad(e, e->g1, H, a.ao, H, w.sa.out, 0, H));
+    KIT_TRY(linear_dgrad(e, e->g1, H, w.sa.out, 0, H, e->g2, H, nullptr, 0));
+    e->launches += 2;
+    KIT_TRY(attention_bwd(a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, e->g2, H, a.lse, e->gqkv, 3 * H,
+                          e->gqkv + H, 3 * H, e->gqkv + 2 * H, 3 * H, B, NH, T, T, d, &e->enc_mask, e->st));
+    KIT_TRY(linear_wgrad(e, e->gqkv, 3 * H, x_in, H, w.sa.in, 0, 3 * H));
+    KIT_TRY(linear_dgrad(e, e->gqkv, 3 * H, w.sa.in, 0, 3 * H, e->g0, H, e->g1, H));
+    dx = e->g0;
+    if (half > 0 && l == half) done();
+  }
+  // input branch
+  KIT_TRY(swiglu_bwd(e, dx, e->ei, L.swi_i, e->si12, e->sig, e->g1, e->g2));
+  e->launches++;
+  KIT_TRY(embed_post_bwd(e->g2, e->ei_raw, nullptr, e->g1, e->grads + L.learned_i, M, H, e->st));
+  KIT_TRY(eg(e, 1, e->g1, H, e->xe, e->K2p, e->grads + L.emb_i.w, IN, H, IN, (int)M, nullptr, nullptr, 0, OUT_F32_ATOMIC,
+             ACT_NONE, nullptr, 0));
+  e->launches++;
+  KIT_TRY(colsum(e->g1, H, e->grads + L.emb_i.b, M, H, e->st));
+  done();
+  return KIT_OK;
+}
+
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __bfloat162float(src[i]);
+}
+
+}  // namespace kit
+
+// ---------------------------------------------------------------- C ABI
+extern "C" int32_t kit_layout_num_entries(const KitModelConfig* cfg) {
+  Layout L;
+  if (build_layout(cfg, L)) return -1;
+  return (int32_t)L.entries.size();
+}
+extern "C" int kit_layout_entry(const KitModelConfig* cfg, int32_t index, char* name, int32_t name_cap, int64_t* offset,
+                                int64_t* numel, int64_t* rows, int64_t* cols, int32_t* is_buffer) {
+  Layout L;
+  KIT_TRY(build_layout(cfg, L));
+  KIT_REQUIRE(index >= 0 && index < (int)L.entries.size(), "layout entry %d out of range", index);
+  const Entry& en = L.entries[index];
+  if (name != nullptr && name_cap > 0) snprintf(name, name_cap, "%s", en.name.c_str());
+  if (offset) *offset = en.offset;
+  if (numel) *numel = en.numel;
+  if (rows) *rows = en.rows;
+  if (cols) *cols = en.cols;
+  if (is_buffer) *is_buffer = en.is_buffer;
+  return KIT_OK;
+}
+extern "C" int64_t kit_layout_trainable_floats(const KitModelConfig* cfg) {
+  Layout L;
+  if (build_layout(cfg, L)) return -1;
+  return L.trainable;
+}
+extern "C" int64_t kit_layout_total_floats(const KitModelConfig* cfg) {
+  Layout L;
+  if (build_layout(cfg, L)) return -1;
+  return L.total;
+}
+extern "C" int32_t kit_layout_num_buckets(const KitModelConfig* cfg) {
+  Layout L;
+  if (build_layout(cfg, L)) return -1;
+  return (int32_t)L.buckets.size();
+}
+extern "C" int kit_layout_bucket(const KitModelConfig* cfg, int32_t bucket, int64_t* begin, int64_t* end) {
+  Layout L;
+  KIT_TRY(build_layout(cfg, L));
+  KIT_REQUIRE(bucket >= 0 && bucket < (int)L.buckets.size(), "bucket %d out of range", bucket);
+  *begin = L.buckets[bucket].first;
+  *end = L.buckets[bucket].second;
+  return KIT_OK;
+}
+
+extern "C" int kit_engine_create(const KitModelConfig* cfg, int32_t batch, int32_t seq_len, KitEngine** out) {
+  KIT_REQUIRE(out != nullptr, "kit_engine_create: out is null");
+  KIT_REQUIRE(batch > 0 && seq_len > 0, "kit_engine_create: batch and seq_len must be positive");
+  KitEngine* e = new KitEngine();
+  int rc = build_layout(cfg, e->L);
+  if (rc) {
+    delete e;
+    return rc;
+  }
+  if (seq_len > cfg->max_len) {
+    delete e;
+    set_error("seq_len %d exceeds the positional table (%d rows, model.py:74-75)", seq_len, cfg->max_len);
+    return KIT_ERR_INVALID;
+  }
+  e->B = batch;
+  e->T = seq_len;
+  e->M = (int64_t)batch * seq_len;
+  e->K2p = (int)up8(cfg->input_size);
+  plan_workspace(e);
+  *out = e;
+  return KIT_OK;
+}
+extern "C" int kit_engine_destroy(KitEngine* e) {
+  delete e;
+  return KIT_OK;
+}
+extern "C" int64_t kit_engine_workspace_bytes(const KitEngine* e) { return e ? e->ws_bytes : -1; }
+
+extern "C" int kit_engine_bind(KitEngine* e, float* params, float* grads, void* workspace, int64_t workspace_bytes) {
+  KIT_REQUIRE(e && params && workspace, "kit_engine_bind: null argument");
+  KIT_REQUIRE(workspace_bytes >= e->ws_bytes, "workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)e->ws_bytes);
+  KIT_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)params & 31) == 0 && ((uintptr_t)grads & 31) == 0,
+              "kit_engine_bind: workspace must be 256-byte aligned, arenas 32-byte aligned");
+  e->params = params;
+  e->grads = grads;
+  e->ws = (uint8_t*)workspace;
+  resolve_pointers(e);
+  e->fwd_plans.clear();
+  e->bwd_plans.clear();
+  // upload the weight-refresh tables (synchronous, bind time only)
+  std::vector<int> prefix(e->L.wdescs.size() + 1, 0);
+  for (size_t i = 0; i < e->L.wdescs.size(); ++i) {
+    const WeightDesc& d = e->L.wdescs[i];
+    prefix[i + 1] = prefix[i] + ((d.rows + 31) / 32) * ((d.cols_pad + 31) / 32);
+  }
+  e->total_tiles = prefix.back();
+  KIT_CHECK_CUDA(cudaMemcpy(e->wdesc_dev, e->L.wdescs.data(), e->L.wdescs.size() * sizeof(WeightDesc), cudaMemcpyHostToDevice));
+  KIT_CHECK_CUDA(cudaMemcpy(e->tile_prefix_dev, prefix.data(), prefix.size() * sizeof(int), cudaMemcpyHostToDevice));
+  e->bound = true;
+  e->weights_fresh = false;
+  return KIT_OK;
+}
+
+extern "C" int kit_engine_refresh_weights(KitEngine* e, void* stream) {
+  KIT_REQUIRE(e && e->bound, "kit_engine_refresh_weights: engine not bound");
+  KIT_TRY(weight_refresh(e->params, e->wb, e->wdesc_dev, e->tile_prefix_dev, (int)e->L.wdescs.size(), e->total_tiles,
+                         (cudaStream_t)stream));
+  e->weights_fresh = true;
+  return KIT_OK;
+}
+
+extern "C" int kit_engine_forward(KitEngine* e, const float* x_enc, int64_t x_enc_batch_stride, const float* x_dec,
+                                  int64_t x_dec_batch_stride, const KitAttnMask* enc_mask, const KitAttnMask* dec_mask,
+                                  int32_t zero_masked_enc, float* pred, void* stream) {
+  KIT_REQUIRE(e && e->bound, "kit_engine_forward: engine not bound");
+  KIT_REQUIRE(e->weights_fresh, "kit_engine_forward: call kit_engine_refresh_weights after binding / updating parameters");
+  KIT_REQUIRE(x_enc && x_dec && pred, "kit_engine_forward: null tensor");
+  e->st = (cudaStream_t)stream;
+  return engine_forward(e, x_enc, x_enc_batch_stride, x_dec, x_dec_batch_stride, enc_mask, dec_mask, zero_masked_enc, pred);
+}
+
+extern "C" int kit_engine_backward(KitEngine* e, const float* dpred, KitBucketCallback bucket_done, void* user, void* stream) {
+  KIT_REQUIRE(e && e->bound && e->grads, "kit_engine_backward: engine not bound to a gradient arena");
+  KIT_REQUIRE(!e->fwd_plans.empty(), "kit_engine_backward: run kit_engine_forward first");
+  KIT_REQUIRE(dpred != nullptr, "kit_engine_backward: dpred is null");
+  e->st = (cudaStream_t)stream;
+  return engine_backward(e, dpred, bucket_done, user);
+}
+
+extern "C" int kit_engine_debug_read(KitEngine* e, const char* name, float* out, int64_t out_floats, void* stream) {
+  KIT_REQUIRE(e && e->bound && name && out, "kit_engine_debug_read: bad arguments");
+  auto it = e->bufs.find(name);
+  KIT_REQUIRE(it != e->bufs.end(), "kit_engine_debug_read: no buffer named '%s'", name);
+  const Buf& b = it->second;
+  KIT_REQUIRE(out_floats >= b.elems, "kit_engine_debug_read: output too small (%lld < %lld)", (long long)out_floats, (long long)b.elems);
+  if (b.esize == 4) {
+    KIT_CHECK_CUDA(cudaMemcpyAsync(out, e->ws + b.off, b.elems * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  } else {
+    KIT_REQUIRE(b.esize == 2, "kit_engine_debug_read: buffer '%s' is not a tensor", name);
+    bf16_to_f32_kernel<<<(unsigned)ceil_div(b.elems, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)(e->ws + b.off), out, b.elems);
+    KIT_LAUNCH_CHECK();
+  }
+  return KIT_OK;
+}
+extern "C" int64_t kit_engine_last_launches(const KitEngine* e) { return e ? e->launches : -1; }
+
+extern "C" int kit_gemm_bf16(int32_t mode, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                             int32_t M, int32_t N, int32_t K, const float* bias, const void* addend, int64_t ld_addend,
+                             int32_t out_kind, int32_t act, void* aux, int64_t ld_aux, int32_t split_k, void* stream) {
+  GemmPlan p;
+  KIT_TRY(gemm_plan(&p, mode, (const bf16*)A, lda, (const bf16*)B, ldb, C, ldc, M, N, K, bias, (const bf16*)addend, ld_addend,
+                    out_kind, act, (bf16*)aux, ld_aux, split_k));
+  return gemm_launch(&p, (cudaStream_t)stream);
+}

@@ -1,0 +1,121 @@
+// Host side of the tcgen05 GEMM: TMA descriptor construction, planning and launch.
+#include "gemm_sm100.cuh"
+
+#include <mutex>
+
+namespace kit {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+
+int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_pitch_bytes,
+                       uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  KIT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  KIT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base address must be 16-byte aligned");
+  KIT_REQUIRE((row_pitch_bytes & 15) == 0, "TMA row pitch must be a multiple of 16 bytes (got %llu)",
+              (unsigned long long)row_pitch_bytes);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KIT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return KIT_OK;
+}
+
+constexpr int TN_BN = 128, TN_STAGES = 3;
+constexpr int WG_BN = 128, WG_STAGES = 4;
+
+int gemm_init_attributes() {
+  static int status = 1;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    cudaError_t e1 = cudaFuncSetAttribute(gemm_tcgen05_kernel<TN_BN, 0, TN_STAGES>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          gemm_smem_bytes<TN_BN, TN_STAGES>());
+    cudaError_t e2 = cudaFuncSetAttribute(gemm_tcgen05_kernel<WG_BN, 1, WG_STAGES>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          gemm_smem_bytes<WG_BN, WG_STAGES>());
+    status = (e1 == cudaSuccess && e2 == cudaSuccess) ? 0 : -1;
+    if (status != 0) set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s / %s", cudaGetErrorString(e1),
+                               cudaGetErrorString(e2));
+  });
+  return status == 0 ? KIT_OK : KIT_ERR_CUDA;
+}
+
+int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, void* C, int64_t ldc,
+              int M, int N, int K, const float* bias, const bf16* addend, int64_t ld_addend, int out_kind, int act,
+              bf16* aux, int64_t ld_aux, int split_k) {
+  KIT_REQUIRE(mode == 0 || mode == 1, "gemm mode must be 0 (TN) or 1 (wgrad)");
+  KIT_REQUIRE(M > 0 && N > 0 && K > 0, "gemm dims must be positive (M=%d N=%d K=%d)", M, N, K);
+  KIT_REQUIRE(act == ACT_NONE || aux != nullptr, "gelu epilogues need the aux tensor");
+  GemmParams& p = plan->p;
+  p.M = M; p.N = N; p.K = K;
+  p.C = C; p.ldc = ldc;
+  p.bias = bias;
+  p.addend = addend; p.ld_addend = ld_addend;
+  p.aux = aux; p.ld_aux = ld_aux;
+  p.out_kind = out_kind; p.act = act;
+  plan->mode = mode;
+  const int kb_total = (K + GEMM_BK - 1) / GEMM_BK;
+  int rc;
+  if (mode == 0) {
+    // A [M,K] K-major: box 64(k) x 128(m);  B [N,K] K-major: box 64(k) x BN(n)
+    if ((rc = make_tensor_map_2d(&plan->tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, GEMM_BK, GEMM_BM))) return rc;
+    if ((rc = make_tensor_map_2d(&plan->tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, GEMM_BK, TN_BN))) return rc;
+    KIT_REQUIRE(split_k <= 1 || out_kind == OUT_F32_ATOMIC, "split-K needs the atomic fp32 epilogue");
+    int splits = split_k > 1 ? split_k : 1;
+    if (splits > kb_total) splits = kb_total;
+    p.kb_per_split = (kb_total + splits - 1) / splits;
+    splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    plan->grid = dim3((N + TN_BN - 1) / TN_BN, (M + GEMM_BM - 1) / GEMM_BM, splits);
+  } else {
+    // A [K,M] row-major (MN-major operand): box 64(m) x 64(k);  B [K,N]: box 64(n) x 64(k)
+    if ((rc = make_tensor_map_2d(&plan->tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, GEMM_BK))) return rc;
+    if ((rc = make_tensor_map_2d(&plan->tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, GEMM_BK))) return rc;
+    const int tiles = ((N + WG_BN - 1) / WG_BN) * ((M + GEMM_BM - 1) / GEMM_BM);
+    int splits = split_k;
+    if (splits <= 0) splits = (2 * 148 + tiles - 1) / tiles;
+    if (splits > kb_total) splits = kb_total;
+    if (splits < 1) splits = 1;
+    KIT_REQUIRE(splits == 1 || out_kind == OUT_F32_ATOMIC, "split-K needs the atomic fp32 epilogue");
+    p.kb_per_split = (kb_total + splits - 1) / splits;
+    splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    plan->grid = dim3((N + WG_BN - 1) / WG_BN, (M + GEMM_BM - 1) / GEMM_BM, splits);
+  }
+  return KIT_OK;
+}
+
+int gemm_launch(const GemmPlan* plan, cudaStream_t stream) {
+  int rc = gemm_init_attributes();
+  if (rc) return rc;
+  if (plan->mode == 0) {
+    gemm_tcgen05_kernel<TN_BN, 0, TN_STAGES>
+        <<<plan->grid, GEMM_THREADS, gemm_smem_bytes<TN_BN, TN_STAGES>(), stream>>>(plan->tmA, plan->tmB, plan->p);
+  } else {
+    gemm_tcgen05_kernel<WG_BN, 1, WG_STAGES>
+        <<<plan->grid, GEMM_THREADS, gemm_smem_bytes<WG_BN, WG_STAGES>(), stream>>>(plan->tmA, plan->tmB, plan->p);
+  }
+  KIT_LAUNCH_CHECK();
+  return KIT_OK;
+}
+
+}  // namespace kit

@@ -1,0 +1,602 @@
+// Bandwidth-bound per-token kernels over [M,H] bf16 activations: one warp owns one token row,
+// 16-byte vector loads/stores, warp-shuffle reductions for the per-row statistics, fp32 math.
+#include "rowops.cuh"
+
+namespace kit {
+
+constexpr int ROW_WARPS = 8;  // rows per 256-thread block
+
+// A lane's slice of a row: NV vectors of 8 elements at columns (lane + 32*i)*8.
+template <int NV>
+struct RowVec {
+  float v[NV][8];
+};
+template <int NV, typename T>
+__device__ __forceinline__ void row_load(RowVec<NV>& r, const T* row, int H, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    if (c < H) {
+      load8(row + c, r.v[i]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) r.v[i][u] = 0.f;
+    }
+  }
+}
+template <int NV>
+__device__ __forceinline__ void row_store(const RowVec<NV>& r, bf16* row, int H, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    if (c < H) store8(row + c, r.v[i]);
+  }
+}
+template <int NV>
+__device__ __forceinline__ float row_sum(const RowVec<NV>& r) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += r.v[i][u];
+  return warp_sum(s);
+}
+// mean and biased variance (two-pass, values already in registers); padding lanes hold zeros and
+// are excluded from the centred sum by the column predicate.
+template <int NV>
+__device__ __forceinline__ void row_stats(const RowVec<NV>& r, int H, int lane, float& mean, float& rstd, float eps) {
+  mean = row_sum(r) / (float)H;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    if (c < H) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float d = r.v[i][u] - mean;
+        s += d * d;
+      }
+    }
+  }
+  const float var = warp_sum(s) / (float)H;
+  rstd = rsqrtf(var + eps);
+}
+
+// Sums a per-lane column accumulator over the block's warps and adds it to out[H] with one atomic
+// per column per block.
+template <int NV>
+__device__ __forceinline__ void block_col_reduce_atomic(const RowVec<NV>& acc, float* out, int H,
+                                                        float (*buf)[NV * 256]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    if (c < H) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) buf[warp][c + u] = acc.v[i][u];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < ROW_WARPS; ++w) s += buf[w][c];
+    atomicAdd(out + c, s);
+  }
+}
+
+// ---------------------------------------------------------------- embedding post-processing
+// model.py:124-132: token-norm(raw) + pe[t] + learned      (raw = Linear output incl. bias)
+template <int NV>
+__global__ void embed_post_fwd_kernel(const bf16* __restrict__ raw, const float* __restrict__ pe,
+                                      const float* __restrict__ learned, bf16* __restrict__ out, int64_t M, int H,
+                                      int T) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  RowVec<NV> x;
+  row_load(x, raw + row * H, H, lane);
+  float mean, rstd;
+  row_stats(x, H, lane, mean, rstd, 1e-5f);
+  const int t = (int)(row % T);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    if (c < H) {
+      float p[8], l[8];
+      load8(pe + (int64_t)t * H + c, p);
+      load8(learned + c, l);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x.v[i][u] = (x.v[i][u] - mean) * rstd + p[u] + l[u];
+    }
+  }
+  row_store(x, out + row * H, H, lane);
+}
+
+// d raw = tokennorm_bwd(dout; raw) (+ addend);  d learned += colsum(dout)
+template <int NV>
+__global__ void embed_post_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ raw,
+                                      const bf16* __restrict__ addend, bf16* __restrict__ draw,
+                                      float* __restrict__ dlearned, int64_t M, int H) {
+  __shared__ float s_acc[ROW_WARPS][NV * 256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  RowVec<NV> acc;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc.v[i][u] = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp; row < M; row += (int64_t)gridDim.x * ROW_WARPS) {
+    RowVec<NV> x, dy;
+    row_load(x, raw + row * H, H, lane);
+    row_load(dy, dout + row * H, H, lane);
+    float mean, rstd;
+    row_stats(x, H, lane, mean, rstd, 1e-5f);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float xh = (x.v[i][u] - mean) * rstd;
+        s1 += dy.v[i][u];
+        s2 += dy.v[i][u] * xh;
+        acc.v[i][u] += dy.v[i][u];
+        x.v[i][u] = xh;
+      }
+    // padding lanes: dy = 0 there, so they do not contribute to s1/s2
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+    RowVec<NV> ad;
+    if (addend != nullptr) row_load(ad, addend + row * H, H, lane);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float g = rstd * (dy.v[i][u] - s1 - x.v[i][u] * s2);
+        if (addend != nullptr) g += ad.v[i][u];
+        dy.v[i][u] = g;
+      }
+    row_store(dy, draw + row * H, H, lane);
+  }
+  block_col_reduce_atomic<NV>(acc, dlearned, H, s_acc);
+}
+
+// ---------------------------------------------------------------- residual add + LayerNorm
+// torch/nn/modules/transformer.py:956: y = LN(a + b) * gamma + beta   (b may be null: plain LN)
+template <int NV>
+__global__ void add_ln_fwd_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  bf16* __restrict__ sum_out, bf16* __restrict__ y, float* __restrict__ mean_out,
+                                  float* __restrict__ rstd_out, int64_t M, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  RowVec<NV> x;
+  row_load(x, a + row * H, H, lane);
+  if (b != nullptr) {
+    RowVec<NV> t;
+    row_load(t, b + row * H, H, lane);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x.v[i][u] += t.v[i][u];
+  }
+  if (sum_out != nullptr) {
+    row_store(x, sum_out + row * H, H, lane);
+    // statistics are taken from the values backward will see (bf16-rounded sum)
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x.v[i][u] = __bfloat162float(__float2bfloat16(x.v[i][u]));
+  }
+  float mean, rstd;
+  row_stats(x, H, lane, mean, rstd, 1e-5f);
+  if (lane == 0 && mean_out != nullptr) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    if (c < H) {
+      float g[8], bt[8];
+      load8(gamma + c, g);
+      load8(beta + c, bt);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x.v[i][u] = (x.v[i][u] - mean) * rstd * g[u] + bt[u];
+    }
+  }
+  row_store(x, y + row * H, H, lane);
+}
+
+// dx = LN_bwd(dy) (+ addend);  dgamma += sum_rows dy*xhat;  dbeta += sum_rows dy
+template <int NV>
+__global__ void ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ s_saved,
+                              const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                              const float* __restrict__ gamma, const bf16* __restrict__ addend,
+                              bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                              int64_t M, int H) {
+  __shared__ float s_buf[ROW_WARPS][NV * 256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  RowVec<NV> accg, accb, gm;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      accg.v[i][u] = 0.f;
+      accb.v[i][u] = 0.f;
+      gm.v[i][u] = 0.f;
+    }
+    if (c < H) load8(gamma + c, gm.v[i]);
+  }
+  for (int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp; row < M; row += (int64_t)gridDim.x * ROW_WARPS) {
+    RowVec<NV> x, g;
+    row_load(x, s_saved + row * H, H, lane);
+    row_load(g, dy + row * H, H, lane);
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      const bool ok = c < H;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float xh = ok ? (x.v[i][u] - mean) * rstd : 0.f;
+        const float d = g.v[i][u];
+        accg.v[i][u] += d * xh;
+        accb.v[i][u] += d;
+        const float gg = d * gm.v[i][u];
+        s1 += gg;
+        s2 += gg * xh;
+        x.v[i][u] = xh;
+        g.v[i][u] = gg;
+      }
+    }
+    s1 = warp_sum(s1) / (float)H;
+    s2 = warp_sum(s2) / (float)H;
+    RowVec<NV> ad;
+    if (addend != nullptr) row_load(ad, addend + row * H, H, lane);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float r = rstd * (g.v[i][u] - s1 - x.v[i][u] * s2);
+        if (addend != nullptr) r += ad.v[i][u];
+        g.v[i][u] = r;
+      }
+    row_store(g, dx + row * H, H, lane);
+  }
+  block_col_reduce_atomic<NV>(accg, dgamma, H, s_buf);
+  block_col_reduce_atomic<NV>(accb, dbeta, H, s_buf);
+}
+
+// ---------------------------------------------------------------- SwiGLU gate (model.py:18-22)
+// x12 [M,2H] = fc1(x) | fc2(x);  g = x1 * sigmoid(x2)
+__global__ void swiglu_gate_fwd_kernel(const bf16* __restrict__ x12, bf16* __restrict__ g, int64_t M, int H) {
+  const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (idx >= M * H) return;
+  const int64_t row = idx / H;
+  const int c = (int)(idx % H);
+  float a[8], b[8];
+  load8(x12 + row * 2 * H + c, a);
+  load8(x12 + row * 2 * H + H + c, b);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) a[u] = a[u] * sigmoidf_(b[u]);
+  store8(g + idx, a);
+}
+__global__ void swiglu_gate_bwd_kernel(const bf16* __restrict__ dg, const bf16* __restrict__ x12,
+                                       bf16* __restrict__ dx12, int64_t M, int H) {
+  const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (idx >= M * H) return;
+  const int64_t row = idx / H;
+  const int c = (int)(idx % H);
+  float a[8], b[8], d[8];
+  load8(x12 + row * 2 * H + c, a);
+  load8(x12 + row * 2 * H + H + c, b);
+  load8(dg + idx, d);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float s = sigmoidf_(b[u]);
+    const float da = d[u] * s;
+    const float db = d[u] * a[u] * s * (1.f - s);
+    a[u] = da;
+    b[u] = db;
+  }
+  store8(dx12 + row * 2 * H + c, a);
+  store8(dx12 + row * 2 * H + H + c, b);
+}
+
+// ---------------------------------------------------------------- output head (model.py:150-152)
+// z = dec + filled_emb;  n = token_norm(z);  out = n * sigmoid(n)
+template <int NV>
+__global__ void final_norm_silu_fwd_kernel(const bf16* __restrict__ dec, const bf16* __restrict__ femb,
+                                           bf16* __restrict__ z_out, bf16* __restrict__ out, int64_t M, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  RowVec<NV> x, t;
+  row_load(x, dec + row * H, H, lane);
+  row_load(t, femb + row * H, H, lane);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x.v[i][u] = __bfloat162float(__float2bfloat16(x.v[i][u] + t.v[i][u]));
+  row_store(x, z_out + row * H, H, lane);
+  float mean, rstd;
+  row_stats(x, H, lane, mean, rstd, 1e-5f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float n = (x.v[i][u] - mean) * rstd;
+      x.v[i][u] = n * sigmoidf_(n);
+    }
+  row_store(x, out + row * H, H, lane);
+}
+template <int NV>
+__global__ void final_norm_silu_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ z,
+                                           bf16* __restrict__ dz, int64_t M, int H) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  RowVec<NV> x, d;
+  row_load(x, z + row * H, H, lane);
+  row_load(d, dout + row * H, H, lane);
+  float mean, rstd;
+  row_stats(x, H, lane, mean, rstd, 1e-5f);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    const bool ok = c < H;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float n = ok ? (x.v[i][u] - mean) * rstd : 0.f;
+      const float s = sigmoidf_(n);
+      const float dn = d.v[i][u] * (s + n * s * (1.f - s));
+      s1 += dn;
+      s2 += dn * n;
+      x.v[i][u] = n;
+      d.v[i][u] = dn;
+    }
+  }
+  s1 = warp_sum(s1) / (float)H;
+  s2 = warp_sum(s2) / (float)H;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) d.v[i][u] = rstd * (d.v[i][u] - s1 - x.v[i][u] * s2);
+  row_store(d, dz + row * H, H, lane);
+}
+
+// ---------------------------------------------------------------- column sums (bias gradients)
+// out[n] += sum_m x[m, n];  x bf16 [M, ld]; block = 32 column-groups(8 wide) x 8 row lanes
+__global__ void colsum_kernel(const bf16* __restrict__ x, int64_t ld, float* __restrict__ out, int64_t M, int N) {
+  __shared__ float s[8][256 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + cg * 8;
+  float acc[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+  if (c < N) {
+    for (int64_t r = (int64_t)blockIdx.y * 8 + rl; r < M; r += (int64_t)gridDim.y * 8) {
+      float t[8];
+      load8(x + r * ld + c, t);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += t[u];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) s[rl][cg * 8 + u] = acc[u];
+  __syncthreads();
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s[w][threadIdx.x];
+    atomicAdd(out + cc, t);
+  }
+}
+
+// ---------------------------------------------------------------- casts
+// fp32 [rows, cols] (ld src_ld) -> bf16 [rows, dst_ld], columns >= cols zero-filled.
+// Optional per-row zeroing: row_zero[row * row_zero_stride...] handled by the caller variant below.
+__global__ void cast_pad_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t src_ld,
+                                bf16* __restrict__ dst, int64_t dst_ld) {
+  const int64_t per_row = dst_ld / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * per_row) return;
+  const int64_t r = idx / per_row;
+  const int c = (int)(idx % per_row) * 8;
+  float v[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) v[u] = (c + u < cols) ? src[r * src_ld + c + u] : 0.f;
+  store8(dst + r * dst_ld + c, v);
+}
+
+// Packs the model inputs: frame (b,t) lives at src + b*batch_stride + t*cols (A1_train.py:93-94
+// slices are pointer offsets); optional zeroing of frames whose mask is 1
+// (A4_train_with_pretrained.py:107-108).
+__global__ void pack_frames_kernel(const float* __restrict__ src, int64_t batch_stride, int B, int T, int cols,
+                                   const float* __restrict__ zero_mask, int64_t zero_mask_stride,
+                                   bf16* __restrict__ dst, int dst_ld) {
+  const int per_row = dst_ld / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * T * per_row) return;
+  const int64_t r = idx / per_row;
+  const int c = (int)(idx % per_row) * 8;
+  const int b = (int)(r / T), t = (int)(r % T);
+  const float* p = src + (int64_t)b * batch_stride + (int64_t)t * cols;
+  const bool z = zero_mask != nullptr && zero_mask[(int64_t)b * zero_mask_stride + t] != 0.f;
+  float v[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) v[u] = (!z && c + u < cols) ? p[c + u] : 0.f;
+  store8(dst + r * dst_ld + c, v);
+}
+
+// ---------------------------------------------------------------- weight refresh (fp32 -> bf16 (+T))
+// One 32x32 tile per block; the tile table maps a flat tile index to (matrix, tile_r, tile_c).
+__global__ void weight_refresh_kernel(const float* __restrict__ params, bf16* __restrict__ wb,
+                                      const WeightDesc* __restrict__ descs, const int* __restrict__ tile_prefix,
+                                      int n_desc) {
+  __shared__ float tile[32][33];
+  int lo = 0, hi = n_desc - 1;
+  const int tid = blockIdx.x;
+  while (lo < hi) {  // last desc with prefix <= tid
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_prefix[mid] <= tid) lo = mid; else hi = mid - 1;
+  }
+  const WeightDesc d = descs[lo];
+  const int local = tid - tile_prefix[lo];
+  const int tiles_c = (d.cols_pad + 31) / 32;
+  const int tr = local / tiles_c, tc = local % tiles_c;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = tr * 32 + ty + 8 * i, c = tc * 32 + tx;
+    float v = 0.f;
+    if (r < d.rows && c < d.cols) v = params[d.src_off + (int64_t)r * d.cols + c];
+    tile[ty + 8 * i][tx] = v;
+    if (r < d.rows_pad && c < d.dst_ld && d.dst_off >= 0) wb[d.dst_off + (int64_t)r * d.dst_ld + c] = __float2bfloat16(v);
+  }
+  if (d.dstT_off < 0) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = tc * 32 + ty + 8 * i, r = tr * 32 + tx;  // transposed element (c, r)
+    if (c < d.cols && r < d.dstT_ld) wb[d.dstT_off + (int64_t)c * d.dstT_ld + r] = __float2bfloat16(tile[tx][ty + 8 * i]);
+  }
+}
+
+// ---------------------------------------------------------------- host launchers
+#define KIT_NV_DISPATCH(H, CALL)                 \
+  do {                                           \
+    if ((H) <= 256) { constexpr int NV = 1; CALL; } \
+    else if ((H) <= 512) { constexpr int NV = 2; CALL; } \
+    else { constexpr int NV = 4; CALL; }         \
+  } while (0)
+
+static inline int check_h(int H) {
+  KIT_REQUIRE(H > 0 && H % 8 == 0 && H <= 1024, "hidden size %d unsupported (multiple of 8, <= 1024)", H);
+  return KIT_OK;
+}
+static inline unsigned row_blocks(int64_t M) { return (unsigned)ceil_div(M, ROW_WARPS); }
+static inline unsigned reduce_blocks(int64_t M) {
+  int64_t b = ceil_div(M, ROW_WARPS * 4);
+  if (b > 148 * 4) b = 148 * 4;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+int embed_post_fwd(const bf16* raw, const float* pe, const float* learned, bf16* out, int64_t M, int H, int T,
+                   cudaStream_t st) {
+  int rc = check_h(H);
+  if (rc) return rc;
+  KIT_NV_DISPATCH(H, (embed_post_fwd_kernel<NV><<<row_blocks(M), 256, 0, st>>>(raw, pe, learned, out, M, H, T)));
+  KIT_LAUNCH_CHECK();
+  return KIT_OK;
+}
+int embed_post_bwd(const bf16* dout, const bf16* raw, const bf16* addend, bf16* draw, float* dlearned, int64_t M, int H,
+                   cudaStream_t st) {
+  int rc = check_h(H);
+  if (rc) return rc;
+  KIT_NV_DISPATCH(H, (embed_post_bwd_kernel<NV><<<reduce_blocks(M), 256, 0, st>>>(dout, raw, addend, draw, dlearned, M, H)));
+  KIT_LAUNCH_CHECK();
+  return KIT_OK;
+}
+int add_ln_fwd(const bf16* a, const bf16* b, const float* gamma, const float* beta, bf16* sum_out, bf16* y, float* mean,
+               float* rstd, int64_t M, int H, cudaStream_t st) {
+  int rc = check_h(H);
+  if (rc) return rc;
+  KIT_NV_DISPATCH(H, (add_ln_fwd_kernel<NV><<<row_blocks(M), 256, 0, st>>>(a, b, gamma, beta, sum_out, y, mean, rstd, M, H)));
+  KIT_LAUNCH_CHECK();
+  return KIT_OK;
+}
+int ln_bwd(const bf16* dy, const bf16* s_saved, const float* mean, const float* rstd, const float* gamma,
+           const bf16* addend, bf16* dx, float* dgamma, float* dbeta, int64_t M, int H, cudaStream_t st) {
+  int rc = check_h(H);
+  if (rc) return rc;
+  KIT_NV_DISPATCH(H, (ln_bwd_kernel<NV><<<reduce_blocks(M), 256, 0, st>>>(dy, s_saved, mean, rstd, gamma, addend, dx,
+                                                                         dgamma, dbeta, M, H)));
+  KIT_LAUNCH_CHECK();
+  return KIT_OK;
+}
+int swiglu_gate_fwd(const bf16* x12, bf16* g, int64_t M, int H, cudaStream_t st) {
+  int rc = check_h(H);
+  if (rc) return rc;
+  swiglu_gate_fwd_kernel<<<(unsigned)ceil_div(M * H / 8, 256), 256, 0, st>>>(x12, g, M, H);
+  KIT_LAUNCH_CHECK();
+  return KIT_OK;
+}
+int swiglu_gate_bwd(const bf16* dg, const bf16* x12, bf16* dx12, int64_t M, int H, cudaStream_t st) {
+  int rc = check_h(H);
+  if (rc) return rc;
+  swiglu_gate_bwd_kernel<<<(unsigned)ceil_div(M * H / 8, 256), 256, 0, st>>>(dg, x12, dx12, M, H);
+  KIT_LAUNCH_CHECK();
+  return KIT_OK;
+}
+int final_norm_silu_fwd(const bf16* dec, const bf16* femb, bf16* z_out, bf16* out, int64_t M, int H, cudaStream_t st) {
+  int rc = check_h(H);
+  if (rc) return rc;
+  KIT_NV_DISPATCH(H, (final_norm_silu_fwd_kernel<NV><<<row_blocks(M), 256, 0, st>>>(dec, femb, z_out, out, M, H)));
+  KIT_LAUNCH_CHECK();
+  return KIT_OK;
+}
+int final_norm_silu_bwd(const bf16* dout, const bf16* z, bf16* dz, int64_t M, int H, cudaStream_t st) {
+  int rc = check_h(H);
+  if (rc) return rc;
+  KIT_NV_DISPATCH(H, (final_norm_silu_bwd_kernel<NV><<<row_blocks(M), 256, 0, st>>>(dout, z, dz, M, H)));
+  KIT_LAUNCH_CHECK();
+  return KIT_OK;
+}
+int colsum(const bf16* x, int64_t ld, float* out, int64_t M, int N, cudaStream_t st) {
+  KIT_REQUIRE(N % 8 == 0 && ld % 8 == 0, "colsum needs N and ld to be multiples of 8 (N=%d ld=%lld)", N, (long long)ld);
+  int64_t ysplit = ceil_div(M, 8 * 16);
+  if (ysplit > 128) ysplit = 128;
+  if (ysplit < 1) ysplit = 1;
+  dim3 grid((unsigned)ceil_div(N, 256), (unsigned)ysplit);
+  colsum_kernel<<<grid, 256, 0, st>>>(x, ld, out, M, N);
+  KIT_LAUNCH_CHECK();
+  return KIT_OK;
+}
+int cast_pad(const float* src, int64_t rows, int64_t cols, int64_t src_ld, bf16* dst, int64_t dst_ld, cudaStream_t st) {
+  KIT_REQUIRE(dst_ld % 8 == 0 && dst_ld >= cols, "cast_pad: dst_ld must be a multiple of 8 and >= cols");
+  cast_pad_kernel<<<(unsigned)ceil_div(rows * (dst_ld / 8), 256), 256, 0, st>>>(src, rows, cols, src_ld, dst, dst_ld);
+  KIT_LAUNCH_CHECK();
+  return KIT_OK;
+}
+int pack_frames(const float* src, int64_t batch_stride, int B, int T, int cols, const float* zero_mask,
+                int64_t zero_mask_stride, bf16* dst, int dst_ld, cudaStream_t st) {
+  KIT_REQUIRE(dst_ld % 8 == 0 && dst_ld >= cols, "pack_frames: dst_ld must be a multiple of 8 and >= cols");
+  pack_frames_kernel<<<(unsigned)ceil_div((int64_t)B * T * (dst_ld / 8), 256), 256, 0, st>>>(
+      src, batch_stride, B, T, cols, zero_mask, zero_mask_stride, dst, dst_ld);
+  KIT_LAUNCH_CHECK();
+  return KIT_OK;
+}
+int weight_refresh(const float* params, bf16* wb, const WeightDesc* descs_dev, const int* tile_prefix_dev, int n_desc,
+                   int total_tiles, cudaStream_t st) {
+  weight_refresh_kernel<<<total_tiles, 256, 0, st>>>(params, wb, descs_dev, tile_prefix_dev, n_desc);
+  KIT_LAUNCH_CHECK();
+  return KIT_OK;
+}
+
+}  // namespace kit
+
+// ---------------------------------------------------------------- C ABI (unit-test entry points)
+using namespace kit;
+extern "C" int kit_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* sum_out,
+                                     void* y, float* mean, float* rstd, int64_t M, int32_t H, void* stream) {
+  return add_ln_fwd((const bf16*)a, (const bf16*)b, gamma, beta, (bf16*)sum_out, (bf16*)y, mean, rstd, M, H,
+                    (cudaStream_t)stream);
+}
+extern "C" int kit_layernorm_bwd(const void* dy, const void* sum_saved, const float* mean, const float* rstd,
+                                 const float* gamma, const void* addend, void* dx, float* dgamma, float* dbeta, int64_t M,
+                                 int32_t H, void* stream) {
+  return ln_bwd((const bf16*)dy, (const bf16*)sum_saved, mean, rstd, gamma, (const bf16*)addend, (bf16*)dx, dgamma, dbeta,
+                M, H, (cudaStream_t)stream);
+}
+extern "C" int kit_cast_fp32_to_bf16_padded(const float* src, int64_t rows, int64_t cols, int64_t src_ld, void* dst,
+                                            int64_t dst_ld, void* stream) {
+  return cast_pad(src, rows, cols, src_ld, (bf16*)dst, dst_ld, (cudaStream_t)stream);
+}

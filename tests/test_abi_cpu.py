@@ -1,0 +1,84 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol kit.h declares, and the
+pure-host entry points (layout queries, argument validation) behave."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from keypoints_interpolation_transformer_b200 import _lib as K
+from oracle import kit_oracle as ko
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "kit.h")).read()
+    declared = set(re.findall(r"\b(kit_[a-z0-9_]+)\s*\(", header))
+    lib = K.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in kit.h but not exported"
+    assert declared == set(K.exported_symbols())
+    assert lib.kit_version() == 1
+
+
+@pytest.mark.parametrize("K2,H,L,NH", [(108, 256, 6, 8), (142, 256, 6, 8), (142, 512, 8, 8), (108, 64, 2, 4)])
+def test_layout_matches_reference_state_dict(K2, H, L, NH):
+    cfg = K.KitModelConfig(K2, H, L, NH, 2048, 2048)
+    lib = K.lib()
+    n = lib.kit_layout_num_entries(C.byref(cfg))
+    schema = dict(ko.state_dict_schema(K2, H, L))
+    seen = {}
+    name = C.create_string_buffer(256)
+    spans = []
+    for i in range(n):
+        off, numel, rows, cols, isbuf = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        K.check(lib.kit_layout_entry(C.byref(cfg), i, name, 256, C.byref(off), C.byref(numel), C.byref(rows),
+                                     C.byref(cols), C.byref(isbuf)))
+        seen[name.value.decode()] = (off.value, numel.value, isbuf.value)
+        spans.append((off.value, off.value + numel.value))
+        assert off.value % 8 == 0
+    assert set(seen) == set(schema)                       # 212 keys at L=6
+    for k, shape in schema.items():
+        n_el = 1
+        for s in shape:
+            n_el *= s
+        assert seen[k][1] == n_el, k
+        assert seen[k][2] == (1 if k.endswith("pos_encoding") else 0)
+    spans.sort()
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0                                   # no overlap
+    trainable = lib.kit_layout_trainable_floats(C.byref(cfg))
+    total = lib.kit_layout_total_floats(C.byref(cfg))
+    assert total - trainable == 2 * 2048 * H
+    n_params = sum(v[1] for k, v in seen.items() if not k.endswith("pos_encoding"))
+    if (K2, H, L) == (142, 256, 6):
+        assert n_params == 18066318
+    if (K2, H, L) == (108, 256, 6):
+        assert n_params == 18040172
+    # buckets tile the trainable range exactly once
+    nb = lib.kit_layout_num_buckets(C.byref(cfg))
+    rng = []
+    for b in range(nb):
+        lo, hi = C.c_int64(), C.c_int64()
+        K.check(lib.kit_layout_bucket(C.byref(cfg), b, C.byref(lo), C.byref(hi)))
+        rng.append((lo.value, hi.value))
+    rng.sort()
+    assert rng[0][0] == 0 and rng[-1][1] == trainable
+    for (a0, a1), (b0, b1) in zip(rng, rng[1:]):
+        assert a1 == b0
+    # swiGLU fc1|fc2 are adjacent so they run as one [2H,H] GEMM
+    assert seen["swiGlu_decoded.fc2.weight"][0] == seen["swiGlu_decoded.fc1.weight"][0] + H * H
+    assert seen["swiGlu_decoded.fc2.bias"][0] == seen["swiGlu_decoded.fc1.bias"][0] + H
+
+
+def test_invalid_config_is_an_error_not_a_fallback():
+    lib = K.lib()
+    bad = K.KitModelConfig(142, 250, 6, 8, 2048, 2048)
+    assert lib.kit_layout_num_entries(C.byref(bad)) == -1
+    assert b"hidden" in lib.kit_last_error()
+    eng = C.c_void_p()
+    rc = lib.kit_engine_create(C.byref(K.KitModelConfig(142, 256, 6, 8, 2048, 2048)), 4, 4096, C.byref(eng))
+    assert rc != 0 and b"positional table" in lib.kit_last_error()
+    with pytest.raises(K.KitError):
+        K.check(lib.kit_loss_fwd_bwd(None, None, None, 1, 1, 0, 1.0, None, None, None, None))

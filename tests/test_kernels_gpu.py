@@ -1,0 +1,228 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (include/kit.h) and
+compared with a plain fp32 PyTorch restatement of the same op on the same seeded inputs.
+
+Tolerances: bf16 tensor-core kernels 2e-2 relative (north_star); fp32 elementwise 1e-5 relative;
+masks / indices bit-exact."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from keypoints_interpolation_transformer_b200 import _lib as K
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _sp():
+    return K.stream_ptr()
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------- GEMM (tcgen05)
+@pytest.mark.parametrize("M,N,Kd", [(128, 128, 64), (256, 128, 256), (300, 200, 144), (1000, 768, 256),
+                                    (16384, 256, 256), (2048, 256, 2048), (1024, 2048, 256), (515, 142, 256)])
+def test_gemm_tn_bias(M, N, Kd):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    a = _bf(torch.randn(M, Kd, generator=g)).to(DEV)
+    b = _bf(torch.randn(N, Kd, generator=g) / math.sqrt(Kd)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    ref = a.float() @ b.float().t() + bias
+    # bf16 out
+    if N % 8 == 0:
+        c = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+        K.check(K.lib().kit_gemm_bf16(0, K.ptr(a), Kd, K.ptr(b), Kd, K.ptr(c), N, M, N, Kd, K.ptr(bias), None, 0,
+                                      K.OUT_BF16, K.ACT_NONE, None, 0, 1, _sp()))
+        torch.cuda.synchronize()
+        assert _rel(c, ref) < 5e-3
+        assert (c.float() - ref).abs().max().item() < 0.05 * max(1.0, ref.abs().max().item())
+    # fp32 out, unaligned leading dimension allowed
+    c32 = torch.full((M, N), float("nan"), device=DEV)
+    K.check(K.lib().kit_gemm_bf16(0, K.ptr(a), Kd, K.ptr(b), Kd, K.ptr(c32), N, M, N, Kd, K.ptr(bias), None, 0,
+                                  K.OUT_F32, K.ACT_NONE, None, 0, 1, _sp()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(c32).all()
+    assert _rel(c32, ref) < 1e-4          # fp32 accumulate of exact bf16 products
+
+
+def test_gemm_tn_epilogues():
+    M, N, Kd = 640, 512, 256
+    g = torch.Generator(device="cpu").manual_seed(5)
+    a = _bf(torch.randn(M, Kd, generator=g)).to(DEV)
+    b = _bf(torch.randn(N, Kd, generator=g) / math.sqrt(Kd)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    add = _bf(torch.randn(M, N, generator=g)).to(DEV)
+    pre = a.float() @ b.float().t() + bias
+    c = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    lib = K.lib()
+    # bias + residual addend
+    K.check(lib.kit_gemm_bf16(0, K.ptr(a), Kd, K.ptr(b), Kd, K.ptr(c), N, M, N, Kd, K.ptr(bias), K.ptr(add), N,
+                              K.OUT_BF16, K.ACT_NONE, None, 0, 1, _sp()))
+    torch.cuda.synchronize()
+    assert _rel(c, pre + add.float()) < 5e-3
+    # in-place accumulate (addend == output)
+    acc = add.clone()
+    K.check(lib.kit_gemm_bf16(0, K.ptr(a), Kd, K.ptr(b), Kd, K.ptr(acc), N, M, N, Kd, K.ptr(bias), K.ptr(acc), N,
+                              K.OUT_BF16, K.ACT_NONE, None, 0, 1, _sp()))
+    torch.cuda.synchronize()
+    assert _rel(acc, pre + add.float()) < 5e-3
+    # gelu (exact erf) with the pre-activation saved
+    z = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    K.check(lib.kit_gemm_bf16(0, K.ptr(a), Kd, K.ptr(b), Kd, K.ptr(c), N, M, N, Kd, K.ptr(bias), None, 0,
+                              K.OUT_BF16, K.ACT_GELU, K.ptr(z), N, 1, _sp()))
+    torch.cuda.synchronize()
+    assert _rel(z, pre) < 5e-3
+    assert _rel(c, torch.nn.functional.gelu(pre)) < 5e-3
+    # multiply by gelu'(z)
+    zz = _bf(torch.randn(M, N, generator=g)).to(DEV)
+    K.check(lib.kit_gemm_bf16(0, K.ptr(a), Kd, K.ptr(b), Kd, K.ptr(c), N, M, N, Kd, None, None, 0,
+                              K.OUT_BF16, K.ACT_GELU_BWD, K.ptr(zz), N, 1, _sp()))
+    torch.cuda.synchronize()
+    zf = zz.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).sum().backward()
+    assert _rel(c, (pre - bias) * zf.grad) < 5e-3
+
+
+@pytest.mark.parametrize("Kr,M,N,ldc", [(64, 128, 128, 128), (1024, 256, 256, 256), (16384, 256, 256, 256),
+                                        (4096, 2048, 256, 256), (4096, 256, 2048, 2048), (500, 142, 256, 256),
+                                        (1000, 256, 142, 142), (8192, 768, 256, 256)])
+def test_gemm_wgrad_accumulates(Kr, M, N, ldc):
+    g = torch.Generator(device="cpu").manual_seed(Kr + M)
+    lda = (M + 7) // 8 * 8
+    ldb = (N + 7) // 8 * 8
+    a = torch.zeros(Kr, lda, dtype=torch.bfloat16)
+    b = torch.zeros(Kr, ldb, dtype=torch.bfloat16)
+    a[:, :M] = _bf(torch.randn(Kr, M, generator=g))
+    b[:, :N] = _bf(torch.randn(Kr, N, generator=g) / math.sqrt(Kr))
+    a, b = a.to(DEV), b.to(DEV)
+    c0 = torch.randn(M, ldc, generator=g).to(DEV)
+    c = c0.clone()
+    K.check(K.lib().kit_gemm_bf16(1, K.ptr(a), lda, K.ptr(b), ldb, K.ptr(c), ldc, M, N, Kr, None, None, 0,
+                                  K.OUT_F32_ATOMIC, K.ACT_NONE, None, 0, 0, _sp()))
+    torch.cuda.synchronize()
+    ref = c0.clone()
+    ref[:, :N] += a[:, :M].float().t() @ b[:, :N].float()
+    assert _rel(c, ref) < 1e-4
+    if ldc > N:
+        assert torch.equal(c[:, N:], c0[:, N:])      # columns outside N untouched
+
+
+# ------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, bias):
+    d = q.shape[-1]
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(d)
+    if bias is not None:
+        s = s + bias
+    return torch.softmax(s, dim=-1) @ v
+
+
+def _mask_bias(fm, flags, Sq, Sk):
+    B = fm.shape[0]
+    i = torch.arange(Sq, device=fm.device).view(1, Sq, 1)
+    j = torch.arange(Sk, device=fm.device).view(1, 1, Sk)
+    bias = torch.zeros(B, Sq, Sk, device=fm.device)
+    if flags & K.MASK_REPEAT_INC:
+        bias = bias.masked_fill((j > i) & (fm.view(B, 1, Sk) == 1), float("-inf"))
+    if flags & K.MASK_TRIANGLE:
+        bias = bias.masked_fill(j > i, float("-inf"))
+    if flags & K.MASK_KEYPAD_ADD:
+        bias = bias + fm.view(B, 1, Sk)
+    return bias
+
+
+@pytest.mark.parametrize("B,NH,S,d,flags,explicit", [
+    (3, 4, 64, 32, 0, False), (2, 8, 64, 32, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD, False),
+    (2, 8, 64, 32, K.MASK_REPEAT_INC, False), (2, 4, 12, 16, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD, False),
+    (2, 2, 100, 64, K.MASK_TRIANGLE, False), (1, 4, 256, 32, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD, False),
+    (2, 4, 40, 32, 0, True)])
+def test_attention_fwd_bwd(B, NH, S, d, flags, explicit):
+    H = NH * d
+    g = torch.Generator(device="cpu").manual_seed(B * 100 + S)
+    qkv = _bf(torch.randn(B * S, 3 * H, generator=g)).to(DEV)
+    dout = _bf(torch.randn(B * S, H, generator=g)).to(DEV)
+    fm = (torch.rand(B, S, generator=g) < 0.4).float().to(DEV)
+    fm[:, 0] = 0
+    mask = K.KitAttnMask()
+    bias = None
+    if flags:
+        mask.frame_mask = fm.data_ptr()
+        mask.frame_mask_stride = S
+        mask.flags = flags
+        bias = _mask_bias(fm, flags, S, S)[:, None]
+    eb = None
+    if explicit:
+        eb = torch.randn(B, S, S, generator=g).to(DEV)
+        eb[:, :, -3:] = float("-inf")
+        mask.bias = eb.data_ptr()
+        mask.bias_stride_b = S * S
+        mask.bias_stride_h = 0
+        bias = eb[:, None]
+    out = torch.empty(B * S, H, dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(B, NH, S, device=DEV)
+    lib = K.lib()
+    q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+    K.check(lib.kit_attention_fwd(K.ptr(q), 3 * H, K.ptr(k), 3 * H, K.ptr(v), 3 * H, K.ptr(out), H, K.ptr(lse), B, NH, S,
+                                  S, d, C.byref(mask), _sp()))
+    dq = torch.empty(B * S, 3 * H, dtype=torch.bfloat16, device=DEV)
+    K.check(lib.kit_attention_bwd(K.ptr(q), 3 * H, K.ptr(k), 3 * H, K.ptr(v), 3 * H, K.ptr(out), H, K.ptr(dout), H,
+                                  K.ptr(lse), K.ptr(dq[:, :H]), 3 * H, K.ptr(dq[:, H:2 * H]), 3 * H, K.ptr(dq[:, 2 * H:]),
+                                  3 * H, B, NH, S, S, d, C.byref(mask), _sp()))
+    torch.cuda.synchronize()
+
+    def heads(x):
+        return x.float().view(B, S, NH, d).transpose(1, 2)
+    qf, kf, vf = (heads(t).detach().requires_grad_(True) for t in (q, k, v))
+    ref = _attn_ref(qf, kf, vf, bias)
+    ref.backward(heads(dout))
+    got = heads(out)
+    assert _rel(got, ref) < 1e-2
+    assert _rel(heads(dq[:, :H]), qf.grad) < 2e-2
+    assert _rel(heads(dq[:, H:2 * H]), kf.grad) < 2e-2
+    assert _rel(heads(dq[:, 2 * H:]), vf.grad) < 2e-2
+
+
+# ------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("M,H", [(1000, 256), (333, 64), (512, 512), (64, 1024)])
+def test_add_layernorm_fwd_bwd(M, H):
+    g = torch.Generator(device="cpu").manual_seed(M + H)
+    a = _bf(torch.randn(M, H, generator=g)).to(DEV)
+    b = _bf(torch.randn(M, H, generator=g)).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(H, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(H, generator=g)).to(DEV)
+    s = torch.empty(M, H, dtype=torch.bfloat16, device=DEV)
+    y = torch.empty(M, H, dtype=torch.bfloat16, device=DEV)
+    mean = torch.empty(M, device=DEV)
+    rstd = torch.empty(M, device=DEV)
+    lib = K.lib()
+    K.check(lib.kit_add_layernorm_fwd(K.ptr(a), K.ptr(b), K.ptr(gamma), K.ptr(beta), K.ptr(s), K.ptr(y), K.ptr(mean),
+                                      K.ptr(rstd), M, H, _sp()))
+    torch.cuda.synchronize()
+    sref = (a.float() + b.float())
+    assert _rel(s, sref) < 4e-3
+    sx = s.float().detach().requires_grad_(True)
+    gr = gamma.clone().requires_grad_(True)
+    br = beta.clone().requires_grad_(True)
+    yref = torch.nn.functional.layer_norm(sx, (H,), gr, br, 1e-5)
+    assert _rel(y, yref) < 4e-3
+    assert torch.allclose(mean, sx.mean(-1), atol=1e-5, rtol=1e-5)
+    dy = _bf(torch.randn(M, H, generator=g)).to(DEV)
+    add = _bf(torch.randn(M, H, generator=g)).to(DEV)
+    yref.backward(dy.float())
+    dx = torch.empty(M, H, dtype=torch.bfloat16, device=DEV)
+    dgamma = torch.zeros(H, device=DEV)
+    dbeta = torch.zeros(H, device=DEV)
+    K.check(lib.kit_layernorm_bwd(K.ptr(dy), K.ptr(s), K.ptr(mean), K.ptr(rstd), K.ptr(gamma), K.ptr(add), K.ptr(dx),
+                                  K.ptr(dgamma), K.ptr(dbeta), M, H, _sp()))
+    torch.cuda.synchronize()
+    assert _rel(dx, sx.grad + add.float()) < 5e-3
+    assert _rel(dgamma, gr.grad) < 1e-4
+    assert _rel(dbeta, br.grad) < 1e-4
