@@ -98,7 +98,9 @@ typedef struct KitAttnMask {
   int64_t bias_stride_h;     /* elements between heads   (0 = shared)  */
 } KitAttnMask;
 
-int kit_engine_create(const KitModelConfig* cfg, int32_t batch, int32_t seq_len, KitEngine** out);
+/* training != 0 keeps every layer's activations for kit_engine_backward; training == 0 lets all layers
+ * share one set of buffers (inference: 3_test_IA_interpolation / A1_train.py:139-218 eval). */
+int kit_engine_create(const KitModelConfig* cfg, int32_t batch, int32_t seq_len, int32_t training, KitEngine** out);
 int kit_engine_destroy(KitEngine* e);
 int64_t kit_engine_workspace_bytes(const KitEngine* e);
 /* params/grads: fp32 arenas of kit_layout_total_floats / kit_layout_trainable_floats floats. */

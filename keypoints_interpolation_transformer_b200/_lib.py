@@ -56,7 +56,7 @@ _SIGNATURES = {
     "kit_layout_total_floats": (_I64, [C.POINTER(KitModelConfig)]),
     "kit_layout_num_buckets": (_I32, [C.POINTER(KitModelConfig)]),
     "kit_layout_bucket": (C.c_int, [C.POINTER(KitModelConfig), _I32, C.POINTER(_I64), C.POINTER(_I64)]),
-    "kit_engine_create": (C.c_int, [C.POINTER(KitModelConfig), _I32, _I32, C.POINTER(_P)]),
+    "kit_engine_create": (C.c_int, [C.POINTER(KitModelConfig), _I32, _I32, _I32, C.POINTER(_P)]),
     "kit_engine_destroy": (C.c_int, [_P]),
     "kit_engine_workspace_bytes": (_I64, [_P]),
     "kit_engine_bind": (C.c_int, [_P, _P, _P, _P, _I64]),

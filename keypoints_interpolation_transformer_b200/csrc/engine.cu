@@ -206,6 +206,7 @@ using namespace kit;
 struct KitEngine {
   Layout L;
   int B = 0, T = 0;
+  int training = 1;  // 0: layers share one set of activation buffers (inference only)
   int64_t M = 0;
   int K2p = 0;
   std::map<std::string, Buf> bufs;
@@ -264,7 +265,8 @@ static void plan_workspace(KitEngine* e) {
   e->alloc("dp", M * e->K2p, 2, e->K2p);
   e->alloc("st_encn", 2 * M, 4, 0);
   e->alloc("st_decn", 2 * M, 4, 0);
-  for (int l = 0; l < L.cfg.layers; ++l) {
+  const int n_saved = e->training ? L.cfg.layers : 1;
+  for (int l = 0; l < n_saved; ++l) {
     const std::string p = "enc" + std::to_string(l) + ".";
     e->alloc(p + "qkv", M * 3 * H, 2, 3 * H);
     for (const char* n : {"ao", "s1", "x1", "s2", "x2"}) e->alloc(p + n, M * H, 2, H);
@@ -274,7 +276,7 @@ static void plan_workspace(KitEngine* e) {
     e->alloc(p + "st1", 2 * M, 4, 0);
     e->alloc(p + "st2", 2 * M, 4, 0);
   }
-  for (int l = 0; l < L.cfg.layers; ++l) {
+  for (int l = 0; l < n_saved; ++l) {
     const std::string p = "dec" + std::to_string(l) + ".";
     e->alloc(p + "qkv", M * 3 * H, 2, 3 * H);
     e->alloc(p + "kvc", M * 2 * H, 2, 2 * H);
@@ -286,11 +288,12 @@ static void plan_workspace(KitEngine* e) {
     for (const char* n : {"st1", "st2", "st3"}) e->alloc(p + n, 2 * M, 4, 0);
   }
   // backward scratch
-  for (const char* n : {"g0", "g1", "g2", "g3", "gmem"}) e->alloc(n, M * H, 2, H);
-  e->alloc("gff", M * FF, 2, FF);
-  e->alloc("gqkv", M * 3 * H, 2, 3 * H);
-  e->alloc("gkv", M * 2 * H, 2, 2 * H);
-  e->alloc("g2h", M * 2 * H, 2, 2 * H);
+  const int64_t gm = e->training ? M : 8;
+  for (const char* n : {"g0", "g1", "g2", "g3", "gmem"}) e->alloc(n, gm * H, 2, H);
+  e->alloc("gff", gm * FF, 2, FF);
+  e->alloc("gqkv", gm * 3 * H, 2, 3 * H);
+  e->alloc("gkv", gm * 2 * H, 2, 2 * H);
+  e->alloc("g2h", gm * 2 * H, 2, 2 * H);
 }
 
 static void resolve_pointers(KitEngine* e) {
@@ -308,13 +311,13 @@ static void resolve_pointers(KitEngine* e) {
   e->ea.resize(L.cfg.layers);
   e->da.resize(L.cfg.layers);
   for (int l = 0; l < L.cfg.layers; ++l) {
-    const std::string p = "enc" + std::to_string(l) + ".";
+    const std::string p = "enc" + std::to_string(e->training ? l : 0) + ".";
     EncAct& a = e->ea[l];
     a.qkv = wsptr<bf16>(e, p + "qkv"); a.ao = wsptr<bf16>(e, p + "ao"); a.s1 = wsptr<bf16>(e, p + "s1");
     a.x1 = wsptr<bf16>(e, p + "x1"); a.z = wsptr<bf16>(e, p + "z"); a.hh = wsptr<bf16>(e, p + "hh");
     a.s2 = wsptr<bf16>(e, p + "s2"); a.x2 = wsptr<bf16>(e, p + "x2");
     a.lse = wsptr<float>(e, p + "lse"); a.st1 = wsptr<float>(e, p + "st1"); a.st2 = wsptr<float>(e, p + "st2");
-    const std::string q = "dec" + std::to_string(l) + ".";
+    const std::string q = "dec" + std::to_string(e->training ? l : 0) + ".";
     DecAct& d = e->da[l];
     d.qkv = wsptr<bf16>(e, q + "qkv"); d.ao = wsptr<bf16>(e, q + "ao"); d.s1 = wsptr<bf16>(e, q + "s1");
     d.y1 = wsptr<bf16>(e, q + "y1"); d.qc = wsptr<bf16>(e, q + "qc"); d.kvc = wsptr<bf16>(e, q + "kvc");
@@ -636,7 +639,8 @@ extern "C" int kit_layout_bucket(const KitModelConfig* cfg, int32_t bucket, int6
   return KIT_OK;
 }
 
-extern "C" int kit_engine_create(const KitModelConfig* cfg, int32_t batch, int32_t seq_len, KitEngine** out) {
+extern "C" int kit_engine_create(const KitModelConfig* cfg, int32_t batch, int32_t seq_len, int32_t training,
+                                 KitEngine** out) {
   KIT_REQUIRE(out != nullptr, "kit_engine_create: out is null");
   KIT_REQUIRE(batch > 0 && seq_len > 0, "kit_engine_create: batch and seq_len must be positive");
   KitEngine* e = new KitEngine();
@@ -652,6 +656,7 @@ extern "C" int kit_engine_create(const KitModelConfig* cfg, int32_t batch, int32
   }
   e->B = batch;
   e->T = seq_len;
+  e->training = training ? 1 : 0;
   e->M = (int64_t)batch * seq_len;
   e->K2p = (int)up8(cfg->input_size);
   plan_workspace(e);
@@ -709,6 +714,7 @@ extern "C" int kit_engine_forward(KitEngine* e, const float* x_enc, int64_t x_en
 
 extern "C" int kit_engine_backward(KitEngine* e, const float* dpred, KitBucketCallback bucket_done, void* user, void* stream) {
   KIT_REQUIRE(e && e->bound && e->grads, "kit_engine_backward: engine not bound to a gradient arena");
+  KIT_REQUIRE(e->training, "kit_engine_backward: engine was created for inference (training = 0)");
   KIT_REQUIRE(!e->fwd_plans.empty(), "kit_engine_backward: run kit_engine_forward first");
   KIT_REQUIRE(dpred != nullptr, "kit_engine_backward: dpred is null");
   e->st = (cudaStream_t)stream;

@@ -1,0 +1,52 @@
+"""Adam over the flat parameter arena: one kernel for the whole model (A1_train.py:135,256 uses
+torch.optim.Adam with default betas/eps, no weight decay).  ``param_groups[0]['lr']`` is honoured at
+every step so the reference's per-epoch ``lr_lambda`` write (A1_train.py:42-54) keeps working."""
+import torch
+
+from . import _lib as K
+
+
+class FlatAdam:
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.model = model
+        self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "params": list(model.parameters())}]
+        self.step_count = 0
+        self.exp_avg = None
+        self.exp_avg_sq = None
+        self.grad_scale = 1.0        # 1/world_size under data parallelism (sum all-reduce)
+
+    def _state(self):
+        n = self.model.layout.trainable
+        dev = self.model.flat_params.device
+        if self.exp_avg is None or self.exp_avg.device != dev:
+            self.exp_avg = torch.zeros(n, device=dev)
+            self.exp_avg_sq = torch.zeros(n, device=dev)
+        return n
+
+    def zero_grad(self, set_to_none=False):
+        g = self.model.ensure_flat_grads()
+        g.zero_()
+
+    @torch.no_grad()
+    def step(self):
+        n = self._state()
+        g = self.model.ensure_flat_grads()
+        grp = self.param_groups[0]
+        self.step_count += 1
+        K.check(K.lib().kit_adam_step(K.ptr(self.model.flat_params), K.ptr(g), K.ptr(self.exp_avg),
+                                      K.ptr(self.exp_avg_sq), n, float(grp["lr"]), float(grp["betas"][0]),
+                                      float(grp["betas"][1]), float(grp["eps"]), self.step_count,
+                                      float(self.grad_scale), K.stream_ptr()))
+        self.model.mark_dirty()
+
+    def state_dict(self):
+        self._state()
+        return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
+
+    def load_state_dict(self, sd):
+        self._state()
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.param_groups[0].update(sd["param_groups"][0])

@@ -1,0 +1,164 @@
+"""The train / eval step of the reference (A1_train.py:84-218) on the sm_100a engine.
+
+Two surfaces:
+
+* ``train_epoch`` / ``eval_epoch`` keep the reference's signatures and loop structure
+  (one dataloader item per iteration, ``(inputs, sota, mask)`` tuples, a list of per-step losses
+  returned) so A1_train.py's ``train()`` can call them unchanged.
+* ``TrainStep`` / ``EvalStep`` are the batched fast path: the A1 slices are pointer offsets into the
+  dataloader tensor, the masks are synthesised in-kernel, loss + dLoss/dpred is one fused pass, the
+  gradients land in the flat arena (all-reduced per bucket under data parallelism) and Adam is one
+  kernel.  No autograd graph, no per-parameter Python work, no host synchronisation.
+"""
+import torch
+
+from . import _lib as K
+from .engine import make_mask
+from .euclidean_loss import EuclideanLoss, MSELoss, fused_loss
+from .optim import FlatAdam
+
+
+class TrainStep:
+    """fwd + loss + bwd + (all-reduce) + Adam for one batch laid out as the dataloader yields it:
+    inputs [B,T+1,K,2] (SOS + hold-filled frames), sota [B,T,K,2], mask [B,T+1] (A1_train.py:91-135).
+
+    criterion: "mse" (A1_train.py:254) or "euclid" (A4_train_with_pretrained.py:259).
+    zero_masked: A4_train_with_pretrained.py:107-108.  reducer: parallel.BucketReducer or None."""
+
+    def __init__(self, model, optimizer=None, criterion="mse", zero_masked=False, reducer=None, lr=5e-6):
+        self.model = model
+        self.optimizer = optimizer if optimizer is not None else FlatAdam(model, lr=lr)
+        self.kind = {"mse": K.LOSS_MSE, "euclid": K.LOSS_EUCLID}[criterion]
+        self.zero_masked = zero_masked
+        self.reducer = reducer
+        self.pred = None
+        self.last_launches = 0
+
+    def forward_backward(self, inputs, sota, mask):
+        model = self.model
+        B, T1 = inputs.shape[0], inputs.shape[1]
+        T = T1 - 1
+        K2 = inputs.shape[2] * inputs.shape[3]
+        assert inputs.is_cuda and inputs.dtype == torch.float32 and inputs.is_contiguous()
+        assert mask.dtype == torch.float32 and mask.is_contiguous() and sota.is_contiguous()
+        eng = model.engine_for(B, T, training=True)
+        grads = model.ensure_flat_grads()
+        x_dec = inputs[:, 1:]                                   # A1_train.py:94 -- a pointer offset
+        enc_mask = make_mask(mask[:, :-1], K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD)     # x_mask  (A1_train.py:99,117,121)
+        dec_mask = make_mask(mask[:, 1:], K.MASK_REPEAT_INC)                          # y_mask  (A1_train.py:100,118)
+        if self.pred is None or self.pred.shape != (B, T, K2 // 2, 2):
+            self.pred = torch.empty(B, T, K2 // 2, 2, device=inputs.device)
+        eng.forward(inputs, T1 * K2, x_dec, T1 * K2, enc_mask, dec_mask, self.pred, self.zero_masked)
+        loss, dpred = fused_loss(self.pred, sota, None, self.kind, want_grad=True)
+        grads.zero_()                                            # optimizer.zero_grad()  (A1_train.py:133)
+        if self.reducer is not None:
+            self.reducer.begin()
+            eng.backward(dpred, self.reducer.bucket_ready)
+            self.reducer.finish()
+        else:
+            eng.backward(dpred)
+        self.last_launches = eng.fwd_launches + eng.bwd_launches + 3
+        return loss
+
+    def __call__(self, inputs, sota, mask):
+        loss = self.forward_backward(inputs, sota, mask)
+        self.optimizer.step()                                    # A1_train.py:135
+        self.last_launches += 2                                  # adam + weight refresh at next forward
+        return loss
+
+
+class EvalStep:
+    """A1_train.py:149-186 batched: forward, blend pred*m + y*(1-m), EuclideanLoss -- masks and blend
+    fused into the kernels.  Returns (loss, pred_blended?)."""
+
+    def __init__(self, model, zero_masked=False):
+        self.model = model
+        self.zero_masked = zero_masked
+        self.pred = None
+
+    @torch.no_grad()
+    def __call__(self, inputs, sota, mask, blend_output=False):
+        model = self.model
+        B, T1 = inputs.shape[0], inputs.shape[1]
+        T = T1 - 1
+        K2 = inputs.shape[2] * inputs.shape[3]
+        eng = model.engine_for(B, T, training=False)
+        enc_mask = make_mask(mask[:, :-1], K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD)
+        dec_mask = make_mask(mask[:, 1:], K.MASK_REPEAT_INC)
+        if self.pred is None or self.pred.shape != (B, T, K2 // 2, 2):
+            self.pred = torch.empty(B, T, K2 // 2, 2, device=inputs.device)
+        eng.forward(inputs, T1 * K2, inputs[:, 1:], T1 * K2, enc_mask, dec_mask, self.pred, self.zero_masked)
+        y_mask = mask[:, 1:].contiguous()
+        loss, _ = fused_loss(self.pred, sota, y_mask, K.LOSS_EUCLID, want_grad=False)
+        if blend_output:
+            m = y_mask[:, :, None, None]
+            return loss, self.pred * m + sota * (1 - m)
+        return loss, self.pred
+
+
+# ---------------------------------------------------------------------------------------------
+# Reference-shaped epoch loops (A1_train.py:84-137, :139-218)
+# ---------------------------------------------------------------------------------------------
+def train_epoch(model, dataloader, criterion, optimizer, device):
+    """Same contract as A1_train.py:84: iterates ``dataloader`` yielding (inputs, sota, mask) with a
+    leading batch dimension (1 in the reference, any B here), returns the list of per-step losses
+    (numpy scalars).  With a ``FlatAdam`` optimizer the fused step runs; with any other
+    ``torch.optim`` optimizer the autograd-compatible module path runs, call for call like A1."""
+    model.train()
+    losses = []
+    fused = isinstance(optimizer, FlatAdam)
+    step = None
+    if fused:
+        kind = "euclid" if isinstance(criterion, EuclideanLoss) else "mse"
+        step = TrainStep(model, optimizer, criterion=kind)
+    for i, data in enumerate(dataloader):
+        inputs, sota, mask = data
+        inputs = inputs.to(device).float().contiguous()
+        sota = sota.to(device).float().contiguous()
+        mask = mask.to(device).float().contiguous()
+        if fused:
+            loss = step(inputs, sota, mask)
+        else:
+            x = inputs[:, :-1]
+            x_no_sota = inputs[:, 1:]
+            x_mask = mask[:, :-1]
+            y_mask = mask[:, 1:]
+            pred = model(x, x_no_sota, frame_masks=(x_mask, y_mask))
+            loss = criterion(pred, sota).float()
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+            model.mark_dirty()
+        losses.append(loss.clone().detach().cpu().numpy())
+    return losses
+
+
+def eval_epoch(model, dataloader, criterion, epoch, device):
+    """Same contract as A1_train.py:139 (losses list; the wandb/cubic extras stay caller-side)."""
+    model.eval()
+    losses = []
+    step = EvalStep(model)
+    last = None
+    for i, data in enumerate(dataloader):
+        inputs, sota, mask = data
+        inputs = inputs.to(device).float().contiguous()
+        sota = sota.to(device).float().contiguous()
+        mask = mask.to(device).float().contiguous()
+        if isinstance(criterion, EuclideanLoss):
+            loss, pred = step(inputs, sota, mask, blend_output=(i == 1))
+        else:
+            _, pred = step(inputs, sota, mask, blend_output=True)
+            loss = criterion(pred, sota)
+        losses.append(loss.clone().detach().cpu().numpy())
+        if i == 1:
+            x_mask = mask[:, :-1]
+            last = {"inputs": inputs[:, :-1] * (1 - x_mask)[:, :, None, None], "prediction": pred, "sota": sota,
+                    "epoch": epoch}
+    return losses, last
+
+
+def lr_lambda(current_step, lr, optim):
+    """A1_train.py:42-54: write the per-epoch learning rate into the optimiser."""
+    for group in optim.param_groups:
+        group["lr"] = lr[current_step]
+    return optim

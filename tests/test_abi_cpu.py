@@ -78,7 +78,7 @@ def test_invalid_config_is_an_error_not_a_fallback():
     assert lib.kit_layout_num_entries(C.byref(bad)) == -1
     assert b"hidden" in lib.kit_last_error()
     eng = C.c_void_p()
-    rc = lib.kit_engine_create(C.byref(K.KitModelConfig(142, 256, 6, 8, 2048, 2048)), 4, 4096, C.byref(eng))
+    rc = lib.kit_engine_create(C.byref(K.KitModelConfig(142, 256, 6, 8, 2048, 2048)), 4, 4096, 1, C.byref(eng))
     assert rc != 0 and b"positional table" in lib.kit_last_error()
     with pytest.raises(K.KitError):
         K.check(lib.kit_loss_fwd_bwd(None, None, None, 1, 1, 0, 1.0, None, None, None, None))

@@ -1,0 +1,168 @@
+"""Whole-step parity on the GPU: the drop-in module / fused train step against (a) golden outputs
+of the reference itself (tests/golden/*.npz) and (b) the CPU oracle on seeded synthetic batches.
+
+Tolerance (north_star): 2e-2 relative for the bf16 GEMM / attention path, measured as
+||got - ref|| / ||ref|| per tensor; masks bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from keypoints_interpolation_transformer_b200 import _lib as K
+from keypoints_interpolation_transformer_b200 import euclidean_loss, model, optim, train
+from oracle import kit_oracle as ko
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 2e-2
+
+
+def _rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+
+
+def _build(K2, H, L, NH):
+    m = model.KeypointCompleter(K2, H, L, NH)
+    m.load_state_dict(ko.deterministic_state_dict(K2, H, L))
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("name", ["completer_small_k54", "completer_small_k71", "completer_default_k54"])
+def test_train_step_matches_reference_golden(golden_dir, name):
+    g = _load(golden_dir, name)
+    Kp, H, L, NH, B, T = (int(g[k]) for k in ("K", "H", "L", "NH", "B", "T"))
+    m = _build(2 * Kp, H, L, NH)
+    m.train()
+    inputs, gt, mask = (torch.from_numpy(g[k]).to(DEV) for k in ("inputs", "gt", "mask"))
+    step = train.TrainStep(m, optim.FlatAdam(m, lr=0.0), criterion="mse")
+    loss = step.forward_backward(inputs, gt, mask)
+    torch.cuda.synchronize()
+    ref_pred = torch.from_numpy(g["pred"])
+    assert _rel(step.pred, ref_pred) < TOL
+    ref_loss = float(g["loss_mse"].mean())
+    assert abs(loss.item() - ref_loss) < TOL * abs(ref_loss)
+    # gradients of every parameter (norms) and the stored full tensors
+    names = [str(n) for n in g["grad_names"]]
+    got = {n: m.flat_grads[o:o + c].view(s) for n, (o, c, s) in zip(m._param_names, m._param_slices)}
+    tot_ref = float(np.sqrt((g["grad_norms"] ** 2).sum()))
+    tot_got = float(torch.sqrt(sum((got[n].double() ** 2).sum() for n in names)))
+    assert abs(tot_got - tot_ref) < TOL * tot_ref
+    bad = [(n, got[n].norm().item(), r) for n, r in zip(names, g["grad_norms"])
+           if abs(got[n].norm().item() - r) > 5e-2 * max(r, 1e-3 * tot_ref)]
+    assert not bad, bad[:5]
+    for key in g.files:
+        if key.startswith("grad::"):
+            n = key[6:]
+            assert _rel(got[n], torch.from_numpy(g[key])) < 5e-2, n
+    # eval protocol (A1_train.py:184-186) against the golden blended loss
+    m.eval()
+    ev_loss, _ = train.EvalStep(m)(inputs, gt, mask)
+    ref_eval = float(g["loss_euclid_eval"].mean())
+    assert abs(ev_loss.item() - ref_eval) < TOL * abs(ref_eval)
+
+
+def test_reference_call_surface_unbatched_explicit_masks(golden_dir):
+    """A1_train.py:117-124 call for call: get_mask tensors + float pad mask, one sequence."""
+    g = _load(golden_dir, "completer_small_k54")
+    Kp, H, L, NH, B, T = (int(g[k]) for k in ("K", "H", "L", "NH", "B", "T"))
+    m = _build(2 * Kp, H, L, NH)
+    m.eval()
+    inputs, gt, mask = (torch.from_numpy(g[k]).to(DEV) for k in ("inputs", "gt", "mask"))
+    with torch.no_grad():
+        batched = m(inputs[:, :-1], inputs[:, 1:], frame_masks=(mask[:, :-1], mask[:, 1:]))
+    for b in range(B):
+        x, xf = inputs[b, :-1], inputs[b, 1:]
+        x_mask, y_mask = mask[b, :-1].clone(), mask[b, 1:].clone()
+        src_mask = m.get_mask(x_mask, T, "repeat-inc").to(DEV)
+        tgt_mask = m.get_mask(y_mask, T, "repeat-inc").to(DEV)
+        assert torch.equal(src_mask.cpu(), ko.get_mask(x_mask.cpu(), T, "repeat-inc"))      # bit exact
+        with torch.no_grad():
+            pred = m(x, xf, src_pad_mask=x_mask.unsqueeze(0), tgt_pad_mask=y_mask.unsqueeze(0),
+                     src_mask=src_mask, tgt_mask=tgt_mask)
+        assert pred.shape == (T, Kp, 2)
+        assert _rel(pred, torch.from_numpy(g["pred"][b])) < TOL
+        assert (pred - batched[b]).abs().max().item() < 2e-2      # same kernels, different batch size / mask source
+
+
+def test_autograd_path_matches_fused_step():
+    Kp, H, L, NH, B, T = 54, 64, 2, 4, 4, 20
+    m = _build(2 * Kp, H, L, NH)
+    m.train()
+    inputs, gt, mask = (t.to(DEV) for t in ko.synthetic_batch(B, T, Kp, seed=7))
+    step = train.TrainStep(m, optim.FlatAdam(m, lr=0.0), criterion="euclid")
+    loss_f = step.forward_backward(inputs, gt, mask)
+    fused = m.flat_grads.clone()
+    m.zero_grad(set_to_none=True)
+    pred = m(inputs[:, :-1], inputs[:, 1:], frame_masks=(mask[:, :-1], mask[:, 1:]))
+    loss = euclidean_loss.EuclideanLoss()(pred, gt)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_f.item()) < 1e-5 * abs(loss.item())
+    for (n, p), (o, c, s) in zip(m.named_parameters(), m._param_slices):
+        assert p.grad is not None and p.grad.shape == p.shape, n
+        ref = fused[o:o + c].view(s)
+        assert (p.grad - ref).norm().item() <= 1e-3 * ref.norm().item() + 1e-7, n   # atomics reorder only
+    # torch.optim.Adam on the views == FlatAdam on the arena
+    before = m.flat_params.clone()
+    torch.optim.Adam(m.parameters(), lr=1e-3).step()
+    after_torch = m.flat_params.clone()
+    m.flat_params.copy_(before)
+    m.flat_grads.copy_(fused)
+    flat = optim.FlatAdam(m, lr=1e-3)
+    flat.step()
+    torch.cuda.synchronize()
+    n = m.layout.trainable
+    assert (m.flat_params[:n] - after_torch[:n]).abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("Kp,B,T", [(71, 8, 64), (54, 3, 100)])
+def test_default_model_matches_oracle(Kp, B, T):
+    """BASELINE config shape (T=64, K=71, default dims) at a batch the CPU oracle finishes in seconds."""
+    H, L, NH = 256, 6, 8
+    m = _build(2 * Kp, H, L, NH)
+    m.train()
+    inputs, gt, mask = ko.synthetic_batch(B, T, Kp, seed=42)
+    sd = ko.deterministic_state_dict(2 * Kp, H, L)
+    params = {k: v.clone().requires_grad_(not k.endswith("pos_encoding")) for k, v in sd.items()}
+    ref_loss, ref_pred = ko.train_forward_loss(params, inputs, gt, mask, NH, criterion="mse")
+    ref_loss.backward()
+    step = train.TrainStep(m, optim.FlatAdam(m, lr=0.0), criterion="mse")
+    loss = step.forward_backward(inputs.to(DEV), gt.to(DEV), mask.to(DEV))
+    torch.cuda.synchronize()
+    assert _rel(step.pred, ref_pred) < TOL
+    assert abs(loss.item() - ref_loss.item()) < TOL * abs(ref_loss.item())
+    num = den = 0.0
+    worst = (0.0, "")
+    for n, (o, c, s) in zip(m._param_names, m._param_slices):
+        gr = params[n].grad
+        got = m.flat_grads[o:o + c].view(s).cpu()
+        num += float(((got - gr).double() ** 2).sum())
+        den += float((gr.double() ** 2).sum())
+        r = ((got - gr).norm() / gr.norm().clamp_min(1e-9)).item()
+        if r > worst[0] and gr.norm().item() > 1e-3 * den ** 0.5:
+            worst = (r, n)
+    assert (num / den) ** 0.5 < TOL, ((num / den) ** 0.5, worst)
+    assert worst[0] < 6e-2, worst
+    # interpolation-MSE parity on the masked frames (A1_train.py:184-186)
+    m.eval()
+    ev_loss, _ = train.EvalStep(m)(inputs.to(DEV), gt.to(DEV), mask.to(DEV))
+    with torch.no_grad():
+        ref_eval, _ = ko.eval_forward_loss(sd, inputs, gt, mask, NH)
+    assert abs(ev_loss.item() - ref_eval.item()) < TOL * abs(ref_eval.item())
+
+
+def test_adam_updates_match_torch_over_steps():
+    Kp, H, L, NH, B, T = 54, 64, 2, 4, 4, 16
+    m = _build(2 * Kp, H, L, NH)
+    m.train()
+    inputs, gt, mask = (t.to(DEV) for t in ko.synthetic_batch(B, T, Kp, seed=3))
+    step = train.TrainStep(m, optim.FlatAdam(m, lr=1e-3), criterion="mse")
+    losses = [step(inputs, gt, mask).item() for _ in range(8)]
+    assert losses[-1] < losses[0]          # it trains
+    assert all(np.isfinite(losses))
