@@ -125,6 +125,16 @@ int kit_engine_backward(KitEngine* e, const float* dpred, KitBucketCallback buck
 int kit_engine_debug_read(KitEngine* e, const char* name, float* out, int64_t out_floats, void* stream);
 /* Number of kernels the last forward / backward call launched (bench.py's gpu_launches). */
 int64_t kit_engine_last_launches(const KitEngine* e);
+/* Per-category CUDA-event timing of the engine's own launches (bench.py's roofline leg).  Counters are
+ * reset by kit_engine_forward and accumulate over the following backward; profile_read synchronises
+ * on the recorded events.  flops = algorithmic FLOPs of that category's launches (2MNK per GEMM). */
+#define KIT_PROF_GEMM_TN 0
+#define KIT_PROF_GEMM_WGRAD 1
+#define KIT_PROF_ATTN_FWD 2
+#define KIT_PROF_ATTN_BWD 3
+#define KIT_PROF_CATEGORIES 4
+int kit_engine_set_profiling(KitEngine* e, int32_t on);
+int kit_engine_profile_read(KitEngine* e, int32_t category, float* ms, int64_t* launches, double* flops);
 
 /* ------------------------------------------------------------------------------------------
  * Fused per-frame passes (HBM-bound)

@@ -65,6 +65,8 @@ _SIGNATURES = {
     "kit_engine_backward": (C.c_int, [_P, _P, _P, _P, _P]),
     "kit_engine_debug_read": (C.c_int, [_P, C.c_char_p, _P, _I64, _P]),
     "kit_engine_last_launches": (_I64, [_P]),
+    "kit_engine_set_profiling": (C.c_int, [_P, _I32]),
+    "kit_engine_profile_read": (C.c_int, [_P, _I32, C.POINTER(C.c_float), C.POINTER(_I64), C.POINTER(C.c_double)]),
     "kit_prepass": (C.c_int, [C.POINTER(KitPrepassConfig), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "kit_loss_partials": (_I64, [_I64, _I32]),
     "kit_loss_fwd_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P]),

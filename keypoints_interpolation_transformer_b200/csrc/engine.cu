@@ -220,6 +220,14 @@ struct KitEngine {
   std::vector<GemmPlan>* active = nullptr;
   int64_t launches = 0;
   cudaStream_t st = nullptr;
+  // optional per-category CUDA-event profiling (bench.py roofline leg)
+  bool profiling = false;
+  struct ProfRec { int cat; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  size_t ev_used = 0;
+  double cat_flops[KIT_PROF_CATEGORIES] = {0};
+  int64_t cat_launches[KIT_PROF_CATEGORIES] = {0};
   // saved masks (backward reuses the forward's)
   KitAttnMask enc_mask{}, dec_mask{};
   // resolved pointers
@@ -329,6 +337,33 @@ static void resolve_pointers(KitEngine* e) {
   }
 }
 
+static void prof_begin(KitEngine* e, int cat, double flops) {
+  e->cat_launches[cat]++;
+  e->cat_flops[cat] += flops;
+  if (!e->profiling) return;
+  if (e->ev_used >= e->ev_pool.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    e->ev_pool.push_back({a, b});
+  }
+  auto& ev = e->ev_pool[e->ev_used++];
+  e->prof.push_back({cat, ev.first, ev.second});
+  cudaEventRecord(ev.first, e->st);
+}
+static void prof_end(KitEngine* e) {
+  if (!e->profiling) return;
+  cudaEventRecord(e->prof.back().b, e->st);
+}
+static void prof_reset(KitEngine* e) {
+  e->prof.clear();
+  e->ev_used = 0;
+  for (int i = 0; i < KIT_PROF_CATEGORIES; ++i) {
+    e->cat_flops[i] = 0;
+    e->cat_launches[i] = 0;
+  }
+}
+
 // GEMM through the per-engine plan cache (tensor maps are built once per call site).
 static int eg(KitEngine* e, int mode, const bf16* A, int64_t lda, const bf16* Bm, int64_t ldb, void* C, int64_t ldc, int M,
               int N, int K, const float* bias, const bf16* addend, int64_t ld_add, int out_kind, int act, bf16* aux,
@@ -344,7 +379,31 @@ static int eg(KitEngine* e, int mode, const bf16* A, int64_t lda, const bf16* Bm
   GemmPlan& p = plans[e->cursor++];
   p.p.C = C;  // the only pointer that may change between calls (pred / grads are caller memory)
   e->launches++;
-  return gemm_launch(&p, e->st);
+  prof_begin(e, mode == 0 ? KIT_PROF_GEMM_TN : KIT_PROF_GEMM_WGRAD, 2.0 * (double)M * (double)N * (double)K);
+  const int rc = gemm_launch(&p, e->st);
+  prof_end(e);
+  return rc;
+}
+// attention through the profiler: 4*S*S*d flops per head forward, 10*S*S*d backward
+static int eattn_fwd(KitEngine* e, const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv,
+                     bf16* out, int64_t ldo, float* lse, const KitAttnMask* mask) {
+  const int H = e->L.cfg.hidden, NH = e->L.cfg.heads, d = H / NH;
+  e->launches++;
+  prof_begin(e, KIT_PROF_ATTN_FWD, 4.0 * e->B * NH * (double)e->T * e->T * d);
+  const int rc = attention_fwd(q, ldq, k, ldk, v, ldv, out, ldo, lse, e->B, NH, e->T, e->T, d, mask, e->st);
+  prof_end(e);
+  return rc;
+}
+static int eattn_bwd(KitEngine* e, const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv,
+                     const bf16* o, int64_t ldo, const bf16* dout, int64_t ld_do, const float* lse, bf16* dq, int64_t ld_dq,
+                     bf16* dk, int64_t ld_dk, bf16* dv, int64_t ld_dv, const KitAttnMask* mask) {
+  const int H = e->L.cfg.hidden, NH = e->L.cfg.heads, d = H / NH;
+  e->launches += 2;
+  prof_begin(e, KIT_PROF_ATTN_BWD, 10.0 * e->B * NH * (double)e->T * e->T * d);
+  const int rc = attention_bwd(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq, dk, ld_dk, dv, ld_dv, e->B, NH,
+                               e->T, e->T, d, mask, e->st);
+  prof_end(e);
+  return rc;
 }
 #define KIT_TRY(x)      \
   do {                  \
@@ -402,6 +461,7 @@ static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const f
   e->active = &e->fwd_plans;
   e->cursor = 0;
   e->launches = 0;
+  prof_reset(e);
   e->enc_mask = em ? *em : KitAttnMask{};
   e->dec_mask = dm ? *dm : KitAttnMask{};
   const float* zm = (zero_masked && em) ? em->frame_mask : nullptr;
@@ -425,8 +485,7 @@ static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const f
     const EncW& w = L.enc[l];
     EncAct& a = e->ea[l];
     KIT_TRY(linear_fwd(e, x, H, w.sa.in, 0, 3 * H, a.qkv, 3 * H, nullptr, 0));
-    e->launches++;
-    KIT_TRY(attention_fwd(a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, a.lse, B, NH, T, T, d, &e->enc_mask, e->st));
+    KIT_TRY(eattn_fwd(e, a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, a.lse, &e->enc_mask));
     KIT_TRY(linear_fwd(e, a.ao, H, w.sa.out, 0, H, a.s1, H, x, H));
     e->launches++;
     KIT_TRY(add_ln_fwd(a.s1, nullptr, e->params + w.n1.g, e->params + w.n1.b, nullptr, a.x1, a.st1, a.st1 + M, M, H, e->st));
@@ -445,15 +504,13 @@ static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const f
     const DecW& w = L.dec[l];
     DecAct& a = e->da[l];
     KIT_TRY(linear_fwd(e, y, H, w.sa.in, 0, 3 * H, a.qkv, 3 * H, nullptr, 0));
-    e->launches++;
-    KIT_TRY(attention_fwd(a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, a.lse, B, NH, T, T, d, &e->dec_mask, e->st));
+    KIT_TRY(eattn_fwd(e, a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, a.lse, &e->dec_mask));
     KIT_TRY(linear_fwd(e, a.ao, H, w.sa.out, 0, H, a.s1, H, y, H));
     e->launches++;
     KIT_TRY(add_ln_fwd(a.s1, nullptr, e->params + w.n1.g, e->params + w.n1.b, nullptr, a.y1, a.st1, a.st1 + M, M, H, e->st));
     KIT_TRY(linear_fwd(e, a.y1, H, w.ca.in, 0, H, a.qc, H, nullptr, 0));
     KIT_TRY(linear_fwd(e, e->mem, H, w.ca.in, H, 2 * H, a.kvc, 2 * H, nullptr, 0));
-    e->launches++;
-    KIT_TRY(attention_fwd(a.qc, H, a.kvc, 2 * H, a.kvc + H, 2 * H, a.aoc, H, a.lsec, B, NH, T, T, d, nullptr, e->st));
+    KIT_TRY(eattn_fwd(e, a.qc, H, a.kvc, 2 * H, a.kvc + H, 2 * H, a.aoc, H, a.lsec, nullptr));
     KIT_TRY(linear_fwd(e, a.aoc, H, w.ca.out, 0, H, a.s2, H, a.y1, H));
     e->launches++;
     KIT_TRY(add_ln_fwd(a.s2, nullptr, e->params + w.n2.g, e->params + w.n2.b, nullptr, a.y2, a.st2, a.st2 + M, M, H, e->st));
@@ -519,9 +576,8 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
     KIT_TRY(ln_bwd(e->g2, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1, e->grads + w.n2.g, e->grads + w.n2.b, M, H, e->st));
     KIT_TRY(linear_wgrad(e, e->g1, H, a.aoc, H, w.ca.out, 0, H));
     KIT_TRY(linear_dgrad(e, e->g1, H, w.ca.out, 0, H, e->g2, H, nullptr, 0));  // g2 = d aoc
-    e->launches += 2;
-    KIT_TRY(attention_bwd(a.qc, H, a.kvc, 2 * H, a.kvc + H, 2 * H, a.aoc, H, e->g2, H, a.lsec, e->gqkv, H, e->gkv, 2 * H,
-                          e->gkv + H, 2 * H, B, NH, T, T, d, nullptr, e->st));  // gqkv used as [M,H] dq
+    KIT_TRY(eattn_bwd(e, a.qc, H, a.kvc, 2 * H, a.kvc + H, 2 * H, a.aoc, H, e->g2, H, a.lsec, e->gqkv, H, e->gkv, 2 * H,
+                      e->gkv + H, 2 * H, nullptr));  // gqkv used as [M,H] dq
     KIT_TRY(linear_wgrad(e, e->gqkv, H, a.y1, H, w.ca.in, 0, H));
     KIT_TRY(linear_wgrad(e, e->gkv, 2 * H, e->mem, H, w.ca.in, H, 2 * H));
     KIT_TRY(linear_dgrad(e, e->gkv, 2 * H, w.ca.in, H, 2 * H, e->gmem, H, mem_grad_started ? e->gmem : nullptr, H));
@@ -532,9 +588,8 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
     KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1, e->grads + w.n1.g, e->grads + w.n1.b, M, H, e->st));
     KIT_TRY(linear_wgrad(e, e->g1, H, a.ao, H, w.sa.out, 0, H));
     KIT_TRY(linear_dgrad(e, e->g1, H, w.sa.out, 0, H, e->g2, H, nullptr, 0));  // g2 = d ao
-    e->launches += 2;
-    KIT_TRY(attention_bwd(a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, e->g2, H, a.lse, e->gqkv, 3 * H,
-                          e->gqkv + H, 3 * H, e->gqkv + 2 * H, 3 * H, B, NH, T, T, d, &e->dec_mask, e->st));
+    KIT_TRY(eattn_bwd(e, a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, e->g2, H, a.lse, e->gqkv, 3 * H,
+                      e->gqkv + H, 3 * H, e->gqkv + 2 * H, 3 * H, &e->dec_mask));
     KIT_TRY(linear_wgrad(e, e->gqkv, 3 * H, y_in, H, w.sa.in, 0, 3 * H));
     KIT_TRY(linear_dgrad(e, e->gqkv, 3 * H, w.sa.in, 0, 3 * H, e->g0, H, e->g1, H));  // g0 = d y_in
     dy = e->g0;
@@ -568,9 +623,8 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
     KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1, e->grads + w.n1.g, e->grads + w.n1.b, M, H, e->st));
     KIT_TRY(linear_wgrad(e, e->g1, H, a.ao, H, w.sa.out, 0, H));
     KIT_TRY(linear_dgrad(e, e->g1, H, w.sa.out, 0, H, e->g2, H, nullptr, 0));
-    e->launches += 2;
-    KIT_TRY(attention_bwd(a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, e->g2, H, a.lse, e->gqkv, 3 * H,
-                          e->gqkv + H, 3 * H, e->gqkv + 2 * H, 3 * H, B, NH, T, T, d, &e->enc_mask, e->st));
+    KIT_TRY(eattn_bwd(e, a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, e->g2, H, a.lse, e->gqkv, 3 * H,
+                      e->gqkv + H, 3 * H, e->gqkv + 2 * H, 3 * H, &e->enc_mask));
     KIT_TRY(linear_wgrad(e, e->gqkv, 3 * H, x_in, H, w.sa.in, 0, 3 * H));
     KIT_TRY(linear_dgrad(e, e->gqkv, 3 * H, w.sa.in, 0, 3 * H, e->g0, H, e->g1, H));
     dx = e->g0;
@@ -737,6 +791,27 @@ extern "C" int kit_engine_debug_read(KitEngine* e, const char* name, float* out,
   return KIT_OK;
 }
 extern "C" int64_t kit_engine_last_launches(const KitEngine* e) { return e ? e->launches : -1; }
+
+extern "C" int kit_engine_set_profiling(KitEngine* e, int32_t on) {
+  KIT_REQUIRE(e != nullptr, "kit_engine_set_profiling: null engine");
+  e->profiling = on != 0;
+  return KIT_OK;
+}
+extern "C" int kit_engine_profile_read(KitEngine* e, int32_t category, float* ms, int64_t* launches, double* flops) {
+  KIT_REQUIRE(e != nullptr && category >= 0 && category < KIT_PROF_CATEGORIES, "kit_engine_profile_read: bad arguments");
+  float total = 0.f;
+  for (const auto& r : e->prof) {
+    if (r.cat != category) continue;
+    KIT_CHECK_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    KIT_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    total += t;
+  }
+  if (ms) *ms = total;
+  if (launches) *launches = e->cat_launches[category];
+  if (flops) *flops = e->cat_flops[category];
+  return KIT_OK;
+}
 
 extern "C" int kit_gemm_bf16(int32_t mode, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                              int32_t M, int32_t N, int32_t K, const float* bias, const void* addend, int64_t ld_addend,

@@ -109,6 +109,20 @@ class StepEngine:
         K.check(K.lib().kit_engine_backward(self._h, K.ptr(dpred), cb, None, K.stream_ptr()))
         self.bwd_launches = K.lib().kit_engine_last_launches(self._h)
 
+    PROF_CATEGORIES = ("gemm_tn", "gemm_wgrad", "attn_fwd", "attn_bwd")
+
+    def set_profiling(self, on):
+        K.check(K.lib().kit_engine_set_profiling(self._h, 1 if on else 0))
+
+    def profile(self):
+        """{category: (ms, launches, flops)} of the last forward (+ backward); synchronises."""
+        out = {}
+        for i, name in enumerate(self.PROF_CATEGORIES):
+            ms, n, fl = C.c_float(), C.c_int64(), C.c_double()
+            K.check(K.lib().kit_engine_profile_read(self._h, i, C.byref(ms), C.byref(n), C.byref(fl)))
+            out[name] = (ms.value, n.value, fl.value)
+        return out
+
     def debug_read(self, name):
         lib = K.lib()
         out = torch.empty(self.workspace.numel() // 2 if False else self._buf_elems(name), device=self.params.device)
