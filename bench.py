@@ -54,7 +54,7 @@ def cpu_reference_run(steps, warmup, batch=CPU_SAMPLE_B):
         loss, _ = ko.train_forward_loss(params, inputs, gt, mask, NH, criterion="mse")
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(warmup):
         step()
@@ -228,7 +228,7 @@ def gpu_run(args):
     seqs = B_PER_GPU * world * args.steps
     value = seqs / (ms * 1e-3)
     e2e = seqs / (ms_e2e * 1e-3)
-    cpu = cpu_reference_run(steps=2, warmup=1) if world == 1 else None
+    cpu = cpu_reference_run(steps=2, warmup=1) if (world == 1 and not args.no_cpu_baseline) else None
     breakdown = {k: {"ms_per_step": v[0] / prof_steps, "launches_per_step": v[1] // prof_steps,
                      "tflops": (v[2] / (v[0] * 1e-3) / 1e12) if v[0] > 0 else None} for k, v in acc.items()}
     line = {
@@ -267,6 +267,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="kit", choices=["kit", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":          # rank 0 alone runs it; other ranks exit 0 without work
