@@ -1,0 +1,191 @@
+"""GPU parity of the HBM-bound per-frame passes (pre-pass, loss, get_mask, Adam) against the
+reference-generated golden fixtures and the CPU oracle.  fp32 elementwise tolerance 1e-5 relative;
+masks, indices, zero patterns and hold-fill copies bit-exact."""
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from keypoints_interpolation_transformer_b200 import _lib as K
+from keypoints_interpolation_transformer_b200 import augmentation, dataloader, euclidean_loss, model, optim
+from keypoints_interpolation_transformer_b200 import preprocess as PP
+from oracle import kit_oracle as ko
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=False)
+
+
+def test_normalize_pose_matches_reference(golden_dir):
+    g = _load(golden_dir, "normalize_pose")
+    ls, rs, re = (int(v) for v in g["ids"])
+    body = {"pose_left_shoulder": ls, "pose_right_shoulder": rs, "pose_right_eye": re}
+    for n in range(3):
+        data = g[f"in{n}"].copy()
+        out = dataloader.normalize_pose(data, body)
+        assert out is data                                    # in place, like the reference
+        ref = g[f"out{n}"]
+        assert np.array_equal(out == 0, ref == 0)
+        np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-7)
+
+
+def test_augmentations_match_reference(golden_dir):
+    g = _load(golden_dir, "augmentation")
+    ids = {"pose": list(g["pose"]), "left_hand": list(g["left_hand"]), "rigth_hand": list(g["right_hand"])}
+    body = {"pose_chest_middle_up": 0, "pose_left_shoulder": 5, "pose_left_elbow": 7, "pose_left_wrist": 9,
+            "pose_right_shoulder": 6, "pose_right_elbow": 8, "pose_right_wrist": 10}
+    aug = augmentation.augmentation(ids, body)
+    assert np.array_equal(np.array(aug.ARM_IDENTIFIERS_ORDER), g["arm_chains"])
+    base = g["base"]
+    for n in range(3):
+        random.seed(100 + n)
+        s = torch.from_numpy(base.copy())
+        out = aug.augment_rotate(s, (-15, 15))
+        assert out is s
+        np.testing.assert_allclose(out.numpy(), g[f"rotate{n}"], rtol=1e-5, atol=1e-6)
+        random.seed(200 + n)
+        out = aug.augment_shear(torch.from_numpy(base.copy()), "squeeze", (-0.15, 0.15)).numpy()
+        np.testing.assert_allclose(out, g[f"squeeze{n}"], rtol=1e-5, atol=1e-6)
+        assert np.array_equal(out == 0, g[f"squeeze{n}"] == 0)
+        random.seed(300 + n)
+        out = aug.augment_shear(torch.from_numpy(base.copy()), "perspective", (-0.15, 0.15)).numpy()
+        np.testing.assert_allclose(out, g[f"persp{n}"], rtol=1e-5, atol=1e-6)
+        assert np.array_equal(out == 0, g[f"persp{n}"] == 0)
+        random.seed(400 + n)
+        out = aug.augment_arm_joint_rotate(torch.from_numpy(base.copy()), 0.5, (-15, 15)).numpy()
+        np.testing.assert_allclose(out, g[f"arm{n}"], rtol=1e-5, atol=1e-6)
+
+
+def test_put_missing_frames_and_sos_bit_exact(golden_dir):
+    g = _load(golden_dir, "missing_frames")
+    for n in range(int(g["count"])):
+        T, seed = (int(v) for v in g[f"meta{n}"])
+        random.seed(seed)
+        np.random.seed(seed)
+        video = torch.arange(T, dtype=torch.float32).view(T, 1, 1).repeat(1, 3, 2).clone()
+        v2, mask = dataloader.put_missing_frames(video, False, str(g[f"ds{n}"]))
+        assert v2 is video
+        assert np.array_equal(v2[:, 0, 0].numpy().astype(np.int32), g[f"src{n}"])
+        assert np.array_equal(mask.cpu().numpy(), g[f"mask{n}"])
+        v3, m3 = dataloader.add_sos(v2, mask.cpu())
+        assert np.array_equal(v3.numpy(), g[f"sos_video{n}"])
+        assert np.array_equal(m3.numpy(), g[f"sos_mask{n}"])
+    random.seed(77)
+    video = (1 + torch.arange(30, dtype=torch.float32)).view(30, 1, 1).repeat(1, 2, 2).clone()
+    v2, mask = dataloader.put_missing_frames(video, True, "AUTSL")
+    assert np.array_equal(v2.numpy(), g["rand_video"])
+    assert np.array_equal(mask.cpu().numpy(), g["rand_mask"])
+
+
+@pytest.mark.parametrize("B,T,Kp,zero_masked", [(5, 64, 71, False), (3, 33, 54, True), (2, 256, 71, True)])
+def test_fused_prepass_slices_and_bf16_operands(B, T, Kp, zero_masked):
+    """The whole pre-pass against the oracle: hold-fill + SOS + A1 slices (+ A4 zeroing), bit exact."""
+    rs = np.random.RandomState(B * T)
+    raw = rs.uniform(0.05, 0.95, size=(B, T, Kp, 2)).astype(np.float32)
+    raw[rs.uniform(size=(B, T, Kp)) < 0.03] = 0.0
+    pr = random.Random(5)
+    src = np.empty((B, T), np.int32)
+    msk = np.empty((B, T), np.float32)
+    for b in range(B):
+        blocks = ko.missing_blocks_from_config(T, ko.AUTSL_CONFIG, rng=pr, nprng=rs)
+        src[b], msk[b] = ko.hold_fill_sources(T, blocks)
+    pp = PP.Prepass(Kp, DEV)
+    res = pp(torch.from_numpy(raw), torch.from_numpy(src), torch.from_numpy(msk), zero_masked_enc=zero_masked, want_bf16=True)
+    torch.cuda.synchronize()
+    assert torch.equal(res["y"].cpu(), torch.from_numpy(raw))
+    k2p = pp.k2p
+    for b in range(B):
+        ref_in, ref_mask = ko.apply_sources_add_sos(raw[b], src[b], msk[b])
+        assert np.array_equal(res["inputs"][b].cpu().numpy(), ref_in)
+        assert np.array_equal(res["mask"][b].cpu().numpy(), ref_mask)
+        x, xf, _, xm, _ = ko.step_slices(torch.from_numpy(ref_in)[None], torch.from_numpy(raw[b])[None],
+                                         torch.from_numpy(ref_mask)[None], zero_masked=zero_masked)
+        xe = res["x_enc"].view(B, T, k2p)[b].float().cpu()
+        xd = res["x_dec"].view(B, T, k2p)[b].float().cpu()
+        assert torch.equal(xe[:, :2 * Kp], x[0].reshape(T, 2 * Kp).to(torch.bfloat16).float())
+        assert torch.equal(xd[:, :2 * Kp], xf[0].reshape(T, 2 * Kp).to(torch.bfloat16).float())
+        assert (xe[:, 2 * Kp:] == 0).all() and (xd[:, 2 * Kp:] == 0).all()
+
+
+def test_get_mask_bit_exact(golden_dir):
+    g = _load(golden_dir, "get_mask")
+    m = model.KeypointCompleter(108, 64, 1, 4)
+    for n, T in enumerate([1, 2, 7, 16, 33]):
+        fm = torch.from_numpy(g[f"mask{n}"])
+        for typ in ["triangle", "repeat", "repeat-inc", "all"]:
+            key = f"{typ}{n}"
+            if key not in g.files:
+                continue
+            for dev in ("cpu", DEV):
+                got = m.get_mask(fm.to(dev), T, typ).cpu().numpy()
+                assert got.shape == g[key].shape and np.array_equal(got, g[key]), (key, dev)
+
+
+def test_loss_matches_reference_and_is_deterministic(golden_dir):
+    g = _load(golden_dir, "loss")
+    o = torch.from_numpy(g["o"]).to(DEV).requires_grad_(True)
+    t = torch.from_numpy(g["t"]).to(DEV)
+    loss = euclidean_loss.EuclideanLoss()(o, t)
+    assert loss.dim() == 0
+    assert abs(loss.item() - float(g["euclid"])) <= 1e-5 * float(g["euclid"])
+    (loss * 3.0).backward()
+    ref = o.detach().clone().requires_grad_(True)
+    (ko.euclidean_loss(ref, t) * 3.0).backward()
+    assert torch.allclose(o.grad, ref.grad, rtol=1e-5, atol=1e-9)
+    mse = euclidean_loss.MSELoss()(o.detach(), t)
+    assert abs(mse.item() - float(g["mse"])) <= 1e-5 * float(g["mse"])
+    again = euclidean_loss.EuclideanLoss()(o.detach(), t)
+    assert again.item() == loss.item()                       # fixed reduction order
+    # A1 usage: .float(), .clone().detach().cpu().numpy()
+    assert np.isfinite(loss.float().clone().detach().cpu().numpy())
+    # eval blend (A1_train.py:184-186)
+    fm = (torch.rand(3, 17, device=DEV) < 0.4).float()
+    got = euclidean_loss.MaskedEuclideanLoss()(o.detach(), t, fm)
+    want = ko.euclidean_loss(ko.eval_blend(o.detach().cpu(), t.cpu(), fm.cpu()), t.cpu())
+    assert abs(got.item() - want.item()) <= 1e-5 * want.item()
+    d = euclidean_loss.EuclideanDistanceLoss()(o.detach()[0], t[0])
+    assert abs(d.item() - float(g["euclid_dist"])) <= 1e-5 * float(g["euclid_dist"])
+
+
+def test_loss_at_baseline_inference_size_properties():
+    """BASELINE config 4 size (B=4096, T=256, K=71): size-independent properties."""
+    B, T, Kp = 4096, 256, 71
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    p = torch.rand(B, T, Kp, 2, device=DEV, generator=gen)
+    t = torch.rand(B, T, Kp, 2, device=DEV, generator=gen)
+    l1, d1 = euclidean_loss.fused_loss(p, t)
+    l0, _ = euclidean_loss.fused_loss(p, p)
+    assert l0.item() == 0.0
+    ref = ((p - t) ** 2).sum(-1).mean()
+    assert abs(l1.item() - ref.item()) <= 1e-5 * ref.item()
+    assert torch.allclose(d1, 2 * (p - t) / (B * T * Kp), rtol=1e-5, atol=1e-12)
+    fm = (torch.rand(B, T, device=DEV, generator=gen) < 0.3).float()
+    lm, dm = euclidean_loss.fused_loss(p, t, fm)
+    lc, _ = euclidean_loss.fused_loss(p, t, 1 - fm)
+    assert abs(lm.item() + lc.item() - l1.item()) <= 1e-5 * l1.item()        # masked + complement = total
+    assert (dm[fm == 0] == 0).all()
+
+
+def test_flat_adam_matches_torch_adam():
+    n = 4096 * 3
+    gen = torch.Generator(device="cpu").manual_seed(1)
+    p0 = torch.randn(n, generator=gen)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=3e-4)
+    p = p0.clone().to(DEV)
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    for step in range(1, 6):
+        gsrc = torch.randn(n, generator=gen)
+        ref.grad = gsrc.clone()
+        opt.step()
+        K.check(K.lib().kit_adam_step(K.ptr(p), K.ptr(gsrc.to(DEV)), K.ptr(m), K.ptr(v), n, 3e-4, 0.9, 0.999, 1e-8, step,
+                                      1.0, K.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.allclose(p.cpu(), ref.detach(), rtol=1e-5, atol=1e-7)
