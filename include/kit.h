@@ -206,10 +206,11 @@ int kit_gemm_bf16(int32_t mode, const void* A, int64_t lda, const void* B, int64
 int kit_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                       int64_t ldo, float* lse, int32_t B, int32_t NH, int32_t Sq, int32_t Sk, int32_t d,
                       const KitAttnMask* mask, void* stream);
+/* dq_accum: fp32 workspace [B*Sq, NH*d], required only when Sk > 64 (dQ summed over key tiles). */
 int kit_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                       const void* out, int64_t ldo, const void* dout, int64_t ld_do, const float* lse, void* dq,
-                      int64_t ld_dq, void* dk, int64_t ld_dk, void* dv, int64_t ld_dv, int32_t B, int32_t NH,
-                      int32_t Sq, int32_t Sk, int32_t d, const KitAttnMask* mask, void* stream);
+                      int64_t ld_dq, void* dk, int64_t ld_dk, void* dv, int64_t ld_dv, float* dq_accum, int32_t B,
+                      int32_t NH, int32_t Sq, int32_t Sk, int32_t d, const KitAttnMask* mask, void* stream);
 
 /* Row kernels over [M,H] bf16 (H multiple of 8, <= 1024).  See csrc/rowops.cu. */
 int kit_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* sum_out,

@@ -77,7 +77,7 @@ _SIGNATURES = {
     "kit_attention_fwd": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I32, _I32, _I32, _I32, _I32,
                                     C.POINTER(KitAttnMask), _P]),
     "kit_attention_bwd": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _P, _I64,
-                                    _I32, _I32, _I32, _I32, _I32, C.POINTER(KitAttnMask), _P]),
+                                    _P, _I32, _I32, _I32, _I32, _I32, C.POINTER(KitAttnMask), _P]),
     "kit_add_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "kit_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "kit_cast_fp32_to_bf16_padded": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _P]),

@@ -1,17 +1,17 @@
 // softmax(Q K^T / sqrt(d) + mask) V, forward and backward, with the attention masks of the
 // reference synthesised in-kernel from the [B,T] frame mask (model.py:193-202 "repeat-inc",
 // A1_train.py:121 float key-padding mask that PyTorch ADDS to the logits) so that no [B*NH,S,S]
-// tensor ever exists.  Flash-style tiling: 64 queries x 64 keys per step, online softmax, fp32
-// math on bf16 operands; the backward recomputes P from the saved log-sum-exp.
-//
-// v1: CUDA-core tiles (the attention matmuls are 3 % of the step's FLOPs at T=64).
+// tensor ever exists.  Flash-style: 64 queries x 64 keys per step, online softmax in fp32, bf16
+// operands on the tensor cores (warp-level mma.sync m16n8k16 -- the per-head problems are
+// 64x64x32, far below one tcgen05 tile; the kernels are bound by operand traffic and softmax ALU).
+// The backward recomputes P from the saved log-sum-exp and works on the TRANSPOSED score tile
+// (keys as MMA rows) so that dK/dV are warp-private and only dS crosses shared memory.
 #include "attention.cuh"
 
 namespace kit {
 
-constexpr int AT = 64;         // tile edge (queries and keys)
+constexpr int AT = 64;  // tile edge (queries and keys)
 constexpr int AT_THREADS = 128;
-constexpr int ATP = AT + 4;    // padded row length of [*][64] smem tiles (keeps float4 alignment)
 
 struct MaskDev {
   const float* frame_mask;
@@ -30,88 +30,41 @@ __device__ __forceinline__ float mask_bias(const MaskDev& m, int b, int h, int i
   return r;
 }
 
-// rows [r0, r0+64) of a bf16 [*, ld] matrix (columns c0..c0+D) -> fp32 smem, transposed [D][ATP]
-template <int D>
-__device__ __forceinline__ void load_tile_T(float (*dst)[ATP], const bf16* base, int64_t ld, int r0, int nrows) {
-  constexpr int VPR = D / 8;  // 16-byte vectors per row
-  for (int idx = threadIdx.x; idx < AT * VPR; idx += AT_THREADS) {
-    const int r = idx / VPR, v = idx % VPR;
-    float f[8];
-    if (r0 + r < nrows) {
-      load8(base + (int64_t)(r0 + r) * ld + v * 8, f);
-    } else {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) f[u] = 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) dst[v * 8 + u][r] = f[u];
-  }
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// same rows, row-major [64][D+4]
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+
+// rows [r0, r0+64) x D columns of a bf16 matrix -> shared [64][D+8], zero rows beyond nrows
 template <int D>
-__device__ __forceinline__ void load_tile(float (*dst)[D + 4], const bf16* base, int64_t ld, int r0, int nrows) {
+__device__ __forceinline__ void load_tile(bf16 (*dst)[D + 8], const bf16* base, int64_t ld, int r0, int nrows) {
   constexpr int VPR = D / 8;
   for (int idx = threadIdx.x; idx < AT * VPR; idx += AT_THREADS) {
     const int r = idx / VPR, v = idx % VPR;
-    float f[8];
-    if (r0 + r < nrows) {
-      load8(base + (int64_t)(r0 + r) * ld + v * 8, f);
-    } else {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) f[u] = 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) dst[r][v * 8 + u] = f[u];
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (r0 + r < nrows) val = *reinterpret_cast<const uint4*>(base + (int64_t)(r0 + r) * ld + v * 8);
+    *reinterpret_cast<uint4*>(&dst[r][v * 8]) = val;
   }
 }
-
-// acc[4][8] = sum_c At[c][4*ty + i] * Bt[c][8*tx + j]
 template <int D>
-__device__ __forceinline__ void outer_tile(const float (*At)[ATP], const float (*Bt)[ATP], int ty, int tx,
-                                           float acc[4][8]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-#pragma unroll 8
-  for (int c = 0; c < D; ++c) {
-    const float4 a = *reinterpret_cast<const float4*>(&At[c][4 * ty]);
-    const float4 b0 = *reinterpret_cast<const float4*>(&Bt[c][8 * tx]);
-    const float4 b1 = *reinterpret_cast<const float4*>(&Bt[c][8 * tx + 4]);
-    const float av[4] = {a.x, a.y, a.z, a.w};
-    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-  }
+__device__ __forceinline__ uint32_t lds_pair(const bf16 (*t)[D + 8], int r, int c) {
+  return *reinterpret_cast<const uint32_t*>(&t[r][c]);
 }
 
-// out[4][CPT] += sum_r Pt[r][4*ty + i] * V[r][CPT*tx + j]      (reduction over the 64 rows r)
-template <int D>
-__device__ __forceinline__ void reduce_tile(const float (*Pt)[ATP], const float (*V)[D + 4], int ty, int tx,
-                                            float acc[4][D / 8]) {
-  constexpr int CPT = D / 8;
-#pragma unroll 4
-  for (int r = 0; r < AT; ++r) {
-    const float4 p = *reinterpret_cast<const float4*>(&Pt[r][4 * ty]);
-    const float pv[4] = {p.x, p.y, p.z, p.w};
-    float vv[CPT];
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) vv[j] = V[r][CPT * tx + j];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) acc[i][j] = fmaf(pv[i], vv[j], acc[i][j]);
-  }
-}
-
+// ---------------------------------------------------------------------------------------- forward
 template <int D>
 struct FwdSmem {
-  float Qt[D][ATP];
-  float Kt[D][ATP];
-  float V[AT][D + 4];
-  float Pt[AT][ATP];  // [key][query]
+  bf16 K[AT][D + 8];
+  bf16 V[AT][D + 8];
   float fm[AT];
 };
 
@@ -122,140 +75,143 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const bf16* __rest
                                                               bf16* __restrict__ out, int64_t ldo,
                                                               float* __restrict__ lse, int NH, int Sq, int Sk,
                                                               float scale, MaskDev mask) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  FwdSmem<D>& s = *reinterpret_cast<FwdSmem<D>*>(smem_raw);
-  constexpr int CPT = D / 8;
+  __shared__ __align__(16) FwdSmem<D> s;
+  constexpr int KS = D / 16, NT = D / 8;
   const int b = blockIdx.y / NH, h = blockIdx.y % NH;
-  const int q0 = blockIdx.x * AT;
-  const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * AT + warp * 16;
   const bf16* qb = q + (int64_t)b * Sq * ldq + h * D;
   const bf16* kb = k + (int64_t)b * Sk * ldk + h * D;
   const bf16* vb = v + (int64_t)b * Sk * ldv + h * D;
 
-  load_tile_T<D>(s.Qt, qb, ldq, q0, Sq);
-  float m_run[4], l_run[4], o[4][CPT];
+  uint32_t aq[KS][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    m_run[i] = -INFINITY;
-    l_run[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) o[i][j] = 0.f;
+  for (int kk = 0; kk < KS; ++kk) {
+    const int r0 = q0 + g, r1 = q0 + g + 8, c = kk * 16 + 2 * t;
+    aq[kk][0] = r0 < Sq ? *reinterpret_cast<const uint32_t*>(qb + (int64_t)r0 * ldq + c) : 0u;
+    aq[kk][1] = r1 < Sq ? *reinterpret_cast<const uint32_t*>(qb + (int64_t)r1 * ldq + c) : 0u;
+    aq[kk][2] = r0 < Sq ? *reinterpret_cast<const uint32_t*>(qb + (int64_t)r0 * ldq + c + 8) : 0u;
+    aq[kk][3] = r1 < Sq ? *reinterpret_cast<const uint32_t*>(qb + (int64_t)r1 * ldq + c + 8) : 0u;
   }
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float o[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+
   for (int k0 = 0; k0 < Sk; k0 += AT) {
-    __syncthreads();  // previous tile fully consumed (also covers the Qt load on the first pass)
-    load_tile_T<D>(s.Kt, kb, ldk, k0, Sk);
+    __syncthreads();
+    load_tile<D>(s.K, kb, ldk, k0, Sk);
     load_tile<D>(s.V, vb, ldv, k0, Sk);
     if (threadIdx.x < AT) {
       const int j = k0 + threadIdx.x;
       s.fm[threadIdx.x] = (mask.frame_mask != nullptr && j < Sk) ? mask.frame_mask[(int64_t)b * mask.frame_mask_stride + j] : 0.f;
     }
     __syncthreads();
-    float acc[4][8];
-    outer_tile<D>(s.Qt, s.Kt, ty, tx, acc);
-    float p_scale[4];
+    float acc[8][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int qi = q0 + 4 * ty + i;
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        mma16816(acc[j], aq[kk], lds_pair<D>(s.K, j * 8 + g, kk * 16 + 2 * t), lds_pair<D>(s.K, j * 8 + g, kk * 16 + 2 * t + 8));
+    // scale + mask, online softmax for rows (q0+g) and (q0+g+8)
+    float corr[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int qi = q0 + g + 8 * r;
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int kj = k0 + 8 * tx + j;
-        float x = -INFINITY;
-        if (kj < Sk && qi < Sq) x = acc[i][j] * scale + mask_bias(mask, b, h, qi, kj, Sk, s.fm[8 * tx + j]);
-        acc[i][j] = x;
-        mx = fmaxf(mx, x);
-      }
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int kl = j * 8 + 2 * t + c, kj = k0 + kl;
+          float x = -INFINITY;
+          if (kj < Sk && qi < Sq) x = acc[j][2 * r + c] * scale + mask_bias(mask, b, h, qi, kj, Sk, s.fm[kl]);
+          acc[j][2 * r + c] = x;
+          mx = fmaxf(mx, x);
+        }
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-      const float m_new = fmaxf(m_run[i], mx);
+      const float m_new = fmaxf(m_run[r], mx);
       const float m_ref = (m_new == -INFINITY) ? 0.f : m_new;
-      p_scale[i] = __expf(m_run[i] - m_ref);  // exp(-inf) = 0 on the first tile
+      corr[r] = __expf(m_run[r] - m_ref);
       float rs = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float p = __expf(acc[i][j] - m_ref);
-        acc[i][j] = p;
-        rs += p;
-      }
-      rs += __shfl_xor_sync(0xffffffffu, rs, 1);
-      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
-      rs += __shfl_xor_sync(0xffffffffu, rs, 4);
-      l_run[i] = l_run[i] * p_scale[i] + rs;
-      m_run[i] = m_new;
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float p = __expf(acc[j][2 * r + c] - m_ref);
+          acc[j][2 * r + c] = p;
+          rs += p;
+        }
+      l_run[r] = l_run[r] * corr[r] + rs;   // per-thread partial; quad-reduced at the end
+      m_run[r] = m_new;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<float4*>(&s.Pt[8 * tx + j][4 * ty]) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+    for (int j = 0; j < NT; ++j) {
+      o[j][0] *= corr[0]; o[j][1] *= corr[0];
+      o[j][2] *= corr[1]; o[j][3] *= corr[1];
+    }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int kk = 0; kk < 4; ++kk) {   // 16 keys per step
+      uint32_t ap[4];
+      ap[0] = pack_bf16(acc[2 * kk][0], acc[2 * kk][1]);
+      ap[1] = pack_bf16(acc[2 * kk][2], acc[2 * kk][3]);
+      ap[2] = pack_bf16(acc[2 * kk + 1][0], acc[2 * kk + 1][1]);
+      ap[3] = pack_bf16(acc[2 * kk + 1][2], acc[2 * kk + 1][3]);
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) o[i][j] *= p_scale[i];
-    __syncthreads();
-    reduce_tile<D>(s.Pt, s.V, ty, tx, o);
+      for (int j = 0; j < NT; ++j) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, &s.V[kk * 16 + (lane & 15)][j * 8]);
+        mma16816(o[j], ap, b0, b1);
+      }
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int qi = q0 + 4 * ty + i;
+  for (int r = 0; r < 2; ++r) {
+    float l = l_run[r];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    const int qi = q0 + g + 8 * r;
     if (qi >= Sq) continue;
-    const float inv = 1.f / l_run[i];
-    bf16* op = out + ((int64_t)b * Sq + qi) * ldo + h * D + CPT * tx;
+    const float inv = 1.f / l;
+    bf16* op = out + ((int64_t)b * Sq + qi) * ldo + h * D;
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) op[j] = __float2bfloat16(o[i][j] * inv);
-    if (tx == 0 && lse != nullptr) lse[((int64_t)b * NH + h) * Sq + qi] = m_run[i] + __logf(l_run[i]);
+    for (int j = 0; j < NT; ++j)
+      *reinterpret_cast<uint32_t*>(op + j * 8 + 2 * t) = pack_bf16(o[j][2 * r] * inv, o[j][2 * r + 1] * inv);
+    if (t == 0 && lse != nullptr) lse[((int64_t)b * NH + h) * Sq + qi] = m_run[r] + __logf(l);
   }
 }
 
-// ---------------------------------------------------------------- backward
+// ---------------------------------------------------------------------------------------- backward
 template <int D>
 struct BwdSmem {
-  float At[D][ATP];     // Q^T  (dKV kernel: per q tile)     | Q^T (dQ kernel: fixed)
-  float Bt[D][ATP];     // K^T
-  float Ct[D][ATP];     // dO^T
-  float Dt[D][ATP];     // V^T
-  float R0[AT][D + 4];  // dKV: Q row-major   | dQ: K row-major
-  float R1[AT][D + 4];  // dKV: dO row-major
-  float P[AT][ATP];     // dKV: P[query][key] | dQ: dS^T [key][query]
-  float dS[AT][ATP];    // dKV: dS[query][key]
-  float fm[AT];
-  float lse[AT];
-  float delta[AT];
+  bf16 K[AT][D + 8];
+  bf16 V[AT][D + 8];
+  bf16 Q[AT][D + 8];
+  bf16 dO[AT][D + 8];
+  bf16 dS[AT][AT + 8];  // [key][query]
+  float fm[AT];         // frame mask of the keys
+  float lse[AT];        // per query
+  float delta[AT];      // per query: sum_c dO*O
 };
 
-// delta_i = sum_c dO[i,c] * O[i,c] for the 64 rows starting at r0 (one thread pair per row)
+// One CTA per (key tile, b*h): warp w owns keys 16w..16w+15 of the tile.  dQ is written directly when
+// there is a single key tile, else accumulated with fp32 atomics into dq_acc.
 template <int D>
-__device__ __forceinline__ void load_delta_lse(float* delta, float* lse_s, const bf16* ob, int64_t ldo, const bf16* dob,
-                                               int64_t ld_do, const float* lse_g, int r0, int nrows) {
-  for (int r = threadIdx.x; r < AT; r += AT_THREADS) {
-    float d = 0.f, l = 0.f;
-    if (r0 + r < nrows) {
-      for (int c = 0; c < D; c += 8) {
-        float a[8], g[8];
-        load8(ob + (int64_t)(r0 + r) * ldo + c, a);
-        load8(dob + (int64_t)(r0 + r) * ld_do + c, g);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) d = fmaf(a[u], g[u], d);
-      }
-      l = lse_g[r0 + r];
-    }
-    delta[r] = d;
-    lse_s[r] = l;
-  }
-}
-
-// grid (key tiles, B*NH): dK, dV for one key tile, looping over query tiles
-template <int D>
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(
+__global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(
     const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ k, int64_t ldk, const bf16* __restrict__ v,
     int64_t ldv, const bf16* __restrict__ o, int64_t ldo, const bf16* __restrict__ dout, int64_t ld_do,
-    const float* __restrict__ lse, bf16* __restrict__ dk, int64_t ld_dk, bf16* __restrict__ dv, int64_t ld_dv, int NH,
-    int Sq, int Sk, float scale, MaskDev mask) {
+    const float* __restrict__ lse, bf16* __restrict__ dq, int64_t ld_dq, bf16* __restrict__ dk, int64_t ld_dk,
+    bf16* __restrict__ dv, int64_t ld_dv, float* __restrict__ dq_acc, int NH, int Sq, int Sk, float scale, MaskDev mask) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   BwdSmem<D>& s = *reinterpret_cast<BwdSmem<D>*>(smem_raw);
-  constexpr int CPT = D / 8;
+  constexpr int KS = D / 16, NT = D / 8;
   const int b = blockIdx.y / NH, h = blockIdx.y % NH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int k0 = blockIdx.x * AT;
-  const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
+  const bool single_tile = gridDim.x == 1;
   const bf16* qb = q + (int64_t)b * Sq * ldq + h * D;
   const bf16* kb = k + (int64_t)b * Sk * ldk + h * D;
   const bf16* vb = v + (int64_t)b * Sk * ldv + h * D;
@@ -263,135 +219,169 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(
   const bf16* dob = dout + (int64_t)b * Sq * ld_do + h * D;
   const float* lse_g = lse + ((int64_t)b * NH + h) * Sq;
 
-  load_tile_T<D>(s.Bt, kb, ldk, k0, Sk);
-  load_tile_T<D>(s.Dt, vb, ldv, k0, Sk);
+  load_tile<D>(s.K, kb, ldk, k0, Sk);
+  load_tile<D>(s.V, vb, ldv, k0, Sk);
   if (threadIdx.x < AT) {
     const int j = k0 + threadIdx.x;
     s.fm[threadIdx.x] = (mask.frame_mask != nullptr && j < Sk) ? mask.frame_mask[(int64_t)b * mask.frame_mask_stride + j] : 0.f;
   }
-  float dk_acc[4][CPT], dv_acc[4][CPT];
+  __syncthreads();
+  // A fragments of this warp's 16 keys: K (for S^T = K Q^T) and V (for dP^T = V dO^T)
+  uint32_t ak[KS][4], av[KS][4];
+  const int kr = warp * 16 + g;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int kk = 0; kk < KS; ++kk) {
+    const int c = kk * 16 + 2 * t;
+    ak[kk][0] = lds_pair<D>(s.K, kr, c);     ak[kk][1] = lds_pair<D>(s.K, kr + 8, c);
+    ak[kk][2] = lds_pair<D>(s.K, kr, c + 8); ak[kk][3] = lds_pair<D>(s.K, kr + 8, c + 8);
+    av[kk][0] = lds_pair<D>(s.V, kr, c);     av[kk][1] = lds_pair<D>(s.V, kr + 8, c);
+    av[kk][2] = lds_pair<D>(s.V, kr, c + 8); av[kk][3] = lds_pair<D>(s.V, kr + 8, c + 8);
+  }
+  float dk_acc[NT][4], dv_acc[NT][4];
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) dk_acc[i][j] = dv_acc[i][j] = 0.f;
+  for (int j = 0; j < NT; ++j) {
+    dk_acc[j][0] = dk_acc[j][1] = dk_acc[j][2] = dk_acc[j][3] = 0.f;
+    dv_acc[j][0] = dv_acc[j][1] = dv_acc[j][2] = dv_acc[j][3] = 0.f;
+  }
 
   for (int q0 = 0; q0 < Sq; q0 += AT) {
-    __syncthreads();
-    load_tile_T<D>(s.At, qb, ldq, q0, Sq);
-    load_tile_T<D>(s.Ct, dob, ld_do, q0, Sq);
-    load_tile<D>(s.R0, qb, ldq, q0, Sq);
-    load_tile<D>(s.R1, dob, ld_do, q0, Sq);
-    load_delta_lse<D>(s.delta, s.lse, ob, ldo, dob, ld_do, lse_g, q0, Sq);
-    __syncthreads();
-    float sc[4][8], dp[4][8];
-    outer_tile<D>(s.At, s.Bt, ty, tx, sc);  // Q K^T
-    outer_tile<D>(s.Ct, s.Dt, ty, tx, dp);  // dO V^T
+    __syncthreads();   // previous iteration's readers of Q / dO / dS are done
+    load_tile<D>(s.Q, qb, ldq, q0, Sq);
+    load_tile<D>(s.dO, dob, ld_do, q0, Sq);
+    {  // delta_i = sum_c dO[i,c] O[i,c]; two threads per query row
+      const int r = threadIdx.x >> 1, hf = threadIdx.x & 1;
+      float dsum = 0.f;
+      if (q0 + r < Sq) {
+        for (int c = hf * (D / 2); c < (hf + 1) * (D / 2); c += 8) {
+          float a[8], gg[8];
+          load8(ob + (int64_t)(q0 + r) * ldo + c, a);
+          load8(dob + (int64_t)(q0 + r) * ld_do + c, gg);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int qi = q0 + 4 * ty + i;
-      const float l = s.lse[4 * ty + i], dl = s.delta[4 * ty + i];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int kj = k0 + 8 * tx + j;
-        float p = 0.f;
-        if (kj < Sk && qi < Sq) {
-          const float x = sc[i][j] * scale + mask_bias(mask, b, h, qi, kj, Sk, s.fm[8 * tx + j]);
-          p = __expf(x - l);
+          for (int u = 0; u < 8; ++u) dsum = fmaf(a[u], gg[u], dsum);
         }
-        s.P[4 * ty + i][8 * tx + j] = p;
-        s.dS[4 * ty + i][8 * tx + j] = p * (dp[i][j] - dl) * scale;
+      }
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+      if (hf == 0) {
+        s.delta[r] = dsum;
+        s.lse[r] = (q0 + r < Sq) ? lse_g[q0 + r] : 0.f;
       }
     }
     __syncthreads();
-    // dV[key][c] += sum_i P[i][key] dO[i][c];  dK[key][c] += sum_i dS[i][key] Q[i][c]
-    reduce_tile<D>(s.P, s.R1, ty, tx, dv_acc);
-    reduce_tile<D>(s.dS, s.R0, ty, tx, dk_acc);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int kj = k0 + 4 * ty + i;
-    if (kj >= Sk) continue;
-    bf16* dkp = dk + ((int64_t)b * Sk + kj) * ld_dk + h * D + CPT * tx;
-    bf16* dvp = dv + ((int64_t)b * Sk + kj) * ld_dv + h * D + CPT * tx;
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      dkp[j] = __float2bfloat16(dk_acc[i][j]);
-      dvp[j] = __float2bfloat16(dv_acc[i][j]);
-    }
-  }
-}
-
-// grid (query tiles, B*NH): dQ for one query tile, looping over key tiles
-template <int D>
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(
-    const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ k, int64_t ldk, const bf16* __restrict__ v,
-    int64_t ldv, const bf16* __restrict__ o, int64_t ldo, const bf16* __restrict__ dout, int64_t ld_do,
-    const float* __restrict__ lse, bf16* __restrict__ dq, int64_t ld_dq, int NH, int Sq, int Sk, float scale,
-    MaskDev mask) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  BwdSmem<D>& s = *reinterpret_cast<BwdSmem<D>*>(smem_raw);
-  constexpr int CPT = D / 8;
-  const int b = blockIdx.y / NH, h = blockIdx.y % NH;
-  const int q0 = blockIdx.x * AT;
-  const int ty = threadIdx.x >> 3, tx = threadIdx.x & 7;
-  const bf16* qb = q + (int64_t)b * Sq * ldq + h * D;
-  const bf16* kb = k + (int64_t)b * Sk * ldk + h * D;
-  const bf16* vb = v + (int64_t)b * Sk * ldv + h * D;
-  const bf16* ob = o + (int64_t)b * Sq * ldo + h * D;
-  const bf16* dob = dout + (int64_t)b * Sq * ld_do + h * D;
-  const float* lse_g = lse + ((int64_t)b * NH + h) * Sq;
-
-  load_tile_T<D>(s.At, qb, ldq, q0, Sq);
-  load_tile_T<D>(s.Ct, dob, ld_do, q0, Sq);
-  load_delta_lse<D>(s.delta, s.lse, ob, ldo, dob, ld_do, lse_g, q0, Sq);
-  float dq_acc[4][CPT];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) dq_acc[i][j] = 0.f;
-
-  for (int k0 = 0; k0 < Sk; k0 += AT) {
-    __syncthreads();
-    load_tile_T<D>(s.Bt, kb, ldk, k0, Sk);
-    load_tile_T<D>(s.Dt, vb, ldv, k0, Sk);
-    load_tile<D>(s.R0, kb, ldk, k0, Sk);
-    if (threadIdx.x < AT) {
-      const int j = k0 + threadIdx.x;
-      s.fm[threadIdx.x] = (mask.frame_mask != nullptr && j < Sk) ? mask.frame_mask[(int64_t)b * mask.frame_mask_stride + j] : 0.f;
-    }
-    __syncthreads();
-    float sc[4][8], dp[4][8];
-    outer_tile<D>(s.At, s.Bt, ty, tx, sc);
-    outer_tile<D>(s.Ct, s.Dt, ty, tx, dp);
+    // S^T and dP^T for (16 keys of this warp) x (64 queries)
+    float st[8][4], dp[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float ds[4];
+      st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
+      dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+    }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int qi = q0 + 4 * ty + i, kj = k0 + 8 * tx + j;
+    for (int kk = 0; kk < KS; ++kk)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = kk * 16 + 2 * t;
+        mma16816(st[j], ak[kk], lds_pair<D>(s.Q, j * 8 + g, c), lds_pair<D>(s.Q, j * 8 + g, c + 8));
+        mma16816(dp[j], av[kk], lds_pair<D>(s.dO, j * 8 + g, c), lds_pair<D>(s.dO, j * 8 + g, c + 8));
+      }
+    // P^T = exp(S^T*scale + bias - lse[query]);  dS^T = P^T * (dP^T - delta[query]) * scale
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kl = warp * 16 + g + 8 * (e >> 1), kj = k0 + kl;   // key
+        const int ql = j * 8 + 2 * t + (e & 1), qi = q0 + ql;        // query
         float p = 0.f;
         if (kj < Sk && qi < Sq) {
-          const float x = sc[i][j] * scale + mask_bias(mask, b, h, qi, kj, Sk, s.fm[8 * tx + j]);
-          p = __expf(x - s.lse[4 * ty + i]);
+          const float x = st[j][e] * scale + mask_bias(mask, b, h, qi, kj, Sk, s.fm[kl]);
+          p = __expf(x - s.lse[ql]);
         }
-        ds[i] = p * (dp[i][j] - s.delta[4 * ty + i]) * scale;
+        st[j][e] = p;
+        dp[j][e] = p * (dp[j][e] - s.delta[ql]) * scale;
       }
-      *reinterpret_cast<float4*>(&s.P[8 * tx + j][4 * ty]) = make_float4(ds[0], ds[1], ds[2], ds[3]);  // dS^T
+    // dV += P^T dO ; dK += dS^T Q      (reduction over the 64 queries, 16 per k-step)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t ap[4], ad[4];
+      ap[0] = pack_bf16(st[2 * kk][0], st[2 * kk][1]);         ap[1] = pack_bf16(st[2 * kk][2], st[2 * kk][3]);
+      ap[2] = pack_bf16(st[2 * kk + 1][0], st[2 * kk + 1][1]); ap[3] = pack_bf16(st[2 * kk + 1][2], st[2 * kk + 1][3]);
+      ad[0] = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]);         ad[1] = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
+      ad[2] = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]); ad[3] = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, &s.dO[kk * 16 + (lane & 15)][j * 8]);
+        mma16816(dv_acc[j], ap, b0, b1);
+        ldsm_x2_trans(b0, b1, &s.Q[kk * 16 + (lane & 15)][j * 8]);
+        mma16816(dk_acc[j], ad, b0, b1);
+      }
+    }
+    // dS^T (bf16) -> shared [key][query]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      *reinterpret_cast<uint32_t*>(&s.dS[warp * 16 + g][j * 8 + 2 * t]) = pack_bf16(dp[j][0], dp[j][1]);
+      *reinterpret_cast<uint32_t*>(&s.dS[warp * 16 + g + 8][j * 8 + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
     }
     __syncthreads();
-    reduce_tile<D>(s.P, s.R0, ty, tx, dq_acc);  // dQ[i][c] += sum_j dS[i][j] K[j][c]
+    // dQ (16 queries of this warp) = dS (16 x 64 keys) K (64 x D)
+    float dq_acc_r[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) dq_acc_r[j][0] = dq_acc_r[j][1] = dq_acc_r[j][2] = dq_acc_r[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {   // 16 keys per step
+      uint32_t a[4];
+      // 8x8 blocks (transposed on load): lanes 0-7 keys 0-7/queries 0-7, 8-15 queries 8-15, 16-23 keys 8-15, 24-31 both
+      ldsm_x4_trans(a, &s.dS[kk * 16 + (lane & 7) + ((lane >> 4) << 3)][warp * 16 + (((lane >> 3) & 1) << 3)]);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, &s.K[kk * 16 + (lane & 15)][j * 8]);
+        mma16816(dq_acc_r[j], a, b0, b1);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int qi = q0 + warp * 16 + g + 8 * r;
+      if (qi >= Sq) continue;
+      if (single_tile) {
+        bf16* dqp = dq + ((int64_t)b * Sq + qi) * ld_dq + h * D;
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          *reinterpret_cast<uint32_t*>(dqp + j * 8 + 2 * t) = pack_bf16(dq_acc_r[j][2 * r], dq_acc_r[j][2 * r + 1]);
+      } else {
+        float* ap = dq_acc + ((int64_t)b * Sq + qi) * (int64_t)(NH * D) + h * D;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          atomicAdd(ap + j * 8 + 2 * t, dq_acc_r[j][2 * r]);
+          atomicAdd(ap + j * 8 + 2 * t + 1, dq_acc_r[j][2 * r + 1]);
+        }
+      }
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int qi = q0 + 4 * ty + i;
-    if (qi >= Sq) continue;
-    bf16* dqp = dq + ((int64_t)b * Sq + qi) * ld_dq + h * D + CPT * tx;
+  for (int r = 0; r < 2; ++r) {
+    const int kj = k0 + warp * 16 + g + 8 * r;
+    if (kj >= Sk) continue;
+    bf16* dkp = dk + ((int64_t)b * Sk + kj) * ld_dk + h * D;
+    bf16* dvp = dv + ((int64_t)b * Sk + kj) * ld_dv + h * D;
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) dqp[j] = __float2bfloat16(dq_acc[i][j]);
+    for (int j = 0; j < NT; ++j) {
+      *reinterpret_cast<uint32_t*>(dkp + j * 8 + 2 * t) = pack_bf16(dk_acc[j][2 * r], dk_acc[j][2 * r + 1]);
+      *reinterpret_cast<uint32_t*>(dvp + j * 8 + 2 * t) = pack_bf16(dv_acc[j][2 * r], dv_acc[j][2 * r + 1]);
+    }
   }
 }
 
-// ---------------------------------------------------------------- host
+// fp32 dQ accumulator [rows, width] -> bf16 dq (row pitch ld_dq), multi-key-tile case only
+__global__ void dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, int64_t ld_dq, int64_t rows, int width) {
+  const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (idx >= rows * width) return;
+  const int64_t r = idx / width;
+  const int c = (int)(idx % width);
+  float f[8];
+  load8(acc + idx, f);
+  store8(dq + r * ld_dq + c, f);
+}
+
+// ---------------------------------------------------------------------------------------- host
 static MaskDev to_dev(const KitAttnMask* m) {
   MaskDev d;
   d.frame_mask = m ? m->frame_mask : nullptr;
@@ -406,40 +396,35 @@ static MaskDev to_dev(const KitAttnMask* m) {
 template <int D>
 static int fwd_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, bf16* out,
                       int64_t ldo, float* lse, int B, int NH, int Sq, int Sk, const MaskDev& md, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    KIT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(FwdSmem<D>)));
-    attr_done = true;
-  }
   dim3 grid((Sq + AT - 1) / AT, B * NH);
-  attn_fwd_kernel<D><<<grid, AT_THREADS, sizeof(FwdSmem<D>), st>>>(q, ldq, k, ldk, v, ldv, out, ldo, lse, NH, Sq, Sk,
-                                                                   rsqrtf((float)D), md);
+  attn_fwd_kernel<D><<<grid, AT_THREADS, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, lse, NH, Sq, Sk, rsqrtf((float)D), md);
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
 template <int D>
 static int bwd_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, const bf16* o,
                       int64_t ldo, const bf16* dout, int64_t ld_do, const float* lse, bf16* dq, int64_t ld_dq, bf16* dk,
-                      int64_t ld_dk, bf16* dv, int64_t ld_dv, int B, int NH, int Sq, int Sk, const MaskDev& md,
-                      cudaStream_t st) {
+                      int64_t ld_dk, bf16* dv, int64_t ld_dv, float* dq_acc, int B, int NH, int Sq, int Sk,
+                      const MaskDev& md, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    KIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(BwdSmem<D>)));
-    KIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(BwdSmem<D>)));
+    KIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem<D>)));
     attr_done = true;
   }
-  const float scale = rsqrtf((float)D);
-  dim3 gkv((Sk + AT - 1) / AT, B * NH);
-  attn_bwd_dkv_kernel<D><<<gkv, AT_THREADS, sizeof(BwdSmem<D>), st>>>(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse,
-                                                                       dk, ld_dk, dv, ld_dv, NH, Sq, Sk, scale, md);
+  const int ktiles = (Sk + AT - 1) / AT;
+  if (ktiles > 1) {
+    KIT_REQUIRE(dq_acc != nullptr, "attention backward with more than 64 keys needs the fp32 dq accumulator workspace");
+    KIT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)B * Sq * NH * D * sizeof(float), st));
+  }
+  dim3 grid(ktiles, B * NH);
+  attn_bwd_kernel<D><<<grid, AT_THREADS, sizeof(BwdSmem<D>), st>>>(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq,
+                                                                    dk, ld_dk, dv, ld_dv, dq_acc, NH, Sq, Sk, rsqrtf((float)D), md);
   KIT_LAUNCH_CHECK();
-  dim3 gq((Sq + AT - 1) / AT, B * NH);
-  attn_bwd_dq_kernel<D><<<gq, AT_THREADS, sizeof(BwdSmem<D>), st>>>(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq,
-                                                                     ld_dq, NH, Sq, Sk, scale, md);
-  KIT_LAUNCH_CHECK();
+  if (ktiles > 1) {
+    const int64_t n = (int64_t)B * Sq * NH * D;
+    dq_convert_kernel<<<(unsigned)ceil_div(n / 8, 256), 256, 0, st>>>(dq_acc, dq, ld_dq, (int64_t)B * Sq, NH * D);
+    KIT_LAUNCH_CHECK();
+  }
   return KIT_OK;
 }
 
@@ -463,17 +448,17 @@ int attention_fwd(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const 
 }
 int attention_bwd(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, const bf16* o,
                   int64_t ldo, const bf16* dout, int64_t ld_do, const float* lse, bf16* dq, int64_t ld_dq, bf16* dk,
-                  int64_t ld_dk, bf16* dv, int64_t ld_dv, int B, int NH, int Sq, int Sk, int d, const KitAttnMask* mask,
-                  cudaStream_t st) {
+                  int64_t ld_dk, bf16* dv, int64_t ld_dv, float* dq_acc, int B, int NH, int Sq, int Sk, int d,
+                  const KitAttnMask* mask, cudaStream_t st) {
   int rc = check_attn(d, ldq, ldk, ldv, ldo);
   if (rc) return rc;
   rc = check_attn(d, ld_do, ld_dq, ld_dk, ld_dv);
   if (rc) return rc;
   const MaskDev md = to_dev(mask);
   switch (d) {
-    case 16: return bwd_launch<16>(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq, dk, ld_dk, dv, ld_dv, B, NH, Sq, Sk, md, st);
-    case 32: return bwd_launch<32>(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq, dk, ld_dk, dv, ld_dv, B, NH, Sq, Sk, md, st);
-    default: return bwd_launch<64>(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq, dk, ld_dk, dv, ld_dv, B, NH, Sq, Sk, md, st);
+    case 16: return bwd_launch<16>(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq, dk, ld_dk, dv, ld_dv, dq_acc, B, NH, Sq, Sk, md, st);
+    case 32: return bwd_launch<32>(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq, dk, ld_dk, dv, ld_dv, dq_acc, B, NH, Sq, Sk, md, st);
+    default: return bwd_launch<64>(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq, dk, ld_dk, dv, ld_dv, dq_acc, B, NH, Sq, Sk, md, st);
   }
 }
 
@@ -488,9 +473,10 @@ extern "C" int kit_attention_fwd(const void* q, int64_t ldq, const void* k, int6
 }
 extern "C" int kit_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                  const void* out, int64_t ldo, const void* dout, int64_t ld_do, const float* lse, void* dq,
-                                 int64_t ld_dq, void* dk, int64_t ld_dk, void* dv, int64_t ld_dv, int32_t B, int32_t NH,
-                                 int32_t Sq, int32_t Sk, int32_t d, const KitAttnMask* mask, void* stream) {
+                                 int64_t ld_dq, void* dk, int64_t ld_dk, void* dv, int64_t ld_dv, float* dq_accum,
+                                 int32_t B, int32_t NH, int32_t Sq, int32_t Sk, int32_t d, const KitAttnMask* mask,
+                                 void* stream) {
   return attention_bwd((const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (const bf16*)out, ldo,
-                       (const bf16*)dout, ld_do, lse, (bf16*)dq, ld_dq, (bf16*)dk, ld_dk, (bf16*)dv, ld_dv, B, NH, Sq, Sk,
-                       d, mask, (cudaStream_t)stream);
+                       (const bf16*)dout, ld_do, lse, (bf16*)dq, ld_dq, (bf16*)dk, ld_dk, (bf16*)dv, ld_dv, dq_accum, B,
+                       NH, Sq, Sk, d, mask, (cudaStream_t)stream);
 }

@@ -7,6 +7,6 @@ int attention_fwd(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const 
                   cudaStream_t st);
 int attention_bwd(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, const bf16* o,
                   int64_t ldo, const bf16* dout, int64_t ld_do, const float* lse, bf16* dq, int64_t ld_dq, bf16* dk,
-                  int64_t ld_dk, bf16* dv, int64_t ld_dv, int B, int NH, int Sq, int Sk, int d, const KitAttnMask* mask,
-                  cudaStream_t st);
+                  int64_t ld_dk, bf16* dv, int64_t ld_dv, float* dq_acc, int B, int NH, int Sq, int Sk, int d,
+                  const KitAttnMask* mask, cudaStream_t st);
 }  // namespace kit

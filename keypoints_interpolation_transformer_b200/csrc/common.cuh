@@ -47,41 +47,51 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// Exact (erf) GELU, branch-free: erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), whose
+// exp(-u^2) with u = x/sqrt(2) is also the Gaussian the derivative needs.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& gauss) {
+  const float u = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  gauss = __expf(-u * u);                       // exp(-x^2 / 2)
+  const float half_erfc = 0.5f * poly * gauss;  // 0.5 * erfc(|u|)
+  cdf = (x >= 0.f) ? 1.0f - half_erfc : half_erfc;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  float cdf, g;
+  gelu_parts(x, cdf, g);
+  return x * cdf;
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, g;
+  gelu_parts(x, cdf, g);
+  return fmaf(x * 0.39894228040143267794f, g, cdf);
 }
 
-// 8 bf16 <-> 8 floats through one 16-byte vector
-struct __align__(16) bf16x8 { __nv_bfloat162 v[4]; };
+// 8 bf16 <-> 8 floats through ONE 16-byte access (uint4: a struct of __nv_bfloat162 is copied
+// member-wise by nvcc and degenerates into four 4-byte accesses).
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 __device__ __forceinline__ void load8(const bf16* p, float* f) {
-  bf16x8 r = *reinterpret_cast<const bf16x8*>(p);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(r.v[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const float2 a = unpack_bf16(r.x), b = unpack_bf16(r.y), c = unpack_bf16(r.z), d = unpack_bf16(r.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
-__device__ __forceinline__ void store8(bf16* p, const float* f) {
-  bf16x8 r;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) r.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  *reinterpret_cast<bf16x8*>(p) = r;
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
+__device__ __forceinline__ void store8(bf16* p, const float* f) { *reinterpret_cast<uint4*>(p) = pack8(f); }
 __device__ __forceinline__ void load8(const float* p, float* f) {
   float4 a = *reinterpret_cast<const float4*>(p);
   float4 b = *reinterpret_cast<const float4*>(p + 4);
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
   f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-}
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
 }
 
 // ---------------------------------------------------------------- PTX: mbarrier / TMA / tcgen05
@@ -134,6 +144,23 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// smem (generic-proxy writes made visible with fence.proxy.async) -> global tile, clipped at the tensor edge
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// global tile += smem tile (fp32), performed by the TMA unit at L2
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

@@ -241,6 +241,7 @@ struct KitEngine {
   std::vector<EncAct> ea;
   std::vector<DecAct> da;
   bf16 *g0, *g1, *g2, *g3, *gmem, *gff, *gqkv, *gkv, *g2h;
+  float* dq_acc;
 
   int64_t alloc(const std::string& name, int64_t elems, int esize, int64_t ld) {
     Buf b{ws_bytes, elems, esize, ld};
@@ -302,6 +303,7 @@ static void plan_workspace(KitEngine* e) {
   e->alloc("gqkv", gm * 3 * H, 2, 3 * H);
   e->alloc("gkv", gm * 2 * H, 2, 2 * H);
   e->alloc("g2h", gm * 2 * H, 2, 2 * H);
+  e->alloc("dq_acc", (e->training && e->T > 64) ? M * H : 8, 4, H);
 }
 
 static void resolve_pointers(KitEngine* e) {
@@ -314,6 +316,7 @@ static void resolve_pointers(KitEngine* e) {
   KIT_P(sf12); KIT_P(sfg); KIT_P(y0); KIT_P(mem); KIT_P(dec_out); KIT_P(sd12); KIT_P(sdg); KIT_P(sd); KIT_P(zf); KIT_P(sf);
   KIT_P(dp); KIT_P(g0); KIT_P(g1); KIT_P(g2); KIT_P(g3); KIT_P(gmem); KIT_P(gff); KIT_P(gqkv); KIT_P(gkv); KIT_P(g2h);
 #undef KIT_P
+  e->dq_acc = wsptr<float>(e, "dq_acc");
   e->st_encn = wsptr<float>(e, "st_encn");
   e->st_decn = wsptr<float>(e, "st_decn");
   e->ea.resize(L.cfg.layers);
@@ -377,7 +380,11 @@ static int eg(KitEngine* e, int mode, const bf16* A, int64_t lda, const bf16* Bm
     plans.push_back(p);
   }
   GemmPlan& p = plans[e->cursor++];
-  p.p.C = C;  // the only pointer that may change between calls (pred / grads are caller memory)
+  if (p.p.C != C) {  // caller memory moved (pred): the output tensor map must be rebuilt
+    int rc = gemm_plan(&p, mode, A, lda, Bm, ldb, C, ldc, M, N, K, bias, addend, ld_add, out_kind, act, aux, ld_aux,
+                       mode == 1 ? 0 : 1);
+    if (rc) return rc;
+  }
   e->launches++;
   prof_begin(e, mode == 0 ? KIT_PROF_GEMM_TN : KIT_PROF_GEMM_WGRAD, 2.0 * (double)M * (double)N * (double)K);
   const int rc = gemm_launch(&p, e->st);
@@ -400,8 +407,8 @@ static int eattn_bwd(KitEngine* e, const bf16* q, int64_t ldq, const bf16* k, in
   const int H = e->L.cfg.hidden, NH = e->L.cfg.heads, d = H / NH;
   e->launches += 2;
   prof_begin(e, KIT_PROF_ATTN_BWD, 10.0 * e->B * NH * (double)e->T * e->T * d);
-  const int rc = attention_bwd(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq, dk, ld_dk, dv, ld_dv, e->B, NH,
-                               e->T, e->T, d, mask, e->st);
+  const int rc = attention_bwd(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq, dk, ld_dk, dv, ld_dv,
+                               e->T > 64 ? e->dq_acc : nullptr, e->B, NH, e->T, e->T, d, mask, e->st);
   prof_end(e);
   return rc;
 }

@@ -23,6 +23,20 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static int make_tensor_map_2d_typed(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, uint64_t inner,
+                                    uint64_t outer, uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  KIT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KIT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return KIT_OK;
+}
+
 int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_pitch_bytes,
                        uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn fn = get_encode_fn();
@@ -41,22 +55,34 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint6
   return KIT_OK;
 }
 
-constexpr int TN_BN = 128, TN_STAGES = 3;
-constexpr int WG_BN = 128, WG_STAGES = 4;
+constexpr int STAGES_BN128 = 6, STAGES_BN256 = 4;
+
+static int g_num_sms = 0;
 
 int gemm_init_attributes() {
   static int status = 1;
   static std::once_flag once;
   std::call_once(once, []() {
-    cudaError_t e1 = cudaFuncSetAttribute(gemm_tcgen05_kernel<TN_BN, 0, TN_STAGES>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          gemm_smem_bytes<TN_BN, TN_STAGES>());
-    cudaError_t e2 = cudaFuncSetAttribute(gemm_tcgen05_kernel<WG_BN, 1, WG_STAGES>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          gemm_smem_bytes<WG_BN, WG_STAGES>());
-    status = (e1 == cudaSuccess && e2 == cudaSuccess) ? 0 : -1;
-    if (status != 0) set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s / %s", cudaGetErrorString(e1),
-                               cudaGetErrorString(e2));
+    cudaError_t e[4];
+    e[0] = cudaFuncSetAttribute(gemm_tcgen05_kernel<128, 0, STAGES_BN128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                gemm_smem_bytes<128, STAGES_BN128>());
+    e[1] = cudaFuncSetAttribute(gemm_tcgen05_kernel<256, 0, STAGES_BN256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                gemm_smem_bytes<256, STAGES_BN256>());
+    e[2] = cudaFuncSetAttribute(gemm_tcgen05_kernel<128, 1, STAGES_BN128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                gemm_smem_bytes<128, STAGES_BN128>());
+    e[3] = cudaFuncSetAttribute(gemm_tcgen05_kernel<256, 1, STAGES_BN256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                gemm_smem_bytes<256, STAGES_BN256>());
+    status = 0;
+    for (int i = 0; i < 4; ++i) {
+      if (e[i] != cudaSuccess) {
+        status = -1;
+        set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e[i]));
+      }
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
   });
   return status == 0 ? KIT_OK : KIT_ERR_CUDA;
 }
@@ -67,6 +93,8 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
   KIT_REQUIRE(mode == 0 || mode == 1, "gemm mode must be 0 (TN) or 1 (wgrad)");
   KIT_REQUIRE(M > 0 && N > 0 && K > 0, "gemm dims must be positive (M=%d N=%d K=%d)", M, N, K);
   KIT_REQUIRE(act == ACT_NONE || aux != nullptr, "gelu epilogues need the aux tensor");
+  int rc = gemm_init_attributes();
+  if (rc) return rc;
   GemmParams& p = plan->p;
   p.M = M; p.N = N; p.K = K;
   p.C = C; p.ldc = ldc;
@@ -75,44 +103,63 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
   p.aux = aux; p.ld_aux = ld_aux;
   p.out_kind = out_kind; p.act = act;
   plan->mode = mode;
+  const int bn = (N > 128) ? 256 : 128;
+  plan->bn = bn;
+  p.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+  p.tiles_n = (N + bn - 1) / bn;
+  const int tiles = p.tiles_m * p.tiles_n;
   const int kb_total = (K + GEMM_BK - 1) / GEMM_BK;
-  int rc;
+  int splits = 1;
   if (mode == 0) {
     // A [M,K] K-major: box 64(k) x 128(m);  B [N,K] K-major: box 64(k) x BN(n)
     if ((rc = make_tensor_map_2d(&plan->tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, GEMM_BK, GEMM_BM))) return rc;
-    if ((rc = make_tensor_map_2d(&plan->tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, GEMM_BK, TN_BN))) return rc;
-    KIT_REQUIRE(split_k <= 1 || out_kind == OUT_F32_ATOMIC, "split-K needs the atomic fp32 epilogue");
-    int splits = split_k > 1 ? split_k : 1;
-    if (splits > kb_total) splits = kb_total;
-    p.kb_per_split = (kb_total + splits - 1) / splits;
-    splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
-    plan->grid = dim3((N + TN_BN - 1) / TN_BN, (M + GEMM_BM - 1) / GEMM_BM, splits);
+    if ((rc = make_tensor_map_2d(&plan->tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, GEMM_BK, bn))) return rc;
+    splits = split_k > 1 ? split_k : 1;
   } else {
     // A [K,M] row-major (MN-major operand): box 64(m) x 64(k);  B [K,N]: box 64(n) x 64(k)
     if ((rc = make_tensor_map_2d(&plan->tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, GEMM_BK))) return rc;
     if ((rc = make_tensor_map_2d(&plan->tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, GEMM_BK))) return rc;
-    const int tiles = ((N + WG_BN - 1) / WG_BN) * ((M + GEMM_BM - 1) / GEMM_BM);
-    int splits = split_k;
-    if (splits <= 0) splits = (2 * 148 + tiles - 1) / tiles;
-    if (splits > kb_total) splits = kb_total;
-    if (splits < 1) splits = 1;
-    KIT_REQUIRE(splits == 1 || out_kind == OUT_F32_ATOMIC, "split-K needs the atomic fp32 epilogue");
-    p.kb_per_split = (kb_total + splits - 1) / splits;
-    splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
-    plan->grid = dim3((N + WG_BN - 1) / WG_BN, (M + GEMM_BM - 1) / GEMM_BM, splits);
+    splits = split_k;
+    if (splits <= 0) splits = (g_num_sms + tiles - 1) / tiles;   // about one work item per SM
   }
+  // outputs through shared memory + TMA (store / fp32 reduce-add) whenever the layout allows a tensor map
+  const size_t esize = (out_kind == OUT_BF16) ? 2 : 4;
+  p.tma_store = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (((size_t)ldc * esize) % 16 == 0);
+  if (act == ACT_GELU) p.tma_store = p.tma_store && ((reinterpret_cast<uintptr_t>(aux) & 15) == 0) && (((size_t)ld_aux * 2) % 16 == 0);
+  if (p.tma_store) {
+    if (out_kind == OUT_BF16) {
+      if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 64, 32))) return rc;
+    } else {
+      if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 4, 32, 32))) return rc;
+    }
+    plan->tmAux = plan->tmC;
+    if (act == ACT_GELU) {
+      if ((rc = make_tensor_map_2d_typed(&plan->tmAux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, aux, (uint64_t)N, (uint64_t)M, (uint64_t)ld_aux * 2, 64, 32))) return rc;
+    }
+  } else {
+    plan->tmC = plan->tmA;
+    plan->tmAux = plan->tmA;
+  }
+  if (splits > kb_total) splits = kb_total;
+  if (splits < 1) splits = 1;
+  KIT_REQUIRE(splits == 1 || out_kind == OUT_F32_ATOMIC, "split-K needs the atomic fp32 epilogue");
+  p.kb_per_split = (kb_total + splits - 1) / splits;
+  p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  const int items = tiles * p.splits;
+  plan->grid = items < g_num_sms ? items : g_num_sms;
   return KIT_OK;
 }
 
 int gemm_launch(const GemmPlan* plan, cudaStream_t stream) {
-  int rc = gemm_init_attributes();
-  if (rc) return rc;
-  if (plan->mode == 0) {
-    gemm_tcgen05_kernel<TN_BN, 0, TN_STAGES>
-        <<<plan->grid, GEMM_THREADS, gemm_smem_bytes<TN_BN, TN_STAGES>(), stream>>>(plan->tmA, plan->tmB, plan->p);
+  const dim3 grid(plan->grid);
+  if (plan->mode == 0 && plan->bn == 128) {
+    gemm_tcgen05_kernel<128, 0, STAGES_BN128><<<grid, GEMM_THREADS, gemm_smem_bytes<128, STAGES_BN128>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
+  } else if (plan->mode == 0) {
+    gemm_tcgen05_kernel<256, 0, STAGES_BN256><<<grid, GEMM_THREADS, gemm_smem_bytes<256, STAGES_BN256>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
+  } else if (plan->bn == 128) {
+    gemm_tcgen05_kernel<128, 1, STAGES_BN128><<<grid, GEMM_THREADS, gemm_smem_bytes<128, STAGES_BN128>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
   } else {
-    gemm_tcgen05_kernel<WG_BN, 1, WG_STAGES>
-        <<<plan->grid, GEMM_THREADS, gemm_smem_bytes<WG_BN, WG_STAGES>(), stream>>>(plan->tmA, plan->tmB, plan->p);
+    gemm_tcgen05_kernel<256, 1, STAGES_BN256><<<grid, GEMM_THREADS, gemm_smem_bytes<256, STAGES_BN256>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
   }
   KIT_LAUNCH_CHECK();
   return KIT_OK;

@@ -1,13 +1,16 @@
-// tcgen05 / TMEM / TMA GEMM for sm_100a.  One 128 x BN fp32 accumulator tile per CTA lives in
-// tensor memory; operands are staged by TMA into 128B-swizzled shared memory through a
-// STAGES-deep mbarrier ring; one elected thread issues tcgen05.mma; four epilogue warps read the
-// accumulator back with tcgen05.ld and apply the fused epilogue.
+// tcgen05 / TMEM / TMA GEMM for sm_100a -- persistent, warp-specialised.
+//
+// Each CTA (one per SM) loops over 128 x BN output tiles.  Operands are staged by TMA into
+// 128B-swizzled shared memory through a STAGES-deep mbarrier ring that runs ahead across tile
+// boundaries; one elected thread issues tcgen05.mma into one of TWO fp32 accumulators in tensor
+// memory, so the epilogue of tile i (tcgen05.ld -> fused epilogue -> global stores, 8 warps)
+// overlaps the TMA + MMA main loop of tile i+1.
 //
 //   MODE 0 (TN)    C[M,N] = A[M,K] * B[N,K]^T      both operands K-major      (y = x W^T, dx = dy W)
-//   MODE 1 (wgrad) C[M,N] = A[K,M]^T * B[K,N]      both operands MN-major     (dW = dy^T x)
+//   MODE 1 (wgrad) C[M,N] = A[K,M]^T * B[K,N]      both operands MN-major     (dW = dy^T x), split-K
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..9 = epilogue (TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4).
 #pragma once
 #include "common.cuh"
 
@@ -26,58 +29,219 @@ struct GemmParams {
   bf16* aux;  // ACT_GELU: pre-activation out; ACT_GELU_BWD: pre-activation in
   int64_t ld_aux;
   int out_kind, act;
-  int kb_per_split;  // 64-wide k-blocks handled by one blockIdx.z
+  int kb_per_split;  // 64-wide k-blocks per work item
+  int tiles_m, tiles_n, splits;
+  int tma_store;  // 1: outputs leave through shared memory + TMA store / reduce-add (clipped at the edges)
 };
 
 struct GemmPlan {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC, tmAux;
   GemmParams p;
-  int mode;
-  dim3 grid;
+  int mode, bn;
+  int grid;
 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;
+constexpr int GEMM_EPI_WARPS = 8;
+
+constexpr int GEMM_EPI_BUF = 4096;  // per epilogue warp: 32 rows x 128 B staging tile for the TMA store
 
 template <int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
-  return STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + GEMM_EPI_WARPS * GEMM_EPI_BUF + 1024 /*align slack*/ +
+         256 /*barriers*/;
+}
+
+// bias / residual / activation on 32 accumulator columns of one row, in registers.  Columns >= N of a
+// ragged last chunk are computed on garbage and clipped by the TMA store.
+__device__ __forceinline__ void gemm_epilogue_math(const GemmParams& p, int row, int col0, bool row_ok, bool do_act,
+                                                   float (&v)[32]) {
+  const bool full = col0 + 32 <= p.N;
+  if (p.bias != nullptr) {
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+    }
+  }
+  if (p.addend != nullptr && row_ok) {
+    const bf16* ap = p.addend + (int64_t)row * p.ld_addend + col0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float t[8];
+        load8(ap + j, t);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[j + u] += t[u];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) v[j] += __bfloat162float(ap[j]);
+    }
+  }
+  if (!do_act) return;
+  if (p.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act == ACT_GELU_BWD && row_ok) {
+    const bf16* xp = p.aux + (int64_t)row * p.ld_aux + col0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float t[8];
+        load8(xp + j, t);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[j + u] *= gelu_erf_grad(t[u]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) v[j] *= gelu_erf_grad(__bfloat162float(xp[j]));
+    }
+  }
+}
+// 32 bf16 values of this lane's row into the warp's 128B-swizzled staging tile (16-byte chunks j0..j0+3)
+__device__ __forceinline__ void stage_bf16(uint8_t* ebuf, int lane, int j0, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<uint4*>(ebuf + lane * 128 + (((j0 + i) ^ (lane & 7)) << 4)) = pack8(&v[8 * i]);
+}
+__device__ __forceinline__ void stage_f32(uint8_t* ebuf, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(ebuf + lane * 128 + ((i ^ (lane & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+// One row x 32 consecutive columns of the accumulator through the fused epilogue.
+__device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, int row, int col0, float (&v)[32], bool vec_ok) {
+  const bool full_chunk = (col0 + 32 <= p.N) && vec_ok;
+  if (full_chunk) {
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+    }
+    if (p.addend != nullptr) {
+      const bf16* ap = p.addend + (int64_t)row * p.ld_addend + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float t[8];
+        load8(ap + j, t);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[j + u] += t[u];
+      }
+    }
+    if (p.act == ACT_GELU) {
+      bf16* xp = p.aux + (int64_t)row * p.ld_aux + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        store8(xp + j, v + j);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[j + u] = gelu_erf(v[j + u]);
+      }
+    } else if (p.act == ACT_GELU_BWD) {
+      const bf16* xp = p.aux + (int64_t)row * p.ld_aux + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float t[8];
+        load8(xp + j, t);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[j + u] *= gelu_erf_grad(t[u]);
+      }
+    }
+    if (p.out_kind == OUT_BF16) {
+      bf16* cp = reinterpret_cast<bf16*>(p.C) + (int64_t)row * p.ldc + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) store8(cp + j, v + j);
+    } else if (p.out_kind == OUT_F32) {
+      float* cp = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+      float* cp = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
+                     "f"(v[j + 3])
+                     : "memory");
+      }
+    }
+  } else {  // ragged N edge or unaligned leading dimension: scalar path
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      if (col >= p.N) continue;
+      float x = v[j];
+      if (p.bias != nullptr) x += p.bias[col];
+      if (p.addend != nullptr) x += __bfloat162float(p.addend[(int64_t)row * p.ld_addend + col]);
+      if (p.act == ACT_GELU) {
+        p.aux[(int64_t)row * p.ld_aux + col] = __float2bfloat16(x);
+        x = gelu_erf(x);
+      } else if (p.act == ACT_GELU_BWD) {
+        x *= gelu_erf_grad(__bfloat162float(p.aux[(int64_t)row * p.ld_aux + col]));
+      }
+      if (p.out_kind == OUT_BF16) {
+        reinterpret_cast<bf16*>(p.C)[(int64_t)row * p.ldc + col] = __float2bfloat16(x);
+      } else if (p.out_kind == OUT_F32) {
+        reinterpret_cast<float*>(p.C)[(int64_t)row * p.ldc + col] = x;
+      } else {
+        atomicAdd(reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col, x);
+      }
+    }
+  }
 }
 
 template <int BN, int MODE, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                      const __grid_constant__ CUtensorMap tmB,
-                                                                      const GemmParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                         const __grid_constant__ CUtensorMap tmB,
+                                                                         const __grid_constant__ CUtensorMap tmC,
+                                                                         const __grid_constant__ CUtensorMap tmAux,
+                                                                         const GemmParams p) {
   constexpr int BM = GEMM_BM, BK = GEMM_BK;
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  static_assert(BN == 64 || BN == 128 || BN == 256, "BN must be a power-of-two TMEM allocation");
+  constexpr int TMEM_COLS = 2 * BN;  // two accumulators
+  static_assert(BN == 128 || BN == 256, "BN must give a power-of-two TMEM allocation <= 512");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + GEMM_EPI_WARPS * GEMM_EPI_BUF);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int kb_total = (p.K + BK - 1) / BK;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
-  const int num_kb = kb_end - kb_begin;
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int n_items = tiles_mn * p.splits;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], GEMM_EPI_WARPS);
+    }
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -85,22 +249,29 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tcgen05_kernel(const __grid
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-        uint8_t* sA = smem + s * STAGE_BYTES;
-        uint8_t* sB = sA + A_BYTES;
-        const int kc = (kb_begin + i) * BK;
-        if (MODE == 0) {
-          tma_load_2d(sA, &tmA, &full[s], kc, m0);
-          tma_load_2d(sB, &tmB, &full[s], kc, n0);
-        } else {
+      uint32_t cnt = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int split = item / tiles_mn, rem = item - split * tiles_mn;
+        const int n0 = (rem / p.tiles_m) * BN, m0 = (rem % p.tiles_m) * BM;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++cnt) {
+          const int s = cnt % STAGES;
+          const uint32_t ph = (cnt / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+          uint8_t* sA = smem + s * STAGE_BYTES;
+          uint8_t* sB = sA + A_BYTES;
+          const int kc = kb * BK;
+          if (MODE == 0) {
+            tma_load_2d(sA, &tmA, &full[s], kc, m0);
+            tma_load_2d(sB, &tmB, &full[s], kc, n0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * (BK * 128), &tmA, &full[s], m0 + 64 * j, kc);
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * (BK * 128), &tmA, &full[s], m0 + 64 * j, kc);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * (BK * 128), &tmB, &full[s], n0 + 64 * j, kc);
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * (BK * 128), &tmB, &full[s], n0 + 64 * j, kc);
+          }
         }
       }
     }
@@ -108,132 +279,156 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tcgen05_kernel(const __grid
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, MODE == 1, MODE == 1);
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      uint32_t cnt = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int split = item / tiles_mn;
+        const int kb_begin = split * p.kb_per_split;
+        const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aph ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_base = a_base + A_BYTES;
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++cnt) {
+          const int s = cnt % STAGES;
+          const uint32_t ph = (cnt / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_base = a_base + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          uint64_t adesc, bdesc;
-          if (MODE == 0) {  // K-major, one 128B swizzle atom along K: +32 B per UMMA_K
-            adesc = make_smem_desc_sw128(a_base + k * 32, 0, 1024);
-            bdesc = make_smem_desc_sw128(b_base + k * 32, 0, 1024);
-          } else {  // MN-major: 64-element MN atoms LBO apart, 8-row k groups SBO apart
-            adesc = make_smem_desc_sw128(a_base + k * 16 * 128, BK * 128, 1024);
-            bdesc = make_smem_desc_sw128(b_base + k * 16 * 128, BK * 128, 1024);
+          for (int k = 0; k < BK / 16; ++k) {
+            uint64_t adesc, bdesc;
+            if (MODE == 0) {  // K-major, one 128B swizzle atom along K: +32 B per UMMA_K
+              adesc = make_smem_desc_sw128(a_base + k * 32, 0, 1024);
+              bdesc = make_smem_desc_sw128(b_base + k * 32, 0, 1024);
+            } else {  // MN-major: 64-element MN atoms LBO apart, 8-row k groups SBO apart
+              adesc = make_smem_desc_sw128(a_base + k * 16 * 128, BK * 128, 1024);
+              bdesc = make_smem_desc_sw128(b_base + k * 16 * 128, BK * 128, 1024);
+            }
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        umma_commit(&tmem_full[as]);
       }
-      umma_commit(tmem_full);
     }
     __syncwarp();
   } else {
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
+    const int half = (warp - 2) >> 2;
+    constexpr int CHUNKS = BN / 64;   // 32-column chunks per warp (half of the tile's columns)
     const bool vec_ok = ((p.ldc & 7) == 0) && ((p.N & 7) == 0) && (p.addend == nullptr || (p.ld_addend & 7) == 0) &&
                         (p.aux == nullptr || (p.ld_aux & 7) == 0);
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      __syncwarp();
-      tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), r);
-      tmem_ld_wait();
-      const int col0 = n0 + c * 32;
-      if (!row_ok || col0 >= p.N) continue;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      const bool full_chunk = (col0 + 32 <= p.N) && vec_ok;
-      if (full_chunk) {
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col0 + j);
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+    uint8_t* ebuf = epi_smem + (warp - 2) * GEMM_EPI_BUF;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int split = item / tiles_mn, rem = item - split * tiles_mn;
+      const int n0 = (rem / p.tiles_m) * BN, m0 = (rem % p.tiles_m) * BM;
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      const int row0 = m0 + q * 32;
+      const int row = row0 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t tmem_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
+      mbar_wait(&tmem_full[as], aph);
+      tc_fence_after();
+      if (p.tma_store) {
+        // Outputs leave through a per-warp swizzled staging tile and the TMA unit: full-line writes,
+        // automatic clipping at the M / N edges, fp32 accumulation as an L2 reduce-add.
+        auto release_tmem = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        };
+        auto flush = [&](const CUtensorMap* map, int col, bool reduce) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (reduce) tma_reduce_add_2d(map, ebuf, col, row0); else tma_store_2d(map, ebuf, col, row0);
+            tma_store_commit();
           }
-        }
-        if (p.addend != nullptr) {
-          const bf16* ap = p.addend + (int64_t)row * p.ld_addend + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float t[8];
-            load8(ap + j, t);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[j + u] += t[u];
-          }
-        }
-        if (p.act == ACT_GELU) {
-          bf16* xp = p.aux + (int64_t)row * p.ld_aux + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            store8(xp + j, v + j);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[j + u] = gelu_erf(v[j + u]);
-          }
-        } else if (p.act == ACT_GELU_BWD) {
-          const bf16* xp = p.aux + (int64_t)row * p.ld_aux + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float t[8];
-            load8(xp + j, t);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[j + u] *= gelu_erf_grad(t[u]);
-          }
-        }
+        };
+        auto staging_free = [&]() {   // the previous TMA store has finished READING the staging tile
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+        };
         if (p.out_kind == OUT_BF16) {
-          bf16* cp = reinterpret_cast<bf16*>(p.C) + (int64_t)row * p.ldc + col0;
+          constexpr int BLOCKS = BN / 128;   // 64-column output blocks per warp
+#pragma unroll 1
+          for (int blk = 0; blk < BLOCKS; ++blk) {
+            const int colb = n0 + (half * BLOCKS + blk) * 64;
+            if (colb >= p.N) {
+              if (blk == BLOCKS - 1) release_tmem();
+              continue;
+            }
+            const int passes = (p.act == ACT_GELU) ? 2 : 1;   // pass 0 of 2 writes the pre-activation
+#pragma unroll 1
+            for (int pass = 0; pass < passes; ++pass) {
+#pragma unroll 1
+              for (int sub = 0; sub < 2; ++sub) {
+                uint32_t r[32];
+                __syncwarp();
+                tmem_ld32(tmem_row + uint32_t((half * BLOCKS + blk) * 64 + sub * 32), r);
+                tmem_ld_wait();
+                if (blk == BLOCKS - 1 && pass == passes - 1 && sub == 1) release_tmem();
+                float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) store8(cp + j, v + j);
-        } else if (p.out_kind == OUT_F32) {
-          float* cp = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                const int col0 = colb + sub * 32;
+                if (col0 < p.N) gemm_epilogue_math(p, row, col0, row_ok, pass == passes - 1, v);
+                if (sub == 0) staging_free();
+                stage_bf16(ebuf, lane, sub * 4, v);
+              }
+              flush((passes == 2 && pass == 0) ? &tmAux : &tmC, colb, false);
+            }
+          }
         } else {
-          float* cp = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col0;
+          constexpr int CH = BN / 64;   // 32-column fp32 chunks per warp
+#pragma unroll 1
+          for (int c = 0; c < CH; ++c) {
+            const int cc = half * CH + c;
+            uint32_t r[32];
+            __syncwarp();
+            tmem_ld32(tmem_row + uint32_t(cc * 32), r);
+            tmem_ld_wait();
+            if (c == CH - 1) release_tmem();
+            const int col0 = n0 + cc * 32;
+            if (col0 >= p.N) continue;
+            float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + j), "f"(v[j]), "f"(v[j + 1]),
-                         "f"(v[j + 2]), "f"(v[j + 3])
-                         : "memory");
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            gemm_epilogue_math(p, row, col0, row_ok, true, v);
+            staging_free();
+            stage_f32(ebuf, lane, v);
+            flush(&tmC, col0, p.out_kind == OUT_F32_ATOMIC);
           }
         }
-      } else {  // ragged N edge or unaligned leading dimension: scalar path
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS; ++c) {
+          uint32_t r[32];
+          __syncwarp();
+          const int cc = half * CHUNKS + c;
+          tmem_ld32(tmem_row + uint32_t(cc * 32), r);
+          tmem_ld_wait();
+          if (c == CHUNKS - 1) {   // all TMEM reads of this warp are done: release the accumulator early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          }
+          const int col0 = n0 + cc * 32;
+          if (!row_ok || col0 >= p.N) continue;
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          if (col >= p.N) continue;
-          float x = v[j];
-          if (p.bias != nullptr) x += p.bias[col];
-          if (p.addend != nullptr) x += __bfloat162float(p.addend[(int64_t)row * p.ld_addend + col]);
-          if (p.act == ACT_GELU) {
-            p.aux[(int64_t)row * p.ld_aux + col] = __float2bfloat16(x);
-            x = gelu_erf(x);
-          } else if (p.act == ACT_GELU_BWD) {
-            x *= gelu_erf_grad(__bfloat162float(p.aux[(int64_t)row * p.ld_aux + col]));
-          }
-          if (p.out_kind == OUT_BF16) {
-            reinterpret_cast<bf16*>(p.C)[(int64_t)row * p.ldc + col] = __float2bfloat16(x);
-          } else if (p.out_kind == OUT_F32) {
-            reinterpret_cast<float*>(p.C)[(int64_t)row * p.ldc + col] = x;
-          } else {
-            atomicAdd(reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col, x);
-          }
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          gemm_epilogue_chunk(p, row, col0, v, vec_ok);
         }
       }
     }
+    if (p.tma_store && lane == 0) tma_store_wait_all();   // global writes complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // ---------------------------------------------------------------- host side
