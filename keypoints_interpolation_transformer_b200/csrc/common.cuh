@@ -51,7 +51,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 // exp(-u^2) with u = x/sqrt(2) is also the Gaussian the derivative needs.
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& gauss) {
   const float u = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
   const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
   gauss = __expf(-u * u);                       // exp(-x^2 / 2)
   const float half_erfc = 0.5f * poly * gauss;  // 0.5 * erfc(|u|)

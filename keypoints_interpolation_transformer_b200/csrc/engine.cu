@@ -433,9 +433,10 @@ static int linear_dgrad(KitEngine* e, const bf16* dy, int64_t ld_dy, const Linea
 }
 // dW[row0:row0+nrows, :] += dy^T x ; db[row0:...] += colsum(dy)
 static int linear_wgrad(KitEngine* e, const bf16* dy, int64_t ld_dy, const bf16* x, int64_t ldx, const LinearW& w, int row0,
-                        int nrows) {
+                        int nrows, bool bias_done = false) {
   KIT_TRY(eg(e, 1, dy, ld_dy, x, ldx, e->grads + w.w + (int64_t)row0 * w.cols, w.cols, nrows, w.cols, (int)e->M, nullptr,
              nullptr, 0, OUT_F32_ATOMIC, ACT_NONE, nullptr, 0));
+  if (bias_done) return KIT_OK;   // the LayerNorm backward that produced dy already summed its columns
   e->launches++;
   return colsum(dy, ld_dy, e->grads + w.b + row0, e->M, (int)up8(nrows), e->st);
 }
@@ -564,7 +565,7 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
   KIT_TRY(swiglu_bwd(e, e->g3, e->dec_out, L.swi_d, e->sd12, e->sdg, e->g0, e->g1));  // g1 = d dec_out
   e->launches++;
   KIT_TRY(ln_bwd(e->g1, e->da[nl - 1].y3, e->st_decn, e->st_decn + M, e->params + L.dec_norm.g, nullptr, e->g0,
-                 e->grads + L.dec_norm.g, e->grads + L.dec_norm.b, M, H, e->st));
+                 e->grads + L.dec_norm.g, e->grads + L.dec_norm.b, nullptr, M, H, e->st));
   bf16* dy = e->g0;  // gradient w.r.t. the current layer's output
   bool mem_grad_started = false;
   for (int l = nl - 1; l >= 0; --l) {
@@ -573,15 +574,15 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
     const bf16* y_in = (l == 0) ? e->y0 : e->da[l - 1].y3;
     // FFN block
     e->launches++;
-    KIT_TRY(ln_bwd(dy, a.s3, a.st3, a.st3 + M, e->params + w.n3.g, nullptr, e->g1, e->grads + w.n3.g, e->grads + w.n3.b, M, H, e->st));
-    KIT_TRY(linear_wgrad(e, e->g1, H, a.hh, FF, w.l2, 0, H));
+    KIT_TRY(ln_bwd(dy, a.s3, a.st3, a.st3 + M, e->params + w.n3.g, nullptr, e->g1, e->grads + w.n3.g, e->grads + w.n3.b, e->grads + w.l2.b, M, H, e->st));
+    KIT_TRY(linear_wgrad(e, e->g1, H, a.hh, FF, w.l2, 0, H, true));
     KIT_TRY(linear_dgrad(e, e->g1, H, w.l2, 0, H, e->gff, FF, nullptr, 0, ACT_GELU_BWD, a.z, FF));
     KIT_TRY(linear_wgrad(e, e->gff, FF, a.y2, H, w.l1, 0, FF));
     KIT_TRY(linear_dgrad(e, e->gff, FF, w.l1, 0, FF, e->g2, H, e->g1, H));  // g2 = d y2
     // cross-attention block
     e->launches++;
-    KIT_TRY(ln_bwd(e->g2, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1, e->grads + w.n2.g, e->grads + w.n2.b, M, H, e->st));
-    KIT_TRY(linear_wgrad(e, e->g1, H, a.aoc, H, w.ca.out, 0, H));
+    KIT_TRY(ln_bwd(e->g2, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1, e->grads + w.n2.g, e->grads + w.n2.b, e->grads + w.ca.out.b, M, H, e->st));
+    KIT_TRY(linear_wgrad(e, e->g1, H, a.aoc, H, w.ca.out, 0, H, true));
     KIT_TRY(linear_dgrad(e, e->g1, H, w.ca.out, 0, H, e->g2, H, nullptr, 0));  // g2 = d aoc
     KIT_TRY(eattn_bwd(e, a.qc, H, a.kvc, 2 * H, a.kvc + H, 2 * H, a.aoc, H, e->g2, H, a.lsec, e->gqkv, H, e->gkv, 2 * H,
                       e->gkv + H, 2 * H, nullptr));  // gqkv used as [M,H] dq
@@ -592,8 +593,8 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
     KIT_TRY(linear_dgrad(e, e->gqkv, H, w.ca.in, 0, H, e->g2, H, e->g1, H));  // g2 = d y1
     // self-attention block
     e->launches++;
-    KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1, e->grads + w.n1.g, e->grads + w.n1.b, M, H, e->st));
-    KIT_TRY(linear_wgrad(e, e->g1, H, a.ao, H, w.sa.out, 0, H));
+    KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1, e->grads + w.n1.g, e->grads + w.n1.b, e->grads + w.sa.out.b, M, H, e->st));
+    KIT_TRY(linear_wgrad(e, e->g1, H, a.ao, H, w.sa.out, 0, H, true));
     KIT_TRY(linear_dgrad(e, e->g1, H, w.sa.out, 0, H, e->g2, H, nullptr, 0));  // g2 = d ao
     KIT_TRY(eattn_bwd(e, a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, e->g2, H, a.lse, e->gqkv, 3 * H,
                       e->gqkv + H, 3 * H, e->gqkv + 2 * H, 3 * H, &e->dec_mask));
@@ -614,21 +615,21 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
   // ---- encoder
   e->launches++;
   KIT_TRY(ln_bwd(e->gmem, e->ea[nl - 1].x2, e->st_encn, e->st_encn + M, e->params + L.enc_norm.g, nullptr, e->g0,
-                 e->grads + L.enc_norm.g, e->grads + L.enc_norm.b, M, H, e->st));
+                 e->grads + L.enc_norm.g, e->grads + L.enc_norm.b, nullptr, M, H, e->st));
   bf16* dx = e->g0;
   for (int l = nl - 1; l >= 0; --l) {
     const EncW& w = L.enc[l];
     EncAct& a = e->ea[l];
     const bf16* x_in = (l == 0) ? e->x0 : e->ea[l - 1].x2;
     e->launches++;
-    KIT_TRY(ln_bwd(dx, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1, e->grads + w.n2.g, e->grads + w.n2.b, M, H, e->st));
-    KIT_TRY(linear_wgrad(e, e->g1, H, a.hh, FF, w.l2, 0, H));
+    KIT_TRY(ln_bwd(dx, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1, e->grads + w.n2.g, e->grads + w.n2.b, e->grads + w.l2.b, M, H, e->st));
+    KIT_TRY(linear_wgrad(e, e->g1, H, a.hh, FF, w.l2, 0, H, true));
     KIT_TRY(linear_dgrad(e, e->g1, H, w.l2, 0, H, e->gff, FF, nullptr, 0, ACT_GELU_BWD, a.z, FF));
     KIT_TRY(linear_wgrad(e, e->gff, FF, a.x1, H, w.l1, 0, FF));
     KIT_TRY(linear_dgrad(e, e->gff, FF, w.l1, 0, FF, e->g2, H, e->g1, H));  // g2 = d x1
     e->launches++;
-    KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1, e->grads + w.n1.g, e->grads + w.n1.b, M, H, e->st));
-    KIT_TRY(linear_wgrad(e, e->g1, H, a.ao, H, w.sa.out, 0, H));
+    KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1, e->grads + w.n1.g, e->grads + w.n1.b, e->grads + w.sa.out.b, M, H, e->st));
+    KIT_TRY(linear_wgrad(e, e->g1, H, a.ao, H, w.sa.out, 0, H, true));
     KIT_TRY(linear_dgrad(e, e->g1, H, w.sa.out, 0, H, e->g2, H, nullptr, 0));
     KIT_TRY(eattn_bwd(e, a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, e->g2, H, a.lse, e->gqkv, 3 * H,
                       e->gqkv + H, 3 * H, e->gqkv + 2 * H, 3 * H, &e->enc_mask));

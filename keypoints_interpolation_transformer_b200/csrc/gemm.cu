@@ -55,7 +55,7 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint6
   return KIT_OK;
 }
 
-constexpr int STAGES_BN128 = 6, STAGES_BN256 = 4;
+constexpr int STAGES_BN128 = 4, STAGES_BN256 = 3;
 
 static int g_num_sms = 0;
 
@@ -139,6 +139,17 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
   } else {
     plan->tmC = plan->tmA;
     plan->tmAux = plan->tmA;
+  }
+  // epilogue input tile (residual addend or GELU' pre-activation) through TMA as well
+  p.tma_in = 0;
+  if (p.tma_store && out_kind == OUT_BF16 && act != ACT_GELU) {
+    const bf16* in_ptr = (act == ACT_GELU_BWD) ? aux : addend;
+    const int64_t in_ld = (act == ACT_GELU_BWD) ? ld_aux : ld_addend;
+    const bool both = (act == ACT_GELU_BWD) && addend != nullptr;
+    if (in_ptr != nullptr && !both && (reinterpret_cast<uintptr_t>(in_ptr) & 15) == 0 && ((size_t)in_ld * 2) % 16 == 0) {
+      if ((rc = make_tensor_map_2d_typed(&plan->tmAux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, in_ptr, (uint64_t)N, (uint64_t)M, (uint64_t)in_ld * 2, 64, 32))) return rc;
+      p.tma_in = 1;
+    }
   }
   if (splits > kb_total) splits = kb_total;
   if (splits < 1) splits = 1;

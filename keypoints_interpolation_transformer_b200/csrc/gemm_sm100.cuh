@@ -32,6 +32,7 @@ struct GemmParams {
   int kb_per_split;  // 64-wide k-blocks per work item
   int tiles_m, tiles_n, splits;
   int tma_store;  // 1: outputs leave through shared memory + TMA store / reduce-add (clipped at the edges)
+  int tma_in;     // 1: the addend / GELU' pre-activation tile arrives through TMA (tmAux) instead of per-row loads
 };
 
 struct GemmPlan {
@@ -46,7 +47,7 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 320;
 constexpr int GEMM_EPI_WARPS = 8;
 
-constexpr int GEMM_EPI_BUF = 4096;  // per epilogue warp: 32 rows x 128 B staging tile for the TMA store
+constexpr int GEMM_EPI_BUF = 8192;  // per epilogue warp: two 32 rows x 128 B staging tiles for the TMA stores
 
 template <int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
@@ -56,9 +57,10 @@ constexpr int gemm_smem_bytes() {
 
 // bias / residual / activation on 32 accumulator columns of one row, in registers.  Columns >= N of a
 // ragged last chunk are computed on garbage and clipped by the TMA store.
-__device__ __forceinline__ void gemm_epilogue_math(const GemmParams& p, int row, int col0, bool row_ok, bool do_act,
+__device__ __forceinline__ void gemm_epilogue_math(const GemmParams& p, int row, int col0, bool row_ok, const float* in_vals,
                                                    float (&v)[32]) {
   const bool full = col0 + 32 <= p.N;
+  const bool do_act = true;
   if (p.bias != nullptr) {
     if (full) {
 #pragma unroll
@@ -71,6 +73,16 @@ __device__ __forceinline__ void gemm_epilogue_math(const GemmParams& p, int row,
       for (int j = 0; j < 32; ++j)
         if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
     }
+  }
+  if (in_vals != nullptr) {   // tile staged by TMA (zero-filled outside the tensor)
+    if (p.act == ACT_GELU_BWD) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(in_vals[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += in_vals[j];
+    }
+    return;
   }
   if (p.addend != nullptr && row_ok) {
     const bf16* ap = p.addend + (int64_t)row * p.ld_addend + col0;
@@ -89,10 +101,7 @@ __device__ __forceinline__ void gemm_epilogue_math(const GemmParams& p, int row,
     }
   }
   if (!do_act) return;
-  if (p.act == ACT_GELU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (p.act == ACT_GELU_BWD && row_ok) {
+  if (p.act == ACT_GELU_BWD && row_ok) {
     const bf16* xp = p.aux + (int64_t)row * p.ld_aux + col0;
     if (full) {
 #pragma unroll
@@ -219,7 +228,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* in_bars = tmem_empty + 2;     // [GEMM_EPI_WARPS] epilogue input tiles (addend / GELU' aux)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bars + GEMM_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb_total = (p.K + BK - 1) / BK;
@@ -238,6 +248,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], GEMM_EPI_WARPS);
     }
+    for (int s = 0; s < GEMM_EPI_WARPS; ++s) mbar_init(&in_bars[s], 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -320,6 +331,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const bool vec_ok = ((p.ldc & 7) == 0) && ((p.N & 7) == 0) && (p.addend == nullptr || (p.ld_addend & 7) == 0) &&
                         (p.aux == nullptr || (p.ld_aux & 7) == 0);
     uint8_t* ebuf = epi_smem + (warp - 2) * GEMM_EPI_BUF;
+    uint64_t* in_bar = &in_bars[warp - 2];
+    uint32_t in_ph = 0;
+    const bool tma_in = p.tma_in != 0 && p.out_kind == OUT_BF16;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int split = item / tiles_mn, rem = item - split * tiles_mn;
@@ -329,6 +343,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const uint32_t tmem_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
+      auto issue_in = [&](int col) {   // TMA: [32 rows x 64 cols] bf16 input tile -> second staging tile
+        if (lane == 0) {
+          mbar_arrive_expect_tx(in_bar, 4096);
+          tma_load_2d(ebuf + 4096, &tmAux, in_bar, col, row0);
+        }
+      };
+      if (tma_in && n0 + half * (BN / 2) < p.N) issue_in(n0 + half * (BN / 2));   // overlaps the wait for the MMAs
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
       if (p.tma_store) {
@@ -360,25 +381,52 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
               if (blk == BLOCKS - 1) release_tmem();
               continue;
             }
-            const int passes = (p.act == ACT_GELU) ? 2 : 1;   // pass 0 of 2 writes the pre-activation
+            const bool gelu = p.act == ACT_GELU;
+            if (tma_in) {
+              mbar_wait(in_bar, in_ph);
+              in_ph ^= 1;
+            }
 #pragma unroll 1
-            for (int pass = 0; pass < passes; ++pass) {
-#pragma unroll 1
-              for (int sub = 0; sub < 2; ++sub) {
-                uint32_t r[32];
-                __syncwarp();
-                tmem_ld32(tmem_row + uint32_t((half * BLOCKS + blk) * 64 + sub * 32), r);
-                tmem_ld_wait();
-                if (blk == BLOCKS - 1 && pass == passes - 1 && sub == 1) release_tmem();
-                float v[32];
+            for (int sub = 0; sub < 2; ++sub) {
+              uint32_t r[32];
+              __syncwarp();
+              tmem_ld32(tmem_row + uint32_t((half * BLOCKS + blk) * 64 + sub * 32), r);
+              float in_vals[32];
+              if (tma_in) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                const int col0 = colb + sub * 32;
-                if (col0 < p.N) gemm_epilogue_math(p, row, col0, row_ok, pass == passes - 1, v);
-                if (sub == 0) staging_free();
-                stage_bf16(ebuf, lane, sub * 4, v);
+                for (int i = 0; i < 4; ++i) {
+                  const uint4 u = *reinterpret_cast<const uint4*>(ebuf + 4096 + lane * 128 + (((sub * 4 + i) ^ (lane & 7)) << 4));
+                  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+                  in_vals[8 * i] = a.x; in_vals[8 * i + 1] = a.y; in_vals[8 * i + 2] = b.x; in_vals[8 * i + 3] = b.y;
+                  in_vals[8 * i + 4] = c.x; in_vals[8 * i + 5] = c.y; in_vals[8 * i + 6] = d.x; in_vals[8 * i + 7] = d.y;
+                }
+                if (sub == 1) {   // input tile consumed: prefetch the next block's
+                  __syncwarp();
+                  const int next = colb + 64;
+                  if (blk + 1 < BLOCKS && next < p.N) issue_in(next);
+                }
               }
-              flush((passes == 2 && pass == 0) ? &tmAux : &tmC, colb, false);
+              tmem_ld_wait();
+              if (blk == BLOCKS - 1 && sub == 1) release_tmem();
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+              const int col0 = colb + sub * 32;
+              if (col0 < p.N) gemm_epilogue_math(p, row, col0, row_ok, tma_in ? in_vals : nullptr, v);
+              if (sub == 0) staging_free();
+              if (gelu) {   // pre-activation to the second staging tile, activation to the first
+                stage_bf16(ebuf + 4096, lane, sub * 4, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+              }
+              stage_bf16(ebuf, lane, sub * 4, v);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (gelu) tma_store_2d(&tmAux, ebuf + 4096, colb, row0);
+              tma_store_2d(&tmC, ebuf, colb, row0);
+              tma_store_commit();
             }
           }
         } else {
@@ -396,7 +444,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            gemm_epilogue_math(p, row, col0, row_ok, true, v);
+            gemm_epilogue_math(p, row, col0, row_ok, nullptr, v);
             staging_free();
             stage_f32(ebuf, lane, v);
             flush(&tmC, col0, p.out_kind == OUT_F32_ATOMIC);

@@ -215,10 +215,10 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restric
                               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                               const float* __restrict__ gamma, const bf16* __restrict__ addend,
                               bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                              int64_t M, int H) {
+                              float* __restrict__ dxsum, int64_t M, int H) {
   __shared__ float s_buf[ROW_WARPS][NV * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  RowVec<NV> accg, accb, gm;
+  RowVec<NV> accg, accb, accx, gm;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (lane + 32 * i) * 8;
@@ -226,6 +226,7 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restric
     for (int u = 0; u < 8; ++u) {
       accg.v[i][u] = 0.f;
       accb.v[i][u] = 0.f;
+      accx.v[i][u] = 0.f;
       gm.v[i][u] = 0.f;
     }
     if (c < H) load8(gamma + c, gm.v[i]);
@@ -262,6 +263,7 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restric
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         float r = rstd * (g.v[i][u] - s1 - x.v[i][u] * s2);
+        accx.v[i][u] += r;   // column sums of the LN-input gradient = bias gradient of the producing Linear
         if (addend != nullptr) r += ad.v[i][u];
         g.v[i][u] = r;
       }
@@ -269,6 +271,7 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restric
   }
   block_col_reduce_atomic<NV>(accg, dgamma, H, s_buf);
   block_col_reduce_atomic<NV>(accb, dbeta, H, s_buf);
+  if (dxsum != nullptr) block_col_reduce_atomic<NV>(accx, dxsum, H, s_buf);
 }
 
 // ---------------------------------------------------------------- SwiGLU gate (model.py:18-22)
@@ -514,11 +517,11 @@ int add_ln_fwd(const bf16* a, const bf16* b, const float* gamma, const float* be
   return KIT_OK;
 }
 int ln_bwd(const bf16* dy, const bf16* s_saved, const float* mean, const float* rstd, const float* gamma,
-           const bf16* addend, bf16* dx, float* dgamma, float* dbeta, int64_t M, int H, cudaStream_t st) {
+           const bf16* addend, bf16* dx, float* dgamma, float* dbeta, float* dxsum, int64_t M, int H, cudaStream_t st) {
   int rc = check_h(H);
   if (rc) return rc;
   KIT_NV_DISPATCH(H, (ln_bwd_kernel<NV><<<reduce_blocks(M), 256, 0, st>>>(dy, s_saved, mean, rstd, gamma, addend, dx,
-                                                                         dgamma, dbeta, M, H)));
+                                                                         dgamma, dbeta, dxsum, M, H)));
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
@@ -594,7 +597,7 @@ extern "C" int kit_layernorm_bwd(const void* dy, const void* sum_saved, const fl
                                  const float* gamma, const void* addend, void* dx, float* dgamma, float* dbeta, int64_t M,
                                  int32_t H, void* stream) {
   return ln_bwd((const bf16*)dy, (const bf16*)sum_saved, mean, rstd, gamma, (const bf16*)addend, (bf16*)dx, dgamma, dbeta,
-                M, H, (cudaStream_t)stream);
+                nullptr, M, H, (cudaStream_t)stream);
 }
 extern "C" int kit_cast_fp32_to_bf16_padded(const float* src, int64_t rows, int64_t cols, int64_t src_ld, void* dst,
                                             int64_t dst_ld, void* stream) {

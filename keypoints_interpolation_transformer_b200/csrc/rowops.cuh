@@ -22,7 +22,7 @@ int embed_post_bwd(const bf16* dout, const bf16* raw, const bf16* addend, bf16* 
 int add_ln_fwd(const bf16* a, const bf16* b, const float* gamma, const float* beta, bf16* sum_out, bf16* y, float* mean,
                float* rstd, int64_t M, int H, cudaStream_t st);
 int ln_bwd(const bf16* dy, const bf16* s_saved, const float* mean, const float* rstd, const float* gamma,
-           const bf16* addend, bf16* dx, float* dgamma, float* dbeta, int64_t M, int H, cudaStream_t st);
+           const bf16* addend, bf16* dx, float* dgamma, float* dbeta, float* dxsum, int64_t M, int H, cudaStream_t st);
 int swiglu_gate_fwd(const bf16* x12, bf16* g, int64_t M, int H, cudaStream_t st);
 int swiglu_gate_bwd(const bf16* dg, const bf16* x12, bf16* dx12, int64_t M, int H, cudaStream_t st);
 int final_norm_silu_fwd(const bf16* dec, const bf16* femb, bf16* z_out, bf16* out, int64_t M, int H, cudaStream_t st);
