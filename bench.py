@@ -129,6 +129,10 @@ def gpu_run(args):
     import torch.distributed as dist
     from keypoints_interpolation_transformer_b200 import model, optim, parallel, synthetic, train
 
+    # keep stdout clean for the ONE JSON line (NCCL prints its version banner there)
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = parallel.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -218,6 +222,7 @@ def gpu_run(args):
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return
     gemm_ms = acc["gemm_tn"][0] + acc["gemm_wgrad"][0]
     gemm_fl = acc["gemm_tn"][2] + acc["gemm_wgrad"][2]
@@ -256,9 +261,12 @@ def gpu_run(args):
         "cpu_baseline": None if cpu is None else {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                                                  "sample": cpu["sample"]},
     }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

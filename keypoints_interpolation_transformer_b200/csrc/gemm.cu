@@ -24,7 +24,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int make_tensor_map_2d_typed(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, uint64_t inner,
-                                    uint64_t outer, uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_outer) {
+                                    uint64_t outer, uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_outer,
+                                    CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   KIT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   cuuint64_t dims[2] = {inner, outer};
@@ -32,7 +33,7 @@ static int make_tensor_map_2d_typed(CUtensorMap* map, CUtensorMapDataType dtype,
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   KIT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return KIT_OK;
 }
@@ -128,13 +129,13 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
   if (act == ACT_GELU) p.tma_store = p.tma_store && ((reinterpret_cast<uintptr_t>(aux) & 15) == 0) && (((size_t)ld_aux * 2) % 16 == 0);
   if (p.tma_store) {
     if (out_kind == OUT_BF16) {
-      if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 64, 32))) return rc;
+      if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     } else {
-      if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 4, 32, 32))) return rc;
+      if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     }
     plan->tmAux = plan->tmC;
     if (act == ACT_GELU) {
-      if ((rc = make_tensor_map_2d_typed(&plan->tmAux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, aux, (uint64_t)N, (uint64_t)M, (uint64_t)ld_aux * 2, 64, 32))) return rc;
+      if ((rc = make_tensor_map_2d_typed(&plan->tmAux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, aux, (uint64_t)N, (uint64_t)M, (uint64_t)ld_aux * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     }
   } else {
     plan->tmC = plan->tmA;
@@ -147,7 +148,7 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
     const int64_t in_ld = (act == ACT_GELU_BWD) ? ld_aux : ld_addend;
     const bool both = (act == ACT_GELU_BWD) && addend != nullptr;
     if (in_ptr != nullptr && !both && (reinterpret_cast<uintptr_t>(in_ptr) & 15) == 0 && ((size_t)in_ld * 2) % 16 == 0) {
-      if ((rc = make_tensor_map_2d_typed(&plan->tmAux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, in_ptr, (uint64_t)N, (uint64_t)M, (uint64_t)in_ld * 2, 64, 32))) return rc;
+      if ((rc = make_tensor_map_2d_typed(&plan->tmAux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, in_ptr, (uint64_t)N, (uint64_t)M, (uint64_t)in_ld * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
       p.tma_in = 1;
     }
   }
@@ -164,13 +165,13 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
 int gemm_launch(const GemmPlan* plan, cudaStream_t stream) {
   const dim3 grid(plan->grid);
   if (plan->mode == 0 && plan->bn == 128) {
-    gemm_tcgen05_kernel<128, 0, STAGES_BN128><<<grid, GEMM_THREADS, gemm_smem_bytes<128, STAGES_BN128>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
+    gemm_tcgen05_kernel<128, 0, STAGES_BN128><<<grid, gemm_threads<128>(), gemm_smem_bytes<128, STAGES_BN128>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
   } else if (plan->mode == 0) {
-    gemm_tcgen05_kernel<256, 0, STAGES_BN256><<<grid, GEMM_THREADS, gemm_smem_bytes<256, STAGES_BN256>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
+    gemm_tcgen05_kernel<256, 0, STAGES_BN256><<<grid, gemm_threads<256>(), gemm_smem_bytes<256, STAGES_BN256>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
   } else if (plan->bn == 128) {
-    gemm_tcgen05_kernel<128, 1, STAGES_BN128><<<grid, GEMM_THREADS, gemm_smem_bytes<128, STAGES_BN128>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
+    gemm_tcgen05_kernel<128, 1, STAGES_BN128><<<grid, gemm_threads<128>(), gemm_smem_bytes<128, STAGES_BN128>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
   } else {
-    gemm_tcgen05_kernel<256, 1, STAGES_BN256><<<grid, GEMM_THREADS, gemm_smem_bytes<256, STAGES_BN256>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
+    gemm_tcgen05_kernel<256, 1, STAGES_BN256><<<grid, gemm_threads<256>(), gemm_smem_bytes<256, STAGES_BN256>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
   }
   KIT_LAUNCH_CHECK();
   return KIT_OK;

@@ -9,8 +9,9 @@
 //   MODE 0 (TN)    C[M,N] = A[M,K] * B[N,K]^T      both operands K-major      (y = x W^T, dx = dy W)
 //   MODE 1 (wgrad) C[M,N] = A[K,M]^T * B[K,N]      both operands MN-major     (dW = dy^T x), split-K
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..9 = epilogue (TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2.. = epilogue
+// (BN/16 of them: TMEM lane quadrant = warp % 4, 64-column group = (warp - 2) / 4).  The epilogue is
+// ALU / latency bound (GELU, casts), hence the many warps.
 #pragma once
 #include "common.cuh"
 
@@ -44,14 +45,18 @@ struct GemmPlan {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 320;
-constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_MAX_EPI_WARPS = 16;
+constexpr int GEMM_EPI_BUF = 4096;  // per epilogue warp: 2 KB out tile (bf16, 64B-swizzled) + 2 KB second tile
+                                    // (GELU pre-activation out / TMA-staged input), or one 4 KB fp32 out tile
 
-constexpr int GEMM_EPI_BUF = 8192;  // per epilogue warp: two 32 rows x 128 B staging tiles for the TMA stores
+template <int BN>
+constexpr int gemm_epi_warps() { return BN / 16; }
+template <int BN>
+constexpr int gemm_threads() { return 64 + 32 * gemm_epi_warps<BN>(); }
 
 template <int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
-  return STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + GEMM_EPI_WARPS * GEMM_EPI_BUF + 1024 /*align slack*/ +
+  return STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + gemm_epi_warps<BN>() * GEMM_EPI_BUF + 1024 /*align slack*/ +
          256 /*barriers*/;
 }
 
@@ -118,12 +123,22 @@ __device__ __forceinline__ void gemm_epilogue_math(const GemmParams& p, int row,
     }
   }
 }
-// 32 bf16 values of this lane's row into the warp's 128B-swizzled staging tile (16-byte chunks j0..j0+3)
-__device__ __forceinline__ void stage_bf16(uint8_t* ebuf, int lane, int j0, const float (&v)[32]) {
+// 32 bf16 values of this lane's row into a [32 rows x 64 B] tile, 64B-swizzled (conflict-free, TMA SWIZZLE_64B)
+__device__ __forceinline__ void stage_bf16(uint8_t* buf, int lane, const float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
-    *reinterpret_cast<uint4*>(ebuf + lane * 128 + (((j0 + i) ^ (lane & 7)) << 4)) = pack8(&v[8 * i]);
+    *reinterpret_cast<uint4*>(buf + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = pack8(&v[8 * i]);
 }
+__device__ __forceinline__ void unstage_bf16(const uint8_t* buf, int lane, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = *reinterpret_cast<const uint4*>(buf + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4));
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    v[8 * i] = a.x; v[8 * i + 1] = a.y; v[8 * i + 2] = b.x; v[8 * i + 3] = b.y;
+    v[8 * i + 4] = c.x; v[8 * i + 5] = c.y; v[8 * i + 6] = d.x; v[8 * i + 7] = d.y;
+  }
+}
+// 32 fp32 values into a [32 rows x 128 B] tile, 128B-swizzled
 __device__ __forceinline__ void stage_f32(uint8_t* ebuf, int lane, const float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -212,7 +227,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, int row
 }
 
 template <int BN, int MODE, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                          const __grid_constant__ CUtensorMap tmB,
                                                                          const __grid_constant__ CUtensorMap tmC,
                                                                          const __grid_constant__ CUtensorMap tmAux,
@@ -224,12 +239,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + GEMM_EPI_WARPS * GEMM_EPI_BUF);
+  constexpr int EPI_WARPS = gemm_epi_warps<BN>();
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + EPI_WARPS * GEMM_EPI_BUF);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
-  uint64_t* in_bars = tmem_empty + 2;     // [GEMM_EPI_WARPS] epilogue input tiles (addend / GELU' aux)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bars + GEMM_EPI_WARPS);
+  uint64_t* in_bars = tmem_empty + 2;     // [EPI_WARPS] epilogue input tiles (addend / GELU' aux)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bars + GEMM_MAX_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb_total = (p.K + BK - 1) / BK;
@@ -246,9 +262,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], GEMM_EPI_WARPS);
+      mbar_init(&tmem_empty[s], EPI_WARPS);
     }
-    for (int s = 0; s < GEMM_EPI_WARPS; ++s) mbar_init(&in_bars[s], 1);
+    for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&in_bars[s], 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -326,14 +342,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     __syncwarp();
   } else {
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    constexpr int CHUNKS = BN / 64;   // 32-column chunks per warp (half of the tile's columns)
+    const int cg = (warp - 2) >> 2;   // 64-column group of the tile owned by this warp
     const bool vec_ok = ((p.ldc & 7) == 0) && ((p.N & 7) == 0) && (p.addend == nullptr || (p.ld_addend & 7) == 0) &&
                         (p.aux == nullptr || (p.ld_aux & 7) == 0);
     uint8_t* ebuf = epi_smem + (warp - 2) * GEMM_EPI_BUF;
+    uint8_t* ebuf2 = ebuf + 2048;
     uint64_t* in_bar = &in_bars[warp - 2];
     uint32_t in_ph = 0;
     const bool tma_in = p.tma_in != 0 && p.out_kind == OUT_BF16;
+    const bool gelu = p.act == ACT_GELU;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int split = item / tiles_mn, rem = item - split * tiles_mn;
@@ -342,130 +359,84 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const int row0 = m0 + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
-      const uint32_t tmem_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
-      auto issue_in = [&](int col) {   // TMA: [32 rows x 64 cols] bf16 input tile -> second staging tile
+      const int colg = n0 + cg * 64;
+      const uint32_t tmem_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + cg * 64);
+      auto issue_in = [&](int col) {   // TMA: [32 rows x 32 cols] bf16 input tile -> second staging tile
         if (lane == 0) {
-          mbar_arrive_expect_tx(in_bar, 4096);
-          tma_load_2d(ebuf + 4096, &tmAux, in_bar, col, row0);
+          mbar_arrive_expect_tx(in_bar, 2048);
+          tma_load_2d(ebuf2, &tmAux, in_bar, col, row0);
         }
       };
-      if (tma_in && n0 + half * (BN / 2) < p.N) issue_in(n0 + half * (BN / 2));   // overlaps the wait for the MMAs
+      auto release_tmem = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      };
+      auto staging_free = [&]() {   // the previous TMA stores have finished READING the staging tiles
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      };
+      if (tma_in && colg < p.N) issue_in(colg);   // overlaps the wait for the MMAs
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
-      if (p.tma_store) {
-        // Outputs leave through a per-warp swizzled staging tile and the TMA unit: full-line writes,
-        // automatic clipping at the M / N edges, fp32 accumulation as an L2 reduce-add.
-        auto release_tmem = [&]() {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[as]);
-        };
-        auto flush = [&](const CUtensorMap* map, int col, bool reduce) {
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        const int col0 = colg + sub * 32;
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_row + uint32_t(sub * 32), r);
+        float v[32];
+        if (col0 >= p.N) {   // nothing to write (uniform): only keep the TMEM protocol alive
+          tmem_ld_wait();
+          if (sub == 1) release_tmem();
+          continue;
+        }
+        if (p.tma_store && p.out_kind == OUT_BF16) {
+          float in_vals[32];
+          if (tma_in) {
+            mbar_wait(in_bar, in_ph);
+            in_ph ^= 1;
+            unstage_bf16(ebuf2, lane, in_vals);
+            __syncwarp();
+            if (sub == 0 && col0 + 32 < p.N) issue_in(col0 + 32);   // prefetch the second half's input tile
+          }
+          tmem_ld_wait();
+          if (sub == 1) release_tmem();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          gemm_epilogue_math(p, row, col0, row_ok, tma_in ? in_vals : nullptr, v);
+          staging_free();
+          if (gelu) {   // pre-activation to the second tile, activation to the first
+            stage_bf16(ebuf2, lane, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          stage_bf16(ebuf, lane, v);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (reduce) tma_reduce_add_2d(map, ebuf, col, row0); else tma_store_2d(map, ebuf, col, row0);
+            if (gelu) tma_store_2d(&tmAux, ebuf2, col0, row0);
+            tma_store_2d(&tmC, ebuf, col0, row0);
             tma_store_commit();
           }
-        };
-        auto staging_free = [&]() {   // the previous TMA store has finished READING the staging tile
-          if (lane == 0) tma_store_wait_read();
-          __syncwarp();
-        };
-        if (p.out_kind == OUT_BF16) {
-          constexpr int BLOCKS = BN / 128;   // 64-column output blocks per warp
-#pragma unroll 1
-          for (int blk = 0; blk < BLOCKS; ++blk) {
-            const int colb = n0 + (half * BLOCKS + blk) * 64;
-            if (colb >= p.N) {
-              if (blk == BLOCKS - 1) release_tmem();
-              continue;
-            }
-            const bool gelu = p.act == ACT_GELU;
-            if (tma_in) {
-              mbar_wait(in_bar, in_ph);
-              in_ph ^= 1;
-            }
-#pragma unroll 1
-            for (int sub = 0; sub < 2; ++sub) {
-              uint32_t r[32];
-              __syncwarp();
-              tmem_ld32(tmem_row + uint32_t((half * BLOCKS + blk) * 64 + sub * 32), r);
-              float in_vals[32];
-              if (tma_in) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint4 u = *reinterpret_cast<const uint4*>(ebuf + 4096 + lane * 128 + (((sub * 4 + i) ^ (lane & 7)) << 4));
-                  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-                  in_vals[8 * i] = a.x; in_vals[8 * i + 1] = a.y; in_vals[8 * i + 2] = b.x; in_vals[8 * i + 3] = b.y;
-                  in_vals[8 * i + 4] = c.x; in_vals[8 * i + 5] = c.y; in_vals[8 * i + 6] = d.x; in_vals[8 * i + 7] = d.y;
-                }
-                if (sub == 1) {   // input tile consumed: prefetch the next block's
-                  __syncwarp();
-                  const int next = colb + 64;
-                  if (blk + 1 < BLOCKS && next < p.N) issue_in(next);
-                }
-              }
-              tmem_ld_wait();
-              if (blk == BLOCKS - 1 && sub == 1) release_tmem();
-              float v[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-              const int col0 = colb + sub * 32;
-              if (col0 < p.N) gemm_epilogue_math(p, row, col0, row_ok, tma_in ? in_vals : nullptr, v);
-              if (sub == 0) staging_free();
-              if (gelu) {   // pre-activation to the second staging tile, activation to the first
-                stage_bf16(ebuf + 4096, lane, sub * 4, v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-              }
-              stage_bf16(ebuf, lane, sub * 4, v);
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              if (gelu) tma_store_2d(&tmAux, ebuf + 4096, colb, row0);
-              tma_store_2d(&tmC, ebuf, colb, row0);
-              tma_store_commit();
-            }
-          }
-        } else {
-          constexpr int CH = BN / 64;   // 32-column fp32 chunks per warp
-#pragma unroll 1
-          for (int c = 0; c < CH; ++c) {
-            const int cc = half * CH + c;
-            uint32_t r[32];
-            __syncwarp();
-            tmem_ld32(tmem_row + uint32_t(cc * 32), r);
-            tmem_ld_wait();
-            if (c == CH - 1) release_tmem();
-            const int col0 = n0 + cc * 32;
-            if (col0 >= p.N) continue;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            gemm_epilogue_math(p, row, col0, row_ok, nullptr, v);
-            staging_free();
-            stage_f32(ebuf, lane, v);
-            flush(&tmC, col0, p.out_kind == OUT_F32_ATOMIC);
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < CHUNKS; ++c) {
-          uint32_t r[32];
-          __syncwarp();
-          const int cc = half * CHUNKS + c;
-          tmem_ld32(tmem_row + uint32_t(cc * 32), r);
+        } else if (p.tma_store) {   // fp32 tile: plain store or L2 reduce-add (split-K weight gradients)
           tmem_ld_wait();
-          if (c == CHUNKS - 1) {   // all TMEM reads of this warp are done: release the accumulator early
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          if (sub == 1) release_tmem();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          gemm_epilogue_math(p, row, col0, row_ok, nullptr, v);
+          staging_free();
+          stage_f32(ebuf, lane, v);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.out_kind == OUT_F32_ATOMIC) tma_reduce_add_2d(&tmC, ebuf, col0, row0); else tma_store_2d(&tmC, ebuf, col0, row0);
+            tma_store_commit();
           }
-          const int col0 = n0 + cc * 32;
-          if (!row_ok || col0 >= p.N) continue;
-          float v[32];
+        } else {   // layouts a tensor map cannot describe (unaligned pitch): direct global accesses
+          tmem_ld_wait();
+          if (sub == 1) release_tmem();
+          if (!row_ok) continue;
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           gemm_epilogue_chunk(p, row, col0, v, vec_ok);
