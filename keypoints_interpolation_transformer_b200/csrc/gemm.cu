@@ -57,6 +57,7 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint6
 }
 
 constexpr int STAGES_BN128 = 4, STAGES_BN256 = 3;
+constexpr int CLUSTER_BN256 = 2;   // CTA pairs share the B tile through TMA multicast
 
 static int g_num_sms = 0;
 
@@ -65,13 +66,13 @@ int gemm_init_attributes() {
   static std::once_flag once;
   std::call_once(once, []() {
     cudaError_t e[4];
-    e[0] = cudaFuncSetAttribute(gemm_tcgen05_kernel<128, 0, STAGES_BN128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e[0] = cudaFuncSetAttribute(gemm_tcgen05_kernel<128, 0, STAGES_BN128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 gemm_smem_bytes<128, STAGES_BN128>());
-    e[1] = cudaFuncSetAttribute(gemm_tcgen05_kernel<256, 0, STAGES_BN256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e[1] = cudaFuncSetAttribute(gemm_tcgen05_kernel<256, 0, STAGES_BN256, CLUSTER_BN256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 gemm_smem_bytes<256, STAGES_BN256>());
-    e[2] = cudaFuncSetAttribute(gemm_tcgen05_kernel<128, 1, STAGES_BN128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e[2] = cudaFuncSetAttribute(gemm_tcgen05_kernel<128, 1, STAGES_BN128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 gemm_smem_bytes<128, STAGES_BN128>());
-    e[3] = cudaFuncSetAttribute(gemm_tcgen05_kernel<256, 1, STAGES_BN256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e[3] = cudaFuncSetAttribute(gemm_tcgen05_kernel<256, 1, STAGES_BN256, CLUSTER_BN256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 gemm_smem_bytes<256, STAGES_BN256>());
     status = 0;
     for (int i = 0; i < 4; ++i) {
@@ -114,14 +115,19 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
   if (mode == 0) {
     // A [M,K] K-major: box 64(k) x 128(m);  B [N,K] K-major: box 64(k) x BN(n)
     if ((rc = make_tensor_map_2d(&plan->tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, GEMM_BK, GEMM_BM))) return rc;
-    if ((rc = make_tensor_map_2d(&plan->tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, GEMM_BK, bn))) return rc;
+    const int cl = (bn == 256) ? CLUSTER_BN256 : 1;
+    if ((rc = make_tensor_map_2d(&plan->tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, GEMM_BK, bn / cl))) return rc;
     splits = split_k > 1 ? split_k : 1;
   } else {
     // A [K,M] row-major (MN-major operand): box 64(m) x 64(k);  B [K,N]: box 64(n) x 64(k)
     if ((rc = make_tensor_map_2d(&plan->tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, GEMM_BK))) return rc;
     if ((rc = make_tensor_map_2d(&plan->tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, GEMM_BK))) return rc;
     splits = split_k;
-    if (splits <= 0) splits = (g_num_sms + tiles - 1) / tiles;   // about one work item per SM
+    if (splits <= 0) {   // about one work item per cluster
+      const int clm = (bn == 256) ? CLUSTER_BN256 : 1;
+      const int groups = ((p.tiles_m + clm - 1) / clm) * p.tiles_n;
+      splits = (g_num_sms / clm) / groups;
+    }
   }
   // outputs through shared memory + TMA (store / fp32 reduce-add) whenever the layout allows a tensor map
   const size_t esize = (out_kind == OUT_BF16) ? 2 : 4;
@@ -157,24 +163,39 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
   KIT_REQUIRE(splits == 1 || out_kind == OUT_F32_ATOMIC, "split-K needs the atomic fp32 epilogue");
   p.kb_per_split = (kb_total + splits - 1) / splits;
   p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
-  const int items = tiles * p.splits;
-  plan->grid = items < g_num_sms ? items : g_num_sms;
+  const int clw = (bn == 256) ? CLUSTER_BN256 : 1;
+  const int items = ((p.tiles_m + clw - 1) / clw) * p.tiles_n * p.splits;   // work items per cluster
+  const int max_clusters = g_num_sms / clw;
+  plan->grid = (items < max_clusters ? items : max_clusters) * clw;
+  return KIT_OK;
+}
+
+template <typename KernelT>
+static int launch_one(KernelT kernel, int grid, int threads, int smem, int cluster, cudaStream_t stream, const GemmPlan* plan) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  KIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p));
   return KIT_OK;
 }
 
 int gemm_launch(const GemmPlan* plan, cudaStream_t stream) {
-  const dim3 grid(plan->grid);
-  if (plan->mode == 0 && plan->bn == 128) {
-    gemm_tcgen05_kernel<128, 0, STAGES_BN128><<<grid, gemm_threads<128>(), gemm_smem_bytes<128, STAGES_BN128>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
-  } else if (plan->mode == 0) {
-    gemm_tcgen05_kernel<256, 0, STAGES_BN256><<<grid, gemm_threads<256>(), gemm_smem_bytes<256, STAGES_BN256>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
-  } else if (plan->bn == 128) {
-    gemm_tcgen05_kernel<128, 1, STAGES_BN128><<<grid, gemm_threads<128>(), gemm_smem_bytes<128, STAGES_BN128>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
-  } else {
-    gemm_tcgen05_kernel<256, 1, STAGES_BN256><<<grid, gemm_threads<256>(), gemm_smem_bytes<256, STAGES_BN256>(), stream>>>(plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p);
-  }
-  KIT_LAUNCH_CHECK();
-  return KIT_OK;
+  if (plan->mode == 0 && plan->bn == 128)
+    return launch_one(gemm_tcgen05_kernel<128, 0, STAGES_BN128, 1>, plan->grid, gemm_threads<128>(), gemm_smem_bytes<128, STAGES_BN128>(), 1, stream, plan);
+  if (plan->mode == 0)
+    return launch_one(gemm_tcgen05_kernel<256, 0, STAGES_BN256, CLUSTER_BN256>, plan->grid, gemm_threads<256>(), gemm_smem_bytes<256, STAGES_BN256>(), CLUSTER_BN256, stream, plan);
+  if (plan->bn == 128)
+    return launch_one(gemm_tcgen05_kernel<128, 1, STAGES_BN128, 1>, plan->grid, gemm_threads<128>(), gemm_smem_bytes<128, STAGES_BN128>(), 1, stream, plan);
+  return launch_one(gemm_tcgen05_kernel<256, 1, STAGES_BN256, CLUSTER_BN256>, plan->grid, gemm_threads<256>(), gemm_smem_bytes<256, STAGES_BN256>(), CLUSTER_BN256, stream, plan);
 }
 
 }  // namespace kit

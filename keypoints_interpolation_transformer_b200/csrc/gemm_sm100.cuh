@@ -226,7 +226,9 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, int row
   }
 }
 
-template <int BN, int MODE, int STAGES>
+// CL = 2: CTA pairs (thread-block cluster) work on two vertically adjacent M tiles of the same N tile; each CTA
+// fetches half of the shared B tile and TMA-multicasts it to both, cutting the L2 -> SM operand traffic by a third.
+template <int BN, int MODE, int STAGES, int CL>
 __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                          const __grid_constant__ CUtensorMap tmB,
                                                                          const __grid_constant__ CUtensorMap tmC,
@@ -249,7 +251,11 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb_total = (p.K + BK - 1) / BK;
-  const int tiles_mn = p.tiles_m * p.tiles_n;
+  // work items are (split, n tile, group of CL m tiles); CTA `rank` of a cluster takes m tile CL*group + rank
+  const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  const int first_item = blockIdx.x / CL, item_stride = gridDim.x / CL;
+  const int groups_m = (p.tiles_m + CL - 1) / CL;
+  const int tiles_mn = groups_m * p.tiles_n;
   const int n_items = tiles_mn * p.splits;
 
   if (threadIdx.x == 0) {
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
     if (p.tma_store) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);   // every CTA of the cluster must have consumed the slot (multicast B)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -271,15 +277,16 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peer barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t cnt = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int item = first_item; item < n_items; item += item_stride) {
         const int split = item / tiles_mn, rem = item - split * tiles_mn;
-        const int n0 = (rem / p.tiles_m) * BN, m0 = (rem % p.tiles_m) * BM;
+        const int n0 = (rem / groups_m) * BN, m0 = ((rem % groups_m) * CL + rank) * BM;
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb, ++cnt) {
@@ -292,12 +299,19 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
           const int kc = kb * BK;
           if (MODE == 0) {
             tma_load_2d(sA, &tmA, &full[s], kc, m0);
-            tma_load_2d(sB, &tmB, &full[s], kc, n0);
+            if (CL == 1) {
+              tma_load_2d(sB, &tmB, &full[s], kc, n0);
+            } else {   // my half of the B rows, delivered to both CTAs
+              tma_load_2d_mc(sB + rank * (BN / CL) * 128, &tmB, &full[s], kc, n0 + rank * (BN / CL), (uint16_t)((1 << CL) - 1));
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * (BK * 128), &tmA, &full[s], m0 + 64 * j, kc);
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * (BK * 128), &tmB, &full[s], n0 + 64 * j, kc);
+            for (int j = 0; j < BN / 64; ++j) {
+              if (CL == 1) tma_load_2d(sB + j * (BK * 128), &tmB, &full[s], n0 + 64 * j, kc);
+              else if ((j % CL) == rank) tma_load_2d_mc(sB + j * (BK * 128), &tmB, &full[s], n0 + 64 * j, kc, (uint16_t)((1 << CL) - 1));
+            }
           }
         }
       }
@@ -307,7 +321,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, MODE == 1, MODE == 1);
       uint32_t cnt = 0, it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      for (int item = first_item; item < n_items; item += item_stride, ++it) {
         const int split = item / tiles_mn;
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
             }
             umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[s]);
+          if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], (uint16_t)((1 << CL) - 1));
         }
         umma_commit(&tmem_full[as]);
       }
@@ -352,9 +366,9 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
     const bool tma_in = p.tma_in != 0 && p.out_kind == OUT_BF16;
     const bool gelu = p.act == ACT_GELU;
     uint32_t it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    for (int item = first_item; item < n_items; item += item_stride, ++it) {
       const int split = item / tiles_mn, rem = item - split * tiles_mn;
-      const int n0 = (rem / p.tiles_m) * BN, m0 = (rem % p.tiles_m) * BM;
+      const int n0 = (rem / groups_m) * BN, m0 = ((rem % groups_m) * CL + rank) * BM;
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
       const int row0 = m0 + q * 32;
       const int row = row0 + lane;
@@ -447,6 +461,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA exits while its peer may still multicast into it / signal its barriers
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
