@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const bf16* __rest
                                                               bf16* __restrict__ out, int64_t ldo,
                                                               float* __restrict__ lse, int NH, int Sq, int Sk,
                                                               float scale, MaskDev mask) {
+  pdl_grid_sync();
   __shared__ __align__(16) FwdSmem<D> s;
   constexpr int KS = D / 16, NT = D / 8;
   const int b = blockIdx.y / NH, h = blockIdx.y % NH;
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(
     int64_t ldv, const bf16* __restrict__ o, int64_t ldo, const bf16* __restrict__ dout, int64_t ld_do,
     const float* __restrict__ lse, bf16* __restrict__ dq, int64_t ld_dq, bf16* __restrict__ dk, int64_t ld_dk,
     bf16* __restrict__ dv, int64_t ld_dv, float* __restrict__ dq_acc, int NH, int Sq, int Sk, float scale, MaskDev mask) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   BwdSmem<D>& s = *reinterpret_cast<BwdSmem<D>*>(smem_raw);
   constexpr int KS = D / 16, NT = D / 8;
@@ -372,6 +374,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_kernel(
 
 // fp32 dQ accumulator [rows, width] -> bf16 dq (row pitch ld_dq), multi-key-tile case only
 __global__ void dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, int64_t ld_dq, int64_t rows, int width) {
+  pdl_grid_sync();
   const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (idx >= rows * width) return;
   const int64_t r = idx / width;
@@ -397,7 +400,7 @@ template <int D>
 static int fwd_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, bf16* out,
                       int64_t ldo, float* lse, int B, int NH, int Sq, int Sk, const MaskDev& md, cudaStream_t st) {
   dim3 grid((Sq + AT - 1) / AT, B * NH);
-  attn_fwd_kernel<D><<<grid, AT_THREADS, 0, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, lse, NH, Sq, Sk, rsqrtf((float)D), md);
+  launch_kernel(attn_fwd_kernel<D>, dim3(grid), dim3(AT_THREADS), 0, st, q, ldq, k, ldk, v, ldv, out, ldo, lse, NH, Sq, Sk, rsqrtf((float)D), md);
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
@@ -417,12 +420,12 @@ static int bwd_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, co
     KIT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)B * Sq * NH * D * sizeof(float), st));
   }
   dim3 grid(ktiles, B * NH);
-  attn_bwd_kernel<D><<<grid, AT_THREADS, sizeof(BwdSmem<D>), st>>>(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq,
+  launch_kernel(attn_bwd_kernel<D>, dim3(grid), dim3(AT_THREADS), sizeof(BwdSmem<D>), st, q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq,
                                                                     dk, ld_dk, dv, ld_dv, dq_acc, NH, Sq, Sk, rsqrtf((float)D), md);
   KIT_LAUNCH_CHECK();
   if (ktiles > 1) {
     const int64_t n = (int64_t)B * Sq * NH * D;
-    dq_convert_kernel<<<(unsigned)ceil_div(n / 8, 256), 256, 0, st>>>(dq_acc, dq, ld_dq, (int64_t)B * Sq, NH * D);
+    launch_kernel(dq_convert_kernel, dim3((unsigned)ceil_div(n / 8, 256)), dim3(256), 0, st, dq_acc, dq, ld_dq, (int64_t)B * Sq, NH * D);
     KIT_LAUNCH_CHECK();
   }
   return KIT_OK;

@@ -35,6 +35,34 @@ void set_error(const char* fmt, ...);
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute and starts with
+// pdl_grid_sync(): it waits until the kernels before it in the stream have completed (their writes are visible), then lets
+// the NEXT kernel's CTAs be scheduled, so that kernel's launch latency and prologue (barrier init, tensor-memory allocation,
+// descriptor prefetch) overlap this kernel's execution instead of following it.  Nothing before pdl_grid_sync() may touch
+// global memory another kernel writes.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_grid_sync() {
+  pdl_wait();
+  pdl_launch_dependents();
+}
+bool pdl_enabled();   // errors.cu: KIT_PDL=0 turns the attribute off (A/B measurements)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -47,26 +75,71 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
-// Exact (erf) GELU, branch-free: erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), whose
-// exp(-u^2) with u = x/sqrt(2) is also the Gaussian the derivative needs.
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& gauss) {
-  const float u = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
-  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-  gauss = __expf(-u * u);                       // exp(-x^2 / 2)
-  const float half_erfc = 0.5f * poly * gauss;  // 0.5 * erfc(|u|)
-  cdf = (x >= 0.f) ? 1.0f - half_erfc : half_erfc;
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): two lanes of a 64-bit register pair per instruction.
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
 }
-__device__ __forceinline__ float gelu_erf(float x) {
-  float cdf, g;
-  gelu_parts(x, cdf, g);
-  return x * cdf;
+__device__ __forceinline__ void up2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
 }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf, g;
-  gelu_parts(x, cdf, g);
-  return fmaf(x * 0.39894228040143267794f, g, cdf);
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// GELU (activation="gelu" at model.py:87, the erf form) evaluated through 0.5 x (1 + tanh(c0 x + c1 x^3)), c0 = sqrt(2/pi),
+// c1 = 0.044715 c0: within 4.8e-4 absolute of the erf form (plus 2^-11 relative from MUFU.TANH) -- below the bf16 rounding of
+// the activation that is stored -- for one MUFU and 2.5 packed FMA-pipe instructions per element instead of rcp + ex2 + 12
+// scalar ones.  The epilogues that apply it are ALU-bound, not tensor-bound, so this is what the FFN GEMMs' speed hangs on.
+// The derivative differentiates the same expression, so forward and backward stay consistent.
+constexpr float GELU_C0 = 0.7978845608028654f, GELU_C1 = 0.035677408136300125f;
+__device__ __forceinline__ void gelu_pair(float& a, float& b) {
+  const uint64_t x = pk2(a, b);
+  const uint64_t u = mul2(x, fma2(mul2(x, x), pk2(GELU_C1, GELU_C1), pk2(GELU_C0, GELU_C0)));
+  float ua, ub;
+  up2(u, ua, ub);
+  const uint64_t t = pk2(tanh_approx(ua), tanh_approx(ub));
+  const uint64_t hx = mul2(x, pk2(0.5f, 0.5f));
+  up2(fma2(hx, t, hx), a, b);
+}
+// (ga, gb) *= gelu'(za), gelu'(zb)
+__device__ __forceinline__ void gelu_grad_mul_pair(float za, float zb, float& ga, float& gb) {
+  const uint64_t x = pk2(za, zb);
+  const uint64_t sq = mul2(x, x);
+  const uint64_t u = mul2(x, fma2(sq, pk2(GELU_C1, GELU_C1), pk2(GELU_C0, GELU_C0)));
+  float ua, ub;
+  up2(u, ua, ub);
+  const uint64_t t = pk2(tanh_approx(ua), tanh_approx(ub));
+  const uint64_t du = fma2(sq, pk2(3.f * GELU_C1, 3.f * GELU_C1), pk2(GELU_C0, GELU_C0));        // u'(x)
+  const uint64_t sech2 = fma2(mul2(t, pk2(-1.f, -1.f)), t, pk2(1.f, 1.f));                     // 1 - t^2
+  const uint64_t hx = mul2(x, pk2(0.5f, 0.5f));
+  const uint64_t d = fma2(mul2(hx, sech2), du, fma2(t, pk2(0.5f, 0.5f), pk2(0.5f, 0.5f)));     // 0.5(1+t) + 0.5 x (1-t^2) u'
+  up2(mul2(pk2(ga, gb), d), ga, gb);
+}
+__device__ __forceinline__ float gelu_act(float x) {
+  float a = x, b = 0.f;
+  gelu_pair(a, b);
+  return a;
+}
+__device__ __forceinline__ float gelu_act_grad(float x) {
+  float a = 1.f, b = 0.f;
+  gelu_grad_mul_pair(x, 0.f, a, b);
+  return a;
 }
 
 // 8 bf16 <-> 8 floats through ONE 16-byte access (uint4: a struct of __nv_bfloat162 is copied

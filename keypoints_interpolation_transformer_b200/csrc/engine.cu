@@ -651,6 +651,7 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
 }
 
 __global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  pdl_grid_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __bfloat162float(src[i]);
 }
@@ -793,7 +794,7 @@ extern "C" int kit_engine_debug_read(KitEngine* e, const char* name, float* out,
     KIT_CHECK_CUDA(cudaMemcpyAsync(out, e->ws + b.off, b.elems * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   } else {
     KIT_REQUIRE(b.esize == 2, "kit_engine_debug_read: buffer '%s' is not a tensor", name);
-    bf16_to_f32_kernel<<<(unsigned)ceil_div(b.elems, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)(e->ws + b.off), out, b.elems);
+    launch_kernel(bf16_to_f32_kernel, dim3((unsigned)ceil_div(b.elems, 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)(e->ws + b.off), out, b.elems);
     KIT_LAUNCH_CHECK();
   }
   return KIT_OK;

@@ -1,4 +1,5 @@
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -12,6 +13,13 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+bool pdl_enabled() {
+  static const bool on = []() {
+    const char* v = getenv("KIT_PDL");
+    return v == nullptr || v[0] != '0';
+  }();
+  return on;
+}
 }  // namespace kit
 
 extern "C" const char* kit_last_error(void) { return kit::get_error(); }

@@ -2,6 +2,7 @@
 #include "gemm_sm100.cuh"
 
 #include <mutex>
+#include <cstdlib>
 
 namespace kit {
 
@@ -104,6 +105,7 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
   p.addend = addend; p.ld_addend = ld_addend;
   p.aux = aux; p.ld_aux = ld_aux;
   p.out_kind = out_kind; p.act = act;
+  { const char* d = getenv("KIT_GEMM_DBG"); p.dbg = d ? atoi(d) : 0; }
   plan->mode = mode;
   const int bn = (N > 128) ? 256 : 128;
   plan->bn = bn;
@@ -177,13 +179,15 @@ static int launch_one(KernelT kernel, int grid, int threads, int smem, int clust
   cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   KIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p));
   return KIT_OK;
 }

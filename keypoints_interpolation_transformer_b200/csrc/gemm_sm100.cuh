@@ -33,6 +33,7 @@ struct GemmParams {
   int kb_per_split;  // 64-wide k-blocks per work item
   int tiles_m, tiles_n, splits;
   int tma_store;  // 1: outputs leave through shared memory + TMA store / reduce-add (clipped at the edges)
+  int dbg;        // experiments only (KIT_GEMM_DBG): 1 = no TMA stores, 2 = no wait on staging reuse, 4 = no tmem loads
   int tma_in;     // 1: the addend / GELU' pre-activation tile arrives through TMA (tmAux) instead of per-row loads
 };
 
@@ -60,18 +61,19 @@ constexpr int gemm_smem_bytes() {
          256 /*barriers*/;
 }
 
-// bias / residual / activation on 32 accumulator columns of one row, in registers.  Columns >= N of a
-// ragged last chunk are computed on garbage and clipped by the TMA store.
+// bias / residual / activation on 32 accumulator columns of one row, in registers (packed fp32 pairs).  Columns >= N
+// of a ragged last chunk are computed on garbage and clipped by the TMA store.
+__device__ __forceinline__ void add_pair(float& a, float& b, float x, float y) { up2(add2(pk2(a, b), pk2(x, y)), a, b); }
 __device__ __forceinline__ void gemm_epilogue_math(const GemmParams& p, int row, int col0, bool row_ok, const float* in_vals,
                                                    float (&v)[32]) {
   const bool full = col0 + 32 <= p.N;
-  const bool do_act = true;
   if (p.bias != nullptr) {
     if (full) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        add_pair(v[j], v[j + 1], b4.x, b4.y);
+        add_pair(v[j + 2], v[j + 3], b4.z, b4.w);
       }
     } else {
 #pragma unroll
@@ -82,10 +84,10 @@ __device__ __forceinline__ void gemm_epilogue_math(const GemmParams& p, int row,
   if (in_vals != nullptr) {   // tile staged by TMA (zero-filled outside the tensor)
     if (p.act == ACT_GELU_BWD) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(in_vals[j]);
+      for (int j = 0; j < 32; j += 2) gelu_grad_mul_pair(in_vals[j], in_vals[j + 1], v[j], v[j + 1]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += in_vals[j];
+      for (int j = 0; j < 32; j += 2) add_pair(v[j], v[j + 1], in_vals[j], in_vals[j + 1]);
     }
     return;
   }
@@ -97,7 +99,7 @@ __device__ __forceinline__ void gemm_epilogue_math(const GemmParams& p, int row,
         float t[8];
         load8(ap + j, t);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[j + u] += t[u];
+        for (int u = 0; u < 8; u += 2) add_pair(v[j + u], v[j + u + 1], t[u], t[u + 1]);
       }
     } else {
 #pragma unroll
@@ -105,7 +107,6 @@ __device__ __forceinline__ void gemm_epilogue_math(const GemmParams& p, int row,
         if (col0 + j < p.N) v[j] += __bfloat162float(ap[j]);
     }
   }
-  if (!do_act) return;
   if (p.act == ACT_GELU_BWD && row_ok) {
     const bf16* xp = p.aux + (int64_t)row * p.ld_aux + col0;
     if (full) {
@@ -114,12 +115,12 @@ __device__ __forceinline__ void gemm_epilogue_math(const GemmParams& p, int row,
         float t[8];
         load8(xp + j, t);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[j + u] *= gelu_erf_grad(t[u]);
+        for (int u = 0; u < 8; u += 2) gelu_grad_mul_pair(t[u], t[u + 1], v[j + u], v[j + u + 1]);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) v[j] *= gelu_erf_grad(__bfloat162float(xp[j]));
+        if (col0 + j < p.N) v[j] *= gelu_act_grad(__bfloat162float(xp[j]));
     }
   }
 }
@@ -172,7 +173,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, int row
       for (int j = 0; j < 32; j += 8) {
         store8(xp + j, v + j);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[j + u] = gelu_erf(v[j + u]);
+        for (int u = 0; u < 8; u += 2) gelu_pair(v[j + u], v[j + u + 1]);
       }
     } else if (p.act == ACT_GELU_BWD) {
       const bf16* xp = p.aux + (int64_t)row * p.ld_aux + col0;
@@ -181,7 +182,7 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, int row
         float t[8];
         load8(xp + j, t);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[j + u] *= gelu_erf_grad(t[u]);
+        for (int u = 0; u < 8; u += 2) gelu_grad_mul_pair(t[u], t[u + 1], v[j + u], v[j + u + 1]);
       }
     }
     if (p.out_kind == OUT_BF16) {
@@ -211,9 +212,9 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, int row
       if (p.addend != nullptr) x += __bfloat162float(p.addend[(int64_t)row * p.ld_addend + col]);
       if (p.act == ACT_GELU) {
         p.aux[(int64_t)row * p.ld_aux + col] = __float2bfloat16(x);
-        x = gelu_erf(x);
+        x = gelu_act(x);
       } else if (p.act == ACT_GELU_BWD) {
-        x *= gelu_erf_grad(__bfloat162float(p.aux[(int64_t)row * p.ld_aux + col]));
+        x *= gelu_act_grad(__bfloat162float(p.aux[(int64_t)row * p.ld_aux + col]));
       }
       if (p.out_kind == OUT_BF16) {
         reinterpret_cast<bf16*>(p.C)[(int64_t)row * p.ldc + col] = __float2bfloat16(x);
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
   if (CL > 1) cluster_sync_all();   // peer barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();   // everything above overlapped the previous kernel; operands / outputs are touched only below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
         if (lane == 0) mbar_arrive(&tmem_empty[as]);
       };
       auto staging_free = [&]() {   // the previous TMA stores have finished READING the staging tiles
-        if (lane == 0) tma_store_wait_read();
+        if (lane == 0 && !(p.dbg & 2)) tma_store_wait_read();
         __syncwarp();
       };
       if (tma_in && colg < p.N) issue_in(colg);   // overlaps the wait for the MMAs
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
         const int col0 = colg + sub * 32;
         uint32_t r[32];
         __syncwarp();
-        tmem_ld32(tmem_row + uint32_t(sub * 32), r);
+        if (!(p.dbg & 4)) tmem_ld32(tmem_row + uint32_t(sub * 32), r);
         float v[32];
         if (col0 >= p.N) {   // nothing to write (uniform): only keep the TMEM protocol alive
           tmem_ld_wait();
@@ -423,12 +425,12 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
           if (gelu) {   // pre-activation to the second tile, activation to the first
             stage_bf16(ebuf2, lane, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < 32; j += 2) gelu_pair(v[j], v[j + 1]);
           }
           stage_bf16(ebuf, lane, v);
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(p.dbg & 1)) {
             if (gelu) tma_store_2d(&tmAux, ebuf2, col0, row0);
             tma_store_2d(&tmC, ebuf, col0, row0);
             tma_store_commit();

@@ -92,6 +92,7 @@ template <int NV>
 __global__ void embed_post_fwd_kernel(const bf16* __restrict__ raw, const float* __restrict__ pe,
                                       const float* __restrict__ learned, bf16* __restrict__ out, int64_t M, int H,
                                       int T) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -119,6 +120,7 @@ template <int NV>
 __global__ void embed_post_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ raw,
                                       const bf16* __restrict__ addend, bf16* __restrict__ draw,
                                       float* __restrict__ dlearned, int64_t M, int H) {
+  pdl_grid_sync();
   __shared__ float s_acc[ROW_WARPS][NV * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RowVec<NV> acc;
@@ -168,6 +170,7 @@ __global__ void add_ln_fwd_kernel(const bf16* __restrict__ a, const bf16* __rest
                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                   bf16* __restrict__ sum_out, bf16* __restrict__ y, float* __restrict__ mean_out,
                                   float* __restrict__ rstd_out, int64_t M, int H) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -216,6 +219,7 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restric
                               const float* __restrict__ gamma, const bf16* __restrict__ addend,
                               bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                               float* __restrict__ dxsum, int64_t M, int H) {
+  pdl_grid_sync();
   __shared__ float s_buf[ROW_WARPS][NV * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RowVec<NV> accg, accb, accx, gm;
@@ -277,6 +281,7 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restric
 // ---------------------------------------------------------------- SwiGLU gate (model.py:18-22)
 // x12 [M,2H] = fc1(x) | fc2(x);  g = x1 * sigmoid(x2)
 __global__ void swiglu_gate_fwd_kernel(const bf16* __restrict__ x12, bf16* __restrict__ g, int64_t M, int H) {
+  pdl_grid_sync();
   const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (idx >= M * H) return;
   const int64_t row = idx / H;
@@ -290,6 +295,7 @@ __global__ void swiglu_gate_fwd_kernel(const bf16* __restrict__ x12, bf16* __res
 }
 __global__ void swiglu_gate_bwd_kernel(const bf16* __restrict__ dg, const bf16* __restrict__ x12,
                                        bf16* __restrict__ dx12, int64_t M, int H) {
+  pdl_grid_sync();
   const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (idx >= M * H) return;
   const int64_t row = idx / H;
@@ -315,6 +321,7 @@ __global__ void swiglu_gate_bwd_kernel(const bf16* __restrict__ dg, const bf16* 
 template <int NV>
 __global__ void final_norm_silu_fwd_kernel(const bf16* __restrict__ dec, const bf16* __restrict__ femb,
                                            bf16* __restrict__ z_out, bf16* __restrict__ out, int64_t M, int H) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -340,6 +347,7 @@ __global__ void final_norm_silu_fwd_kernel(const bf16* __restrict__ dec, const b
 template <int NV>
 __global__ void final_norm_silu_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ z,
                                            bf16* __restrict__ dz, int64_t M, int H) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -376,6 +384,7 @@ __global__ void final_norm_silu_bwd_kernel(const bf16* __restrict__ dout, const 
 // ---------------------------------------------------------------- column sums (bias gradients)
 // out[n] += sum_m x[m, n];  x bf16 [M, ld]; block = 32 column-groups(8 wide) x 8 row lanes
 __global__ void colsum_kernel(const bf16* __restrict__ x, int64_t ld, float* __restrict__ out, int64_t M, int N) {
+  pdl_grid_sync();
   __shared__ float s[8][256 + 8];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 256 + cg * 8;
@@ -407,6 +416,7 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, int64_t ld, float* __r
 // Optional per-row zeroing: row_zero[row * row_zero_stride...] handled by the caller variant below.
 __global__ void cast_pad_kernel(const float* __restrict__ src, int64_t rows, int64_t cols, int64_t src_ld,
                                 bf16* __restrict__ dst, int64_t dst_ld) {
+  pdl_grid_sync();
   const int64_t per_row = dst_ld / 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * per_row) return;
@@ -424,6 +434,7 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, int64_t rows, int
 __global__ void pack_frames_kernel(const float* __restrict__ src, int64_t batch_stride, int B, int T, int cols,
                                    const float* __restrict__ zero_mask, int64_t zero_mask_stride,
                                    bf16* __restrict__ dst, int dst_ld) {
+  pdl_grid_sync();
   const int per_row = dst_ld / 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)B * T * per_row) return;
@@ -443,6 +454,7 @@ __global__ void pack_frames_kernel(const float* __restrict__ src, int64_t batch_
 __global__ void weight_refresh_kernel(const float* __restrict__ params, bf16* __restrict__ wb,
                                       const WeightDesc* __restrict__ descs, const int* __restrict__ tile_prefix,
                                       int n_desc) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   int lo = 0, hi = n_desc - 1;
   const int tid = blockIdx.x;
@@ -496,7 +508,7 @@ int embed_post_fwd(const bf16* raw, const float* pe, const float* learned, bf16*
                    cudaStream_t st) {
   int rc = check_h(H);
   if (rc) return rc;
-  KIT_NV_DISPATCH(H, (embed_post_fwd_kernel<NV><<<row_blocks(M), 256, 0, st>>>(raw, pe, learned, out, M, H, T)));
+  KIT_NV_DISPATCH(H, (launch_kernel(embed_post_fwd_kernel<NV>, dim3(row_blocks(M)), dim3(256), 0, st, raw, pe, learned, out, M, H, T)));
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
@@ -504,7 +516,7 @@ int embed_post_bwd(const bf16* dout, const bf16* raw, const bf16* addend, bf16* 
                    cudaStream_t st) {
   int rc = check_h(H);
   if (rc) return rc;
-  KIT_NV_DISPATCH(H, (embed_post_bwd_kernel<NV><<<reduce_blocks(M), 256, 0, st>>>(dout, raw, addend, draw, dlearned, M, H)));
+  KIT_NV_DISPATCH(H, (launch_kernel(embed_post_bwd_kernel<NV>, dim3(reduce_blocks(M)), dim3(256), 0, st, dout, raw, addend, draw, dlearned, M, H)));
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
@@ -512,7 +524,7 @@ int add_ln_fwd(const bf16* a, const bf16* b, const float* gamma, const float* be
                float* rstd, int64_t M, int H, cudaStream_t st) {
   int rc = check_h(H);
   if (rc) return rc;
-  KIT_NV_DISPATCH(H, (add_ln_fwd_kernel<NV><<<row_blocks(M), 256, 0, st>>>(a, b, gamma, beta, sum_out, y, mean, rstd, M, H)));
+  KIT_NV_DISPATCH(H, (launch_kernel(add_ln_fwd_kernel<NV>, dim3(row_blocks(M)), dim3(256), 0, st, a, b, gamma, beta, sum_out, y, mean, rstd, M, H)));
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
@@ -520,7 +532,7 @@ int ln_bwd(const bf16* dy, const bf16* s_saved, const float* mean, const float* 
            const bf16* addend, bf16* dx, float* dgamma, float* dbeta, float* dxsum, int64_t M, int H, cudaStream_t st) {
   int rc = check_h(H);
   if (rc) return rc;
-  KIT_NV_DISPATCH(H, (ln_bwd_kernel<NV><<<reduce_blocks(M), 256, 0, st>>>(dy, s_saved, mean, rstd, gamma, addend, dx,
+  KIT_NV_DISPATCH(H, (launch_kernel(ln_bwd_kernel<NV>, dim3(reduce_blocks(M)), dim3(256), 0, st, dy, s_saved, mean, rstd, gamma, addend, dx,
                                                                          dgamma, dbeta, dxsum, M, H)));
   KIT_LAUNCH_CHECK();
   return KIT_OK;
@@ -528,28 +540,28 @@ int ln_bwd(const bf16* dy, const bf16* s_saved, const float* mean, const float* 
 int swiglu_gate_fwd(const bf16* x12, bf16* g, int64_t M, int H, cudaStream_t st) {
   int rc = check_h(H);
   if (rc) return rc;
-  swiglu_gate_fwd_kernel<<<(unsigned)ceil_div(M * H / 8, 256), 256, 0, st>>>(x12, g, M, H);
+  launch_kernel(swiglu_gate_fwd_kernel, dim3((unsigned)ceil_div(M * H / 8, 256)), dim3(256), 0, st, x12, g, M, H);
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
 int swiglu_gate_bwd(const bf16* dg, const bf16* x12, bf16* dx12, int64_t M, int H, cudaStream_t st) {
   int rc = check_h(H);
   if (rc) return rc;
-  swiglu_gate_bwd_kernel<<<(unsigned)ceil_div(M * H / 8, 256), 256, 0, st>>>(dg, x12, dx12, M, H);
+  launch_kernel(swiglu_gate_bwd_kernel, dim3((unsigned)ceil_div(M * H / 8, 256)), dim3(256), 0, st, dg, x12, dx12, M, H);
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
 int final_norm_silu_fwd(const bf16* dec, const bf16* femb, bf16* z_out, bf16* out, int64_t M, int H, cudaStream_t st) {
   int rc = check_h(H);
   if (rc) return rc;
-  KIT_NV_DISPATCH(H, (final_norm_silu_fwd_kernel<NV><<<row_blocks(M), 256, 0, st>>>(dec, femb, z_out, out, M, H)));
+  KIT_NV_DISPATCH(H, (launch_kernel(final_norm_silu_fwd_kernel<NV>, dim3(row_blocks(M)), dim3(256), 0, st, dec, femb, z_out, out, M, H)));
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
 int final_norm_silu_bwd(const bf16* dout, const bf16* z, bf16* dz, int64_t M, int H, cudaStream_t st) {
   int rc = check_h(H);
   if (rc) return rc;
-  KIT_NV_DISPATCH(H, (final_norm_silu_bwd_kernel<NV><<<row_blocks(M), 256, 0, st>>>(dout, z, dz, M, H)));
+  KIT_NV_DISPATCH(H, (launch_kernel(final_norm_silu_bwd_kernel<NV>, dim3(row_blocks(M)), dim3(256), 0, st, dout, z, dz, M, H)));
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
@@ -559,27 +571,27 @@ int colsum(const bf16* x, int64_t ld, float* out, int64_t M, int N, cudaStream_t
   if (ysplit > 128) ysplit = 128;
   if (ysplit < 1) ysplit = 1;
   dim3 grid((unsigned)ceil_div(N, 256), (unsigned)ysplit);
-  colsum_kernel<<<grid, 256, 0, st>>>(x, ld, out, M, N);
+  launch_kernel(colsum_kernel, dim3(grid), dim3(256), 0, st, x, ld, out, M, N);
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
 int cast_pad(const float* src, int64_t rows, int64_t cols, int64_t src_ld, bf16* dst, int64_t dst_ld, cudaStream_t st) {
   KIT_REQUIRE(dst_ld % 8 == 0 && dst_ld >= cols, "cast_pad: dst_ld must be a multiple of 8 and >= cols");
-  cast_pad_kernel<<<(unsigned)ceil_div(rows * (dst_ld / 8), 256), 256, 0, st>>>(src, rows, cols, src_ld, dst, dst_ld);
+  launch_kernel(cast_pad_kernel, dim3((unsigned)ceil_div(rows * (dst_ld / 8), 256)), dim3(256), 0, st, src, rows, cols, src_ld, dst, dst_ld);
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
 int pack_frames(const float* src, int64_t batch_stride, int B, int T, int cols, const float* zero_mask,
                 int64_t zero_mask_stride, bf16* dst, int dst_ld, cudaStream_t st) {
   KIT_REQUIRE(dst_ld % 8 == 0 && dst_ld >= cols, "pack_frames: dst_ld must be a multiple of 8 and >= cols");
-  pack_frames_kernel<<<(unsigned)ceil_div((int64_t)B * T * (dst_ld / 8), 256), 256, 0, st>>>(
+  launch_kernel(pack_frames_kernel, dim3((unsigned)ceil_div((int64_t)B * T * (dst_ld / 8), 256)), dim3(256), 0, st, 
       src, batch_stride, B, T, cols, zero_mask, zero_mask_stride, dst, dst_ld);
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
 int weight_refresh(const float* params, bf16* wb, const WeightDesc* descs_dev, const int* tile_prefix_dev, int n_desc,
                    int total_tiles, cudaStream_t st) {
-  weight_refresh_kernel<<<total_tiles, 256, 0, st>>>(params, wb, descs_dev, tile_prefix_dev, n_desc);
+  launch_kernel(weight_refresh_kernel, dim3(total_tiles), dim3(256), 0, st, params, wb, descs_dev, tile_prefix_dev, n_desc);
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
