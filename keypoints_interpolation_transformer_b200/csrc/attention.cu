@@ -384,6 +384,362 @@ __global__ void dq_convert_kernel(const float* __restrict__ acc, bf16* __restric
   store8(dq + r * ld_dq + c, f);
 }
 
+// ------------------------------------------------------------------------ single-tile kernels (Sq, Sk <= 64)
+// The benchmark shape (T = 64, d = 32) is one 64 x 64 score tile per (batch, head): 4 KB per operand, far too little work
+// to hide a load -> compute -> store chain per CTA.  These kernels are PERSISTENT over the (batch, head) units: while a CTA
+// computes unit i, cp.async is already filling the other shared-memory buffer with unit i+1, and results leave through
+// shared memory as 16-byte coalesced stores.  The mask is folded into two floats per key ({additive bias * log2(e),
+// "masked when key > query"}), computed once per unit, so the inner loops carry no per-element flag logic.
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+  const uint32_t sz = pred ? 16u : 0u;   // src-size 0: the 16 bytes are zero-filled, the address is not dereferenced
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, bool pred) {
+  const uint32_t sz = pred ? 4u : 0u;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// rows [0, 64) x D columns of head h -> shared [64][D+8] through cp.async, rows >= nrows zero-filled
+template <int D>
+__device__ __forceinline__ void async_tile(bf16 (*dst)[D + 8], const bf16* base, int64_t ld, int nrows) {
+  constexpr int VPR = D / 8;
+  for (int idx = threadIdx.x; idx < AT * VPR; idx += AT_THREADS) {
+    const int r = idx / VPR, v = idx % VPR;
+    const bool ok = r < nrows;
+    cp_async16(&dst[r][v * 8], ok ? base + (int64_t)r * ld + v * 8 : base, ok);
+  }
+}
+// shared [64][D+8] rows [0, nrows) -> global rows, 16 bytes per thread
+template <int D>
+__device__ __forceinline__ void store_tile(bf16* base, int64_t ld, const bf16 (*src)[D + 8], int nrows) {
+  constexpr int VPR = D / 8;
+  for (int idx = threadIdx.x; idx < AT * VPR; idx += AT_THREADS) {
+    const int r = idx / VPR, v = idx % VPR;
+    if (r < nrows) *reinterpret_cast<uint4*>(base + (int64_t)r * ld + v * 8) = *reinterpret_cast<const uint4*>(&src[r][v * 8]);
+  }
+}
+// {bias * log2e (or -inf beyond Sk), 1 when the key is masked for every query before it}
+__device__ __forceinline__ float2 key_info(const MaskDev& m, int b, int j, int Sk) {
+  const float fm = (m.frame_mask != nullptr && j < Sk) ? m.frame_mask[(int64_t)b * m.frame_mask_stride + j] : 0.f;
+  float add = (m.flags & KIT_MASK_KEYPAD_ADD) ? fm * LOG2E : 0.f;
+  if (j >= Sk) add = -INFINITY;
+  const bool inc = ((m.flags & KIT_MASK_REPEAT_INC) && fm == 1.f) || (m.flags & KIT_MASK_TRIANGLE);
+  return make_float2(add, inc ? 1.f : 0.f);
+}
+
+template <int D>
+struct FwdTile {
+  bf16 Q[AT][D + 8];   // re-used as the staging tile of O
+  bf16 K[AT][D + 8];
+  bf16 V[AT][D + 8];
+  float2 kinfo[AT];
+};
+
+template <int D>
+__global__ void __launch_bounds__(AT_THREADS) attn_fwd_tile_kernel(const bf16* __restrict__ q, int64_t ldq,
+                                                                   const bf16* __restrict__ k, int64_t ldk,
+                                                                   const bf16* __restrict__ v, int64_t ldv,
+                                                                   bf16* __restrict__ out, int64_t ldo,
+                                                                   float* __restrict__ lse, int NH, int Sq, int Sk,
+                                                                   int units, float scale, MaskDev mask) {
+  pdl_grid_sync();
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  FwdTile<D>* tiles = reinterpret_cast<FwdTile<D>*>(smem_raw);
+  constexpr int KS = D / 16, NT = D / 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int q0 = warp * 16;
+  const float sl2 = scale * LOG2E;
+  auto issue = [&](int unit, FwdTile<D>& s) {
+    const int b = unit / NH, h = unit % NH;
+    async_tile<D>(s.Q, q + (int64_t)b * Sq * ldq + h * D, ldq, Sq);
+    async_tile<D>(s.K, k + (int64_t)b * Sk * ldk + h * D, ldk, Sk);
+    async_tile<D>(s.V, v + (int64_t)b * Sk * ldv + h * D, ldv, Sk);
+    if (threadIdx.x < AT) s.kinfo[threadIdx.x] = key_info(mask, b, threadIdx.x, Sk);
+  };
+  int unit = blockIdx.x, buf = 0;
+  if (unit < units) issue(unit, tiles[0]);
+  cp_async_commit();
+  for (; unit < units; unit += gridDim.x, buf ^= 1) {
+    FwdTile<D>& s = tiles[buf];
+    if (unit + (int)gridDim.x < units) issue(unit + gridDim.x, tiles[buf ^ 1]);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const int b = unit / NH, h = unit % NH;
+    uint32_t aq[KS][4];
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+      const int c = kk * 16 + 2 * t;
+      aq[kk][0] = lds_pair<D>(s.Q, q0 + g, c);     aq[kk][1] = lds_pair<D>(s.Q, q0 + g + 8, c);
+      aq[kk][2] = lds_pair<D>(s.Q, q0 + g, c + 8); aq[kk][3] = lds_pair<D>(s.Q, q0 + g + 8, c + 8);
+    }
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        mma16816(acc[j], aq[kk], lds_pair<D>(s.K, j * 8 + g, kk * 16 + 2 * t), lds_pair<D>(s.K, j * 8 + g, kk * 16 + 2 * t + 8));
+    // logits (base 2) + mask: key (j*8 + 2t + c) is masked for query (q0 + g + 8r) iff it lies after it and kinfo.y != 0
+    const int dq = 2 * t - g - q0;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 ki = *reinterpret_cast<const float4*>(&s.kinfo[j * 8 + 2 * t]);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float x0 = fmaf(acc[j][2 * r], sl2, ki.x), x1 = fmaf(acc[j][2 * r + 1], sl2, ki.z);
+        if (ki.y != 0.f && dq > 8 * r - 8 * j) x0 = -INFINITY;
+        if (ki.w != 0.f && dq + 1 > 8 * r - 8 * j) x1 = -INFINITY;
+        acc[j][2 * r] = x0;
+        acc[j][2 * r + 1] = x1;
+        mx[r] = fmaxf(mx[r], fmaxf(x0, x1));
+      }
+    }
+    float l[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));   // finite: key 0 is never masked and 0 < Sk
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p0 = ex2_approx(acc[j][2 * r] - mx[r]), p1 = ex2_approx(acc[j][2 * r + 1] - mx[r]);
+        acc[j][2 * r] = p0;
+        acc[j][2 * r + 1] = p1;
+        l[r] += p0 + p1;
+      }
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+    }
+    float o[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {   // 16 keys per step
+      uint32_t ap[4];
+      ap[0] = pack_bf16(acc[2 * kk][0], acc[2 * kk][1]);
+      ap[1] = pack_bf16(acc[2 * kk][2], acc[2 * kk][3]);
+      ap[2] = pack_bf16(acc[2 * kk + 1][0], acc[2 * kk + 1][1]);
+      ap[3] = pack_bf16(acc[2 * kk + 1][2], acc[2 * kk + 1][3]);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, &s.V[kk * 16 + (lane & 15)][j * 8]);
+        mma16816(o[j], ap, b0, b1);
+      }
+    }
+    __syncwarp();   // every lane of this warp has its Q fragments: the warp's 16 Q rows become the O staging rows
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float inv = 1.f / l[r];
+      const int ql = q0 + g + 8 * r;
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+        *reinterpret_cast<uint32_t*>(&s.Q[ql][j * 8 + 2 * t]) = pack_bf16(o[j][2 * r] * inv, o[j][2 * r + 1] * inv);
+      if (t == 0 && lse != nullptr && ql < Sq) lse[((int64_t)b * NH + h) * Sq + ql] = (mx[r] + log2f(l[r])) * LN2;
+    }
+    __syncthreads();
+    store_tile<D>(out + (int64_t)b * Sq * ldo + h * D, ldo, s.Q, Sq);
+    __syncthreads();   // this buffer is refilled by the next iteration's prefetch
+  }
+  cp_async_wait<0>();
+}
+
+template <int D>
+struct BwdTile {
+  bf16 Q[AT][D + 8];    // later: dK staging
+  bf16 K[AT][D + 8];
+  bf16 V[AT][D + 8];    // later: dV staging
+  bf16 dO[AT][D + 8];   // later: dQ staging
+  bf16 O[AT][D + 8];
+  float lse[AT];
+  float2 kinfo[AT];
+};
+template <int D>
+struct BwdTileSmem {
+  BwdTile<D> t[2];
+  bf16 dS[AT][AT + 8];   // [key][query]
+  float lse2[AT];        // lse * log2e, +inf for queries >= Sq
+  float delta[AT];
+};
+
+// warp w owns keys 16w..16w+15 for S^T / dP^T / dK / dV and queries 16w..16w+15 for dQ (as attn_bwd_kernel)
+template <int D>
+__global__ void __launch_bounds__(AT_THREADS) attn_bwd_tile_kernel(
+    const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ k, int64_t ldk, const bf16* __restrict__ v,
+    int64_t ldv, const bf16* __restrict__ o, int64_t ldo, const bf16* __restrict__ dout, int64_t ld_do,
+    const float* __restrict__ lse, bf16* __restrict__ dq, int64_t ld_dq, bf16* __restrict__ dk, int64_t ld_dk,
+    bf16* __restrict__ dv, int64_t ld_dv, int NH, int Sq, int Sk, int units, float scale, MaskDev mask) {
+  pdl_grid_sync();
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  BwdTileSmem<D>& sm = *reinterpret_cast<BwdTileSmem<D>*>(smem_raw);
+  constexpr int KS = D / 16, NT = D / 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const float sl2 = scale * LOG2E;
+  auto issue = [&](int unit, BwdTile<D>& s) {
+    const int b = unit / NH, h = unit % NH;
+    async_tile<D>(s.Q, q + (int64_t)b * Sq * ldq + h * D, ldq, Sq);
+    async_tile<D>(s.K, k + (int64_t)b * Sk * ldk + h * D, ldk, Sk);
+    async_tile<D>(s.V, v + (int64_t)b * Sk * ldv + h * D, ldv, Sk);
+    async_tile<D>(s.dO, dout + (int64_t)b * Sq * ld_do + h * D, ld_do, Sq);
+    async_tile<D>(s.O, o + (int64_t)b * Sq * ldo + h * D, ldo, Sq);
+    if (threadIdx.x < AT) {
+      const float* lg = lse + ((int64_t)b * NH + h) * Sq;
+      const bool ok = threadIdx.x < Sq;
+      cp_async4(&s.lse[threadIdx.x], ok ? lg + threadIdx.x : lg, ok);
+      s.kinfo[threadIdx.x] = key_info(mask, b, threadIdx.x, Sk);
+    }
+  };
+  int unit = blockIdx.x, buf = 0;
+  if (unit < units) issue(unit, sm.t[0]);
+  cp_async_commit();
+  for (; unit < units; unit += gridDim.x, buf ^= 1) {
+    BwdTile<D>& s = sm.t[buf];
+    if (unit + (int)gridDim.x < units) issue(unit + gridDim.x, sm.t[buf ^ 1]);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const int b = unit / NH, h = unit % NH;
+    {  // delta_i = sum_c dO[i,c] O[i,c]; two threads per query row
+      const int r = threadIdx.x >> 1, hf = threadIdx.x & 1;
+      float dsum = 0.f;
+#pragma unroll
+      for (int c = hf * (D / 2); c < (hf + 1) * (D / 2); c += 8) {
+        float a[8], gg[8];
+        load8(&s.O[r][c], a);
+        load8(&s.dO[r][c], gg);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dsum = fmaf(a[u], gg[u], dsum);
+      }
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+      if (hf == 0) {
+        sm.delta[r] = dsum;
+        sm.lse2[r] = (r < Sq) ? s.lse[r] * LOG2E : INFINITY;
+      }
+    }
+    uint32_t ak[KS][4], av[KS][4];
+    const int kr = warp * 16 + g;
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+      const int c = kk * 16 + 2 * t;
+      ak[kk][0] = lds_pair<D>(s.K, kr, c);     ak[kk][1] = lds_pair<D>(s.K, kr + 8, c);
+      ak[kk][2] = lds_pair<D>(s.K, kr, c + 8); ak[kk][3] = lds_pair<D>(s.K, kr + 8, c + 8);
+      av[kk][0] = lds_pair<D>(s.V, kr, c);     av[kk][1] = lds_pair<D>(s.V, kr + 8, c);
+      av[kk][2] = lds_pair<D>(s.V, kr, c + 8); av[kk][3] = lds_pair<D>(s.V, kr + 8, c + 8);
+    }
+    __syncthreads();   // delta / lse2 visible
+    float st[8][4], dp[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
+      dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = kk * 16 + 2 * t;
+        mma16816(st[j], ak[kk], lds_pair<D>(s.Q, j * 8 + g, c), lds_pair<D>(s.Q, j * 8 + g, c + 8));
+        mma16816(dp[j], av[kk], lds_pair<D>(s.dO, j * 8 + g, c), lds_pair<D>(s.dO, j * 8 + g, c + 8));
+      }
+    // P^T = 2^(S^T*scale*log2e + bias2 - lse2[query]);  dS^T = P^T * (dP^T - delta[query]) * scale
+    const float2 ki0 = s.kinfo[kr], ki1 = s.kinfo[kr + 8];
+    const int dkq = kr - 2 * t;   // key kr + 8*rr is after query j*8 + 2t + cc  iff  dkq + 8*rr - cc > 8*j
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 l2 = *reinterpret_cast<const float2*>(&sm.lse2[j * 8 + 2 * t]);
+      const float2 de = *reinterpret_cast<const float2*>(&sm.delta[j * 8 + 2 * t]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int rr = e >> 1, cc = e & 1;
+        const float2 ki = rr ? ki1 : ki0;
+        float x = fmaf(st[j][e], sl2, ki.x) - (cc ? l2.y : l2.x);
+        if (ki.y != 0.f && dkq + 8 * rr - cc > 8 * j) x = -INFINITY;
+        const float p = ex2_approx(x);
+        st[j][e] = p;
+        dp[j][e] = p * (dp[j][e] - (cc ? de.y : de.x)) * scale;
+      }
+    }
+    float dk_acc[NT][4], dv_acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      dk_acc[j][0] = dk_acc[j][1] = dk_acc[j][2] = dk_acc[j][3] = 0.f;
+      dv_acc[j][0] = dv_acc[j][1] = dv_acc[j][2] = dv_acc[j][3] = 0.f;
+    }
+    // dV = P^T dO ; dK = dS^T Q      (reduction over the 64 queries, 16 per k-step)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t ap[4], ad[4];
+      ap[0] = pack_bf16(st[2 * kk][0], st[2 * kk][1]);         ap[1] = pack_bf16(st[2 * kk][2], st[2 * kk][3]);
+      ap[2] = pack_bf16(st[2 * kk + 1][0], st[2 * kk + 1][1]); ap[3] = pack_bf16(st[2 * kk + 1][2], st[2 * kk + 1][3]);
+      ad[0] = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]);         ad[1] = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
+      ad[2] = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]); ad[3] = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, &s.dO[kk * 16 + (lane & 15)][j * 8]);
+        mma16816(dv_acc[j], ap, b0, b1);
+        ldsm_x2_trans(b0, b1, &s.Q[kk * 16 + (lane & 15)][j * 8]);
+        mma16816(dk_acc[j], ad, b0, b1);
+      }
+    }
+    // dS^T (bf16) -> shared [key][query]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      *reinterpret_cast<uint32_t*>(&sm.dS[warp * 16 + g][j * 8 + 2 * t]) = pack_bf16(dp[j][0], dp[j][1]);
+      *reinterpret_cast<uint32_t*>(&sm.dS[warp * 16 + g + 8][j * 8 + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
+    }
+    __syncthreads();   // dS complete; nobody reads Q / dO / V any more
+    // dK, dV (this warp's 16 keys) -> the dead Q / V tiles
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        *reinterpret_cast<uint32_t*>(&s.Q[kr + 8 * r][j * 8 + 2 * t]) = pack_bf16(dk_acc[j][2 * r], dk_acc[j][2 * r + 1]);
+        *reinterpret_cast<uint32_t*>(&s.V[kr + 8 * r][j * 8 + 2 * t]) = pack_bf16(dv_acc[j][2 * r], dv_acc[j][2 * r + 1]);
+      }
+    }
+    // dQ (16 queries of this warp) = dS (16 x 64 keys) K (64 x D)
+    float dq_r[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) dq_r[j][0] = dq_r[j][1] = dq_r[j][2] = dq_r[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t a[4];
+      ldsm_x4_trans(a, &sm.dS[kk * 16 + (lane & 7) + ((lane >> 4) << 3)][warp * 16 + (((lane >> 3) & 1) << 3)]);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, &s.K[kk * 16 + (lane & 15)][j * 8]);
+        mma16816(dq_r[j], a, b0, b1);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+        *reinterpret_cast<uint32_t*>(&s.dO[warp * 16 + g + 8 * r][j * 8 + 2 * t]) = pack_bf16(dq_r[j][2 * r], dq_r[j][2 * r + 1]);
+    }
+    __syncthreads();
+    store_tile<D>(dq + (int64_t)b * Sq * ld_dq + h * D, ld_dq, s.dO, Sq);
+    store_tile<D>(dk + (int64_t)b * Sk * ld_dk + h * D, ld_dk, s.Q, Sk);
+    store_tile<D>(dv + (int64_t)b * Sk * ld_dv + h * D, ld_dv, s.V, Sk);
+    __syncthreads();   // this buffer (and dS / delta) are rewritten by the next iterations
+  }
+  cp_async_wait<0>();
+}
+
 // ---------------------------------------------------------------------------------------- host
 static MaskDev to_dev(const KitAttnMask* m) {
   MaskDev d;
@@ -399,6 +755,24 @@ static MaskDev to_dev(const KitAttnMask* m) {
 template <int D>
 static int fwd_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, bf16* out,
                       int64_t ldo, float* lse, int B, int NH, int Sq, int Sk, const MaskDev& md, cudaStream_t st) {
+  if (Sq <= AT && Sk <= AT && md.bias == nullptr) {   // one score tile per (batch, head): persistent double-buffered kernel
+    static int ctas_per_sm = 0, sms = 0;
+    constexpr int smem = 2 * (int)sizeof(FwdTile<D>);
+    if (ctas_per_sm == 0) {
+      KIT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tile_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      KIT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, attn_fwd_tile_kernel<D>, AT_THREADS, smem));
+      int dev = 0;
+      KIT_CHECK_CUDA(cudaGetDevice(&dev));
+      KIT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      KIT_REQUIRE(ctas_per_sm > 0, "attention forward tile kernel does not fit on an SM");
+    }
+    const int units = B * NH;
+    const int grid1 = units < sms * ctas_per_sm ? units : sms * ctas_per_sm;
+    launch_kernel(attn_fwd_tile_kernel<D>, dim3(grid1), dim3(AT_THREADS), smem, st, q, ldq, k, ldk, v, ldv, out, ldo, lse, NH, Sq, Sk,
+                  units, rsqrtf((float)D), md);
+    KIT_LAUNCH_CHECK();
+    return KIT_OK;
+  }
   dim3 grid((Sq + AT - 1) / AT, B * NH);
   launch_kernel(attn_fwd_kernel<D>, dim3(grid), dim3(AT_THREADS), 0, st, q, ldq, k, ldk, v, ldv, out, ldo, lse, NH, Sq, Sk, rsqrtf((float)D), md);
   KIT_LAUNCH_CHECK();
@@ -409,6 +783,24 @@ static int bwd_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, co
                       int64_t ldo, const bf16* dout, int64_t ld_do, const float* lse, bf16* dq, int64_t ld_dq, bf16* dk,
                       int64_t ld_dk, bf16* dv, int64_t ld_dv, float* dq_acc, int B, int NH, int Sq, int Sk,
                       const MaskDev& md, cudaStream_t st) {
+  if (Sq <= AT && Sk <= AT && md.bias == nullptr) {
+    static int ctas_per_sm = 0, sms = 0;
+    constexpr int smem = (int)sizeof(BwdTileSmem<D>);
+    if (ctas_per_sm == 0) {
+      KIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tile_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      KIT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, attn_bwd_tile_kernel<D>, AT_THREADS, smem));
+      int dev = 0;
+      KIT_CHECK_CUDA(cudaGetDevice(&dev));
+      KIT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      KIT_REQUIRE(ctas_per_sm > 0, "attention backward tile kernel does not fit on an SM");
+    }
+    const int units = B * NH;
+    const int grid1 = units < sms * ctas_per_sm ? units : sms * ctas_per_sm;
+    launch_kernel(attn_bwd_tile_kernel<D>, dim3(grid1), dim3(AT_THREADS), smem, st, q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq,
+                  ld_dq, dk, ld_dk, dv, ld_dv, NH, Sq, Sk, units, rsqrtf((float)D), md);
+    KIT_LAUNCH_CHECK();
+    return KIT_OK;
+  }
   static bool attr_done = false;
   if (!attr_done) {
     KIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem<D>)));
