@@ -57,37 +57,43 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint6
   return KIT_OK;
 }
 
-constexpr int STAGES_BN128 = 4, STAGES_BN256 = 3;
-constexpr int CLUSTER_BN256 = 2;   // CTA pairs share the B tile through TMA multicast
-
 static int g_num_sms = 0;
+static long long* g_trace_buf = nullptr;
+
+// every (tile width, mode, epilogue kind) the planner can select; CTA pairs (cta_group::2) for the 256-wide tiles
+#define KIT_GEMM_KERNEL(BN, MODE, EPI) gemm_tcgen05_kernel<BN, MODE, ((BN) == 256 ? 2 : 1), EPI>
+#define KIT_GEMM_SMEM(BN, EPI) gemm_smem_bytes<BN, ((BN) == 256 ? 2 : 1), EPI>()
+#define KIT_GEMM_FOR_ALL(X)                                                                                     \
+  X(128, 0, EPI_STORE) X(128, 0, EPI_ADD) X(128, 0, EPI_GELU) X(128, 0, EPI_GELU_BWD) X(128, 0, EPI_F32) X(128, 0, EPI_GENERIC) \
+  X(256, 0, EPI_STORE) X(256, 0, EPI_ADD) X(256, 0, EPI_GELU) X(256, 0, EPI_GELU_BWD) X(256, 0, EPI_F32) X(256, 0, EPI_GENERIC) \
+  X(128, 1, EPI_F32) X(128, 1, EPI_GENERIC) X(256, 1, EPI_F32) X(256, 1, EPI_GENERIC)
 
 int gemm_init_attributes() {
   static int status = 1;
   static std::once_flag once;
   std::call_once(once, []() {
-    cudaError_t e[4];
-    e[0] = cudaFuncSetAttribute(gemm_tcgen05_kernel<128, 0, STAGES_BN128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                gemm_smem_bytes<128, STAGES_BN128>());
-    e[1] = cudaFuncSetAttribute(gemm_tcgen05_kernel<256, 0, STAGES_BN256, CLUSTER_BN256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                gemm_smem_bytes<256, STAGES_BN256>());
-    e[2] = cudaFuncSetAttribute(gemm_tcgen05_kernel<128, 1, STAGES_BN128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                gemm_smem_bytes<128, STAGES_BN128>());
-    e[3] = cudaFuncSetAttribute(gemm_tcgen05_kernel<256, 1, STAGES_BN256, CLUSTER_BN256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                gemm_smem_bytes<256, STAGES_BN256>());
     status = 0;
-    for (int i = 0; i < 4; ++i) {
-      if (e[i] != cudaSuccess) {
-        status = -1;
-        set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e[i]));
-      }
-    }
+#define KIT_SET_ATTR(BN, MODE, EPI)                                                                                         \
+  {                                                                                                                         \
+    cudaError_t e = cudaFuncSetAttribute(KIT_GEMM_KERNEL(BN, MODE, EPI), cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                         KIT_GEMM_SMEM(BN, EPI));                                                           \
+    if (e != cudaSuccess) {                                                                                                 \
+      status = -1;                                                                                                          \
+      set_error("cudaFuncSetAttribute(max dynamic smem, BN=%d mode=%d epi=%d) failed: %s", BN, MODE, EPI, cudaGetErrorString(e)); \
+    }                                                                                                                       \
+  }
+    KIT_GEMM_FOR_ALL(KIT_SET_ATTR)
+#undef KIT_SET_ATTR
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   });
   return status == 0 ? KIT_OK : KIT_ERR_CUDA;
+}
+
+static bool aligned16(const void* ptr, int64_t ld_elems, size_t esize) {
+  return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ((size_t)ld_elems * esize) % 16 == 0;
 }
 
 int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, void* C, int64_t ldc,
@@ -105,19 +111,25 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
   p.addend = addend; p.ld_addend = ld_addend;
   p.aux = aux; p.ld_aux = ld_aux;
   p.out_kind = out_kind; p.act = act;
-  { const char* d = getenv("KIT_GEMM_DBG"); p.dbg = d ? atoi(d) : 0; }
+  p.trace = nullptr;
+  if (getenv("KIT_GEMM_TRACE") != nullptr) {
+    static long long* trace_buf = nullptr;
+    if (trace_buf == nullptr && cudaMalloc(&trace_buf, 16 * sizeof(long long)) != cudaSuccess) trace_buf = nullptr;
+    p.trace = trace_buf;
+    g_trace_buf = trace_buf;
+  }
   plan->mode = mode;
   const int bn = (N > 128) ? 256 : 128;
+  const int cl = (bn == 256) ? 2 : 1;
   plan->bn = bn;
   p.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
   p.tiles_n = (N + bn - 1) / bn;
-  const int tiles = p.tiles_m * p.tiles_n;
   const int kb_total = (K + GEMM_BK - 1) / GEMM_BK;
+  const int groups = ((p.tiles_m + cl - 1) / cl) * p.tiles_n;
   int splits = 1;
   if (mode == 0) {
-    // A [M,K] K-major: box 64(k) x 128(m);  B [N,K] K-major: box 64(k) x BN(n)
+    // A [M,K] K-major: box 64(k) x 128(m);  B [N,K] K-major: box 64(k) x BN/cl (n) -- each CTA of a pair stages half of B
     if ((rc = make_tensor_map_2d(&plan->tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, GEMM_BK, GEMM_BM))) return rc;
-    const int cl = (bn == 256) ? CLUSTER_BN256 : 1;
     if ((rc = make_tensor_map_2d(&plan->tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, GEMM_BK, bn / cl))) return rc;
     splits = split_k > 1 ? split_k : 1;
   } else {
@@ -125,39 +137,33 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
     if ((rc = make_tensor_map_2d(&plan->tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, GEMM_BK))) return rc;
     if ((rc = make_tensor_map_2d(&plan->tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, GEMM_BK))) return rc;
     splits = split_k;
-    if (splits <= 0) {   // about one work item per cluster
-      const int clm = (bn == 256) ? CLUSTER_BN256 : 1;
-      const int groups = ((p.tiles_m + clm - 1) / clm) * p.tiles_n;
-      splits = (g_num_sms / clm) / groups;
-    }
+    if (splits <= 0) splits = (g_num_sms / cl) / groups;   // about one work item per CTA (pair)
   }
-  // outputs through shared memory + TMA (store / fp32 reduce-add) whenever the layout allows a tensor map
+  // epilogue kind: outputs (and the residual / GELU' input) through shared memory + TMA whenever tensor maps can describe them
   const size_t esize = (out_kind == OUT_BF16) ? 2 : 4;
-  p.tma_store = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (((size_t)ldc * esize) % 16 == 0);
-  if (act == ACT_GELU) p.tma_store = p.tma_store && ((reinterpret_cast<uintptr_t>(aux) & 15) == 0) && (((size_t)ld_aux * 2) % 16 == 0);
-  if (p.tma_store) {
-    if (out_kind == OUT_BF16) {
-      if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-    } else {
-      if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  int epi = EPI_GENERIC;
+  const bool c_ok = aligned16(C, ldc, esize) && (bias == nullptr || (N % 8) == 0);
+  if (c_ok) {
+    if (out_kind != OUT_BF16) {
+      if (act == ACT_NONE && addend == nullptr) epi = EPI_F32;
+    } else if (mode == 0) {
+      if (act == ACT_NONE && addend == nullptr) epi = EPI_STORE;
+      else if (act == ACT_NONE && aligned16(addend, ld_addend, 2)) epi = EPI_ADD;
+      else if (act == ACT_GELU && addend == nullptr && aligned16(aux, ld_aux, 2)) epi = EPI_GELU;
+      else if (act == ACT_GELU_BWD && addend == nullptr && aligned16(aux, ld_aux, 2)) epi = EPI_GELU_BWD;
     }
-    plan->tmAux = plan->tmC;
-    if (act == ACT_GELU) {
-      if ((rc = make_tensor_map_2d_typed(&plan->tmAux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, aux, (uint64_t)N, (uint64_t)M, (uint64_t)ld_aux * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-    }
-  } else {
-    plan->tmC = plan->tmA;
-    plan->tmAux = plan->tmA;
   }
-  // epilogue input tile (residual addend or GELU' pre-activation) through TMA as well
-  p.tma_in = 0;
-  if (p.tma_store && out_kind == OUT_BF16 && act != ACT_GELU) {
-    const bf16* in_ptr = (act == ACT_GELU_BWD) ? aux : addend;
-    const int64_t in_ld = (act == ACT_GELU_BWD) ? ld_aux : ld_addend;
-    const bool both = (act == ACT_GELU_BWD) && addend != nullptr;
-    if (in_ptr != nullptr && !both && (reinterpret_cast<uintptr_t>(in_ptr) & 15) == 0 && ((size_t)in_ld * 2) % 16 == 0) {
-      if ((rc = make_tensor_map_2d_typed(&plan->tmAux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, in_ptr, (uint64_t)N, (uint64_t)M, (uint64_t)in_ld * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-      p.tma_in = 1;
+  plan->epi = epi;
+  plan->tmC = plan->tmA;
+  plan->tmAux = plan->tmA;
+  if (epi == EPI_F32) {
+    if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  } else if (epi != EPI_GENERIC) {
+    if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    const bf16* side = (epi == EPI_ADD) ? addend : aux;
+    const int64_t side_ld = (epi == EPI_ADD) ? ld_addend : ld_aux;
+    if (epi != EPI_STORE) {
+      if ((rc = make_tensor_map_2d_typed(&plan->tmAux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, side, (uint64_t)N, (uint64_t)M, (uint64_t)side_ld * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     }
   }
   if (splits > kb_total) splits = kb_total;
@@ -165,10 +171,9 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
   KIT_REQUIRE(splits == 1 || out_kind == OUT_F32_ATOMIC, "split-K needs the atomic fp32 epilogue");
   p.kb_per_split = (kb_total + splits - 1) / splits;
   p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
-  const int clw = (bn == 256) ? CLUSTER_BN256 : 1;
-  const int items = ((p.tiles_m + clw - 1) / clw) * p.tiles_n * p.splits;   // work items per cluster
-  const int max_clusters = g_num_sms / clw;
-  plan->grid = (items < max_clusters ? items : max_clusters) * clw;
+  const int items = groups * p.splits;   // work items per CTA (pair)
+  const int max_clusters = g_num_sms / cl;
+  plan->grid = (items < max_clusters ? items : max_clusters) * cl;
   return KIT_OK;
 }
 
@@ -193,13 +198,20 @@ static int launch_one(KernelT kernel, int grid, int threads, int smem, int clust
 }
 
 int gemm_launch(const GemmPlan* plan, cudaStream_t stream) {
-  if (plan->mode == 0 && plan->bn == 128)
-    return launch_one(gemm_tcgen05_kernel<128, 0, STAGES_BN128, 1>, plan->grid, gemm_threads<128>(), gemm_smem_bytes<128, STAGES_BN128>(), 1, stream, plan);
-  if (plan->mode == 0)
-    return launch_one(gemm_tcgen05_kernel<256, 0, STAGES_BN256, CLUSTER_BN256>, plan->grid, gemm_threads<256>(), gemm_smem_bytes<256, STAGES_BN256>(), CLUSTER_BN256, stream, plan);
-  if (plan->bn == 128)
-    return launch_one(gemm_tcgen05_kernel<128, 1, STAGES_BN128, 1>, plan->grid, gemm_threads<128>(), gemm_smem_bytes<128, STAGES_BN128>(), 1, stream, plan);
-  return launch_one(gemm_tcgen05_kernel<256, 1, STAGES_BN256, CLUSTER_BN256>, plan->grid, gemm_threads<256>(), gemm_smem_bytes<256, STAGES_BN256>(), CLUSTER_BN256, stream, plan);
+#define KIT_DISPATCH(BN, MODE, EPI)                                                                                          \
+  if (plan->bn == BN && plan->mode == MODE && plan->epi == EPI)                                                              \
+    return launch_one(KIT_GEMM_KERNEL(BN, MODE, EPI), plan->grid, gemm_threads<BN>(), KIT_GEMM_SMEM(BN, EPI), (BN) == 256 ? 2 : 1, \
+                      stream, plan);
+  KIT_GEMM_FOR_ALL(KIT_DISPATCH)
+#undef KIT_DISPATCH
+  set_error("gemm_launch: no kernel for bn=%d mode=%d epi=%d", plan->bn, plan->mode, plan->epi);
+  return KIT_ERR_INVALID;
 }
 
 }  // namespace kit
+
+// experiments only: the 16 clock64 marks of CTA 0 of the last traced GEMM (KIT_GEMM_TRACE=1)
+extern "C" int kit_gemm_trace_read(long long* out16) {
+  if (kit::g_trace_buf == nullptr) return KIT_ERR_INVALID;
+  return cudaMemcpy(out16, kit::g_trace_buf, 16 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? KIT_OK : KIT_ERR_CUDA;
+}

@@ -1,17 +1,26 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a -- persistent, warp-specialised.
 //
 // Each CTA (one per SM) loops over 128 x BN output tiles.  Operands are staged by TMA into
-// 128B-swizzled shared memory through a STAGES-deep mbarrier ring that runs ahead across tile
+// 128B-swizzled shared memory through a multi-stage mbarrier ring that runs ahead across tile
 // boundaries; one elected thread issues tcgen05.mma into one of TWO fp32 accumulators in tensor
-// memory, so the epilogue of tile i (tcgen05.ld -> fused epilogue -> global stores, 8 warps)
-// overlaps the TMA + MMA main loop of tile i+1.
+// memory, so the epilogue of tile i (tcgen05.ld -> fused epilogue -> TMA stores) overlaps the
+// TMA + MMA main loop of tile i+1.
 //
 //   MODE 0 (TN)    C[M,N] = A[M,K] * B[N,K]^T      both operands K-major      (y = x W^T, dx = dy W)
 //   MODE 1 (wgrad) C[M,N] = A[K,M]^T * B[K,N]      both operands MN-major     (dW = dy^T x), split-K
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2.. = epilogue
-// (BN/16 of them: TMEM lane quadrant = warp % 4, 64-column group = (warp - 2) / 4).  The epilogue is
-// ALU / latency bound (GELU, casts), hence the many warps.
+// (BN/16 of them: TMEM lane quadrant = warp % 4, 64-column group = (warp - 2) / 4).
+//
+// CL = 2: a CTA pair (thread-block cluster) computes a 256 x BN tile with tcgen05.mma.cta_group::2: each CTA stages its own
+// 128 rows of A and only HALF of the B tile (32 KB per k-block instead of 48 KB), the leader CTA's MMA thread issues for
+// both, and each CTA's epilogue drains its own 128 accumulator rows.
+//
+// The epilogue is a compile-time kind (EPI_*): what bounds the K = 256 GEMMs of this model is not the tensor pipe but the
+// CUDA-core work per output element and the latency chain tcgen05.ld -> math -> st.shared -> fence -> TMA store of each
+// epilogue warp, so every kind is a straight-line loop over 16-byte chunks with shared-space accesses, inputs (residual /
+// GELU' pre-activation) prefetched by TMA before the accumulator is ready, and 2 or 3 staging tiles per warp in rotation so
+// that a warp rarely waits for its own previous store.
 #pragma once
 #include "common.cuh"
 
@@ -19,6 +28,15 @@ namespace kit {
 
 enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ATOMIC = 2 };
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_GELU_BWD = 2 };
+enum {
+  EPI_STORE = 0,     // bf16 C = acc (+ bias)
+  EPI_ADD = 1,       // bf16 C = acc (+ bias) + addend            (addend tile by TMA, result written in place)
+  EPI_GELU = 2,      // bf16 aux = acc + bias ; C = gelu(aux)
+  EPI_GELU_BWD = 3,  // bf16 C = acc * gelu'(aux)                  (aux tile by TMA, result written in place)
+  EPI_F32 = 4,       // fp32 C = acc (+ bias): TMA store or TMA reduce-add (split-K weight gradients)
+  EPI_GENERIC = 5,   // any combination through direct global accesses (pitches / extents a tensor map cannot describe)
+  EPI_KINDS = 6
+};
 
 struct GemmParams {
   int M, N, K;  // C is [M,N]; K is the reduction extent
@@ -32,121 +50,75 @@ struct GemmParams {
   int out_kind, act;
   int kb_per_split;  // 64-wide k-blocks per work item
   int tiles_m, tiles_n, splits;
-  int tma_store;  // 1: outputs leave through shared memory + TMA store / reduce-add (clipped at the edges)
-  int dbg;        // experiments only (KIT_GEMM_DBG): 1 = no TMA stores, 2 = no wait on staging reuse, 4 = no tmem loads
-  int tma_in;     // 1: the addend / GELU' pre-activation tile arrives through TMA (tmAux) instead of per-row loads
+  long long* trace;   // experiments only (KIT_GEMM_TRACE): clock64 marks of CTA 0, see kit_gemm_trace_read
 };
 
 struct GemmPlan {
   CUtensorMap tmA, tmB, tmC, tmAux;
   GemmParams p;
-  int mode, bn;
+  int mode, bn, epi;
   int grid;
 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_MAX_EPI_WARPS = 16;
-constexpr int GEMM_EPI_BUF = 4096;  // per epilogue warp: 2 KB out tile (bf16, 64B-swizzled) + 2 KB second tile
-                                    // (GELU pre-activation out / TMA-staged input), or one 4 KB fp32 out tile
+constexpr int GEMM_SMEM_LIMIT = 232448;   // 227 KB per CTA
+constexpr int GEMM_SMEM_TAIL = 2048;      // barriers + 1024-byte alignment slack
 
 template <int BN>
 constexpr int gemm_epi_warps() { return BN / 16; }
 template <int BN>
 constexpr int gemm_threads() { return 64 + 32 * gemm_epi_warps<BN>(); }
-
-template <int BN, int STAGES>
+// 2 KB staging tiles ([32 rows x 64 B] bf16, or half of a [32 x 128 B] fp32 tile) per epilogue warp
+template <int EPI>
+constexpr int gemm_epi_tiles() { return EPI == EPI_GENERIC ? 0 : (EPI == EPI_GELU || EPI == EPI_GELU_BWD) ? 3 : 2; }
+template <int BN, int CL>
+constexpr int gemm_stage_bytes() { return GEMM_BM * GEMM_BK * 2 + (BN / CL) * GEMM_BK * 2; }
+template <int BN, int CL, int EPI>
+constexpr int gemm_stages() {
+  const int avail = GEMM_SMEM_LIMIT - GEMM_SMEM_TAIL - gemm_epi_warps<BN>() * gemm_epi_tiles<EPI>() * 2048;
+  const int s = avail / gemm_stage_bytes<BN, CL>();
+  return s > 6 ? 6 : s;
+}
+template <int BN, int CL, int EPI>
 constexpr int gemm_smem_bytes() {
-  return STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + gemm_epi_warps<BN>() * GEMM_EPI_BUF + 1024 /*align slack*/ +
-         256 /*barriers*/;
+  return gemm_stages<BN, CL, EPI>() * gemm_stage_bytes<BN, CL>() + gemm_epi_warps<BN>() * gemm_epi_tiles<EPI>() * 2048 + GEMM_SMEM_TAIL;
 }
 
-// bias / residual / activation on 32 accumulator columns of one row, in registers (packed fp32 pairs).  Columns >= N
-// of a ragged last chunk are computed on garbage and clipped by the TMA store.
+// ---------------------------------------------------------------- shared-space accesses / TMA by 32-bit shared address
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_a(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d_a(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void add_pair(float& a, float& b, float x, float y) { up2(add2(pk2(a, b), pk2(x, y)), a, b); }
-__device__ __forceinline__ void gemm_epilogue_math(const GemmParams& p, int row, int col0, bool row_ok, const float* in_vals,
-                                                   float (&v)[32]) {
-  const bool full = col0 + 32 <= p.N;
-  if (p.bias != nullptr) {
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-        add_pair(v[j], v[j + 1], b4.x, b4.y);
-        add_pair(v[j + 2], v[j + 3], b4.z, b4.w);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-    }
-  }
-  if (in_vals != nullptr) {   // tile staged by TMA (zero-filled outside the tensor)
-    if (p.act == ACT_GELU_BWD) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) gelu_grad_mul_pair(in_vals[j], in_vals[j + 1], v[j], v[j + 1]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) add_pair(v[j], v[j + 1], in_vals[j], in_vals[j + 1]);
-    }
-    return;
-  }
-  if (p.addend != nullptr && row_ok) {
-    const bf16* ap = p.addend + (int64_t)row * p.ld_addend + col0;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float t[8];
-        load8(ap + j, t);
-#pragma unroll
-        for (int u = 0; u < 8; u += 2) add_pair(v[j + u], v[j + u + 1], t[u], t[u + 1]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) v[j] += __bfloat162float(ap[j]);
-    }
-  }
-  if (p.act == ACT_GELU_BWD && row_ok) {
-    const bf16* xp = p.aux + (int64_t)row * p.ld_aux + col0;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float t[8];
-        load8(xp + j, t);
-#pragma unroll
-        for (int u = 0; u < 8; u += 2) gelu_grad_mul_pair(t[u], t[u + 1], v[j + u], v[j + u + 1]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) v[j] *= gelu_act_grad(__bfloat162float(xp[j]));
-    }
-  }
-}
-// 32 bf16 values of this lane's row into a [32 rows x 64 B] tile, 64B-swizzled (conflict-free, TMA SWIZZLE_64B)
-__device__ __forceinline__ void stage_bf16(uint8_t* buf, int lane, const float (&v)[32]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    *reinterpret_cast<uint4*>(buf + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = pack8(&v[8 * i]);
-}
-__device__ __forceinline__ void unstage_bf16(const uint8_t* buf, int lane, float (&v)[32]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint4 u = *reinterpret_cast<const uint4*>(buf + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4));
-    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-    v[8 * i] = a.x; v[8 * i + 1] = a.y; v[8 * i + 2] = b.x; v[8 * i + 3] = b.y;
-    v[8 * i + 4] = c.x; v[8 * i + 5] = c.y; v[8 * i + 6] = d.x; v[8 * i + 7] = d.y;
-  }
-}
-// 32 fp32 values into a [32 rows x 128 B] tile, 128B-swizzled
-__device__ __forceinline__ void stage_f32(uint8_t* ebuf, int lane, const float (&v)[32]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    *reinterpret_cast<float4*>(ebuf + lane * 128 + ((i ^ (lane & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
 
-// One row x 32 consecutive columns of the accumulator through the fused epilogue.
+// One row x 32 consecutive columns of the accumulator through the fused epilogue with direct global accesses (EPI_GENERIC).
 __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, int row, int col0, float (&v)[32], bool vec_ok) {
   const bool full_chunk = (col0 + 32 <= p.N) && vec_ok;
   if (full_chunk) {
@@ -227,30 +199,80 @@ __device__ __forceinline__ void gemm_epilogue_chunk(const GemmParams& p, int row
   }
 }
 
-// CL = 2: CTA pairs (thread-block cluster) work on two vertically adjacent M tiles of the same N tile; each CTA
-// fetches half of the shared B tile and TMA-multicasts it to both, cutting the L2 -> SM operand traffic by a third.
-template <int BN, int MODE, int STAGES, int CL>
+// 32 accumulator columns of this lane's row -> the staging tile(s), 8 columns (one 16-byte bf16 chunk) at a time.
+//   t_out / t_aux: shared addresses of [32 rows x 64 B] tiles in the TMA SWIZZLE_64B layout (16-byte chunk i of row r sits at
+//   chunk i ^ ((r >> 1) & 3)); EPI_F32: t_out is a [32 x 128 B] SWIZZLE_128B tile (chunk i ^ (r & 7)).
+//   EPI_ADD / EPI_GELU_BWD read their input from t_out and overwrite it in place.
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_sub(const GemmParams& p, int col0, int lane, const uint32_t (&r)[32], uint32_t t_out,
+                                                  uint32_t t_aux) {
+  const uint32_t row64 = t_out + lane * 64, sw64 = (lane >> 1) & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[8 * i + u]);
+    if (p.bias != nullptr && col0 + 8 * i < p.N) {   // TMA kinds with a bias have N % 8 == 0 (planner)
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * i));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * i + 4));
+      add_pair(v[0], v[1], b0.x, b0.y); add_pair(v[2], v[3], b0.z, b0.w);
+      add_pair(v[4], v[5], b1.x, b1.y); add_pair(v[6], v[7], b1.z, b1.w);
+    }
+    if (EPI == EPI_F32) {
+      const uint32_t row128 = t_out + lane * 128, sw128 = lane & 7;
+      sts128(row128 + (((2 * i) ^ sw128) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+      sts128(row128 + (((2 * i + 1) ^ sw128) << 4), __float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+      continue;
+    }
+    const uint32_t off = (i ^ sw64) << 4;
+    if (EPI == EPI_ADD || EPI == EPI_GELU_BWD) {
+      const uint4 in = lds128(row64 + off);
+      const float2 a = unpack_bf16(in.x), b = unpack_bf16(in.y), c = unpack_bf16(in.z), d = unpack_bf16(in.w);
+      if (EPI == EPI_ADD) {
+        add_pair(v[0], v[1], a.x, a.y); add_pair(v[2], v[3], b.x, b.y);
+        add_pair(v[4], v[5], c.x, c.y); add_pair(v[6], v[7], d.x, d.y);
+      } else {
+        gelu_grad_mul_pair(a.x, a.y, v[0], v[1]); gelu_grad_mul_pair(b.x, b.y, v[2], v[3]);
+        gelu_grad_mul_pair(c.x, c.y, v[4], v[5]); gelu_grad_mul_pair(d.x, d.y, v[6], v[7]);
+      }
+    }
+    if (EPI == EPI_GELU) {
+      sts128(t_aux + lane * 64 + off, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      gelu_pair(v[0], v[1]); gelu_pair(v[2], v[3]); gelu_pair(v[4], v[5]); gelu_pair(v[6], v[7]);
+    }
+    sts128(row64 + off, pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+
+template <int BN, int MODE, int CL, int EPI>
 __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                          const __grid_constant__ CUtensorMap tmB,
                                                                          const __grid_constant__ CUtensorMap tmC,
                                                                          const __grid_constant__ CUtensorMap tmAux,
                                                                          const GemmParams p) {
   constexpr int BM = GEMM_BM, BK = GEMM_BK;
-  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGES = gemm_stages<BN, CL, EPI>();
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = (BN / CL) * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TMEM_COLS = 2 * BN;  // two accumulators
+  constexpr int EPI_WARPS = gemm_epi_warps<BN>();
+  constexpr int EPI_TILES = gemm_epi_tiles<EPI>();
   static_assert(BN == 128 || BN == 256, "BN must give a power-of-two TMEM allocation <= 512");
+  static_assert(STAGES >= 3, "operand ring too shallow");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
-  constexpr int EPI_WARPS = gemm_epi_warps<BN>();
-  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + EPI_WARPS * GEMM_EPI_BUF);
+  uint64_t* full = reinterpret_cast<uint64_t*>(epi_smem + EPI_WARPS * EPI_TILES * 2048);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
-  uint64_t* in_bars = tmem_empty + 2;     // [EPI_WARPS] epilogue input tiles (addend / GELU' aux)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bars + GEMM_MAX_EPI_WARPS);
+  uint64_t* in_bars = tmem_empty + 2;     // [EPI_WARPS][2] epilogue input tiles (addend / GELU' pre-activation)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bars + 2 * GEMM_MAX_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto mark = [&](int slot) {
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[slot] = clock64();
+  };
+  if (warp == 0) mark(0);
   const int kb_total = (p.K + BK - 1) / BK;
   // work items are (split, n tile, group of CL m tiles); CTA `rank` of a cluster takes m tile CL*group + rank
   const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
@@ -262,26 +284,31 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.tma_store) tma_prefetch_desc(&tmC);
+    if (EPI != EPI_GENERIC) tma_prefetch_desc(&tmC);
+    if (EPI == EPI_ADD || EPI == EPI_GELU || EPI == EPI_GELU_BWD) tma_prefetch_desc(&tmAux);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CL);   // every CTA of the cluster must have consumed the slot (multicast B)
+      mbar_init(&full[s], 1);    // CL = 2: only the leader's is used; it collects the bytes of both CTAs
+      mbar_init(&empty[s], 1);   // one tcgen05.commit arrival (multicast to both CTAs when CL = 2)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], EPI_WARPS);
+      mbar_init(&tmem_empty[s], EPI_WARPS * CL);   // CL = 2: the peer's epilogue warps arrive on the leader's barrier
     }
-    for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&in_bars[s], 1);
+    for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(&in_bars[s], 1);
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if (CL == 1) tmem_alloc<TMEM_COLS>(tmem_slot); else tmem_alloc_cg2<TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();   // peer barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) mark(1);
   pdl_grid_sync();   // everything above overlapped the previous kernel; operands / outputs are touched only below
+  if (warp == 0) mark(2);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -291,28 +318,34 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
         const int n0 = (rem / groups_m) * BN, m0 = ((rem % groups_m) * CL + rank) * BM;
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
+        const int nb = n0 + rank * (BN / CL);   // CL = 2: this CTA stages its half of the B tile
         for (int kb = kb_begin; kb < kb_end; ++kb, ++cnt) {
           const int s = cnt % STAGES;
           const uint32_t ph = (cnt / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+          if (cnt == 0) mark(3);
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], STAGE_BYTES * CL);
           uint8_t* sA = smem + s * STAGE_BYTES;
           uint8_t* sB = sA + A_BYTES;
           const int kc = kb * BK;
           if (MODE == 0) {
-            tma_load_2d(sA, &tmA, &full[s], kc, m0);
             if (CL == 1) {
-              tma_load_2d(sB, &tmB, &full[s], kc, n0);
-            } else {   // my half of the B rows, delivered to both CTAs
-              tma_load_2d_mc(sB + rank * (BN / CL) * 128, &tmB, &full[s], kc, n0 + rank * (BN / CL), (uint16_t)((1 << CL) - 1));
+              tma_load_2d(sA, &tmA, &full[s], kc, m0);
+              tma_load_2d(sB, &tmB, &full[s], kc, nb);
+            } else {
+              tma_load_2d_cg2(sA, &tmA, &full[s], kc, m0);
+              tma_load_2d_cg2(sB, &tmB, &full[s], kc, nb);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * (BK * 128), &tmA, &full[s], m0 + 64 * j, kc);
+            for (int j = 0; j < BM / 64; ++j) {
+              if (CL == 1) tma_load_2d(sA + j * (BK * 128), &tmA, &full[s], m0 + 64 * j, kc);
+              else tma_load_2d_cg2(sA + j * (BK * 128), &tmA, &full[s], m0 + 64 * j, kc);
+            }
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) {
-              if (CL == 1) tma_load_2d(sB + j * (BK * 128), &tmB, &full[s], n0 + 64 * j, kc);
-              else if ((j % CL) == rank) tma_load_2d_mc(sB + j * (BK * 128), &tmB, &full[s], n0 + 64 * j, kc, (uint16_t)((1 << CL) - 1));
+            for (int j = 0; j < BN / CL / 64; ++j) {
+              if (CL == 1) tma_load_2d(sB + j * (BK * 128), &tmB, &full[s], nb + 64 * j, kc);
+              else tma_load_2d_cg2(sB + j * (BK * 128), &tmB, &full[s], nb + 64 * j, kc);
             }
           }
         }
@@ -320,8 +353,8 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, MODE == 1, MODE == 1);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM * CL, BN, MODE == 1, MODE == 1);
       uint32_t cnt = 0, it = 0;
       for (int item = first_item; item < n_items; item += item_stride, ++it) {
         const int split = item / tiles_mn;
@@ -335,6 +368,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
           const int s = cnt % STAGES;
           const uint32_t ph = (cnt / STAGES) & 1;
           mbar_wait(&full[s], ph);
+          if (cnt == 0) mark(4);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t b_base = a_base + A_BYTES;
@@ -348,123 +382,134 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
               adesc = make_smem_desc_sw128(a_base + k * 16 * 128, BK * 128, 1024);
               bdesc = make_smem_desc_sw128(b_base + k * 16 * 128, BK * 128, 1024);
             }
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            if (CL == 1) umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            else umma_bf16_cg2(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          if (CL == 1) umma_commit(&empty[s]); else umma_commit_mc(&empty[s], (uint16_t)((1 << CL) - 1));
+          if (CL == 1) umma_commit(&empty[s]); else umma_commit_cg2(&empty[s], (uint16_t)3);   // slot free in both CTAs
         }
-        umma_commit(&tmem_full[as]);
+        if (CL == 1) umma_commit(&tmem_full[as]); else umma_commit_cg2(&tmem_full[as], (uint16_t)3);
+        if (it == 0) mark(5);
       }
     }
     __syncwarp();
   } else {
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;   // 64-column group of the tile owned by this warp
-    const bool vec_ok = ((p.ldc & 7) == 0) && ((p.N & 7) == 0) && (p.addend == nullptr || (p.ld_addend & 7) == 0) &&
-                        (p.aux == nullptr || (p.ld_aux & 7) == 0);
-    uint8_t* ebuf = epi_smem + (warp - 2) * GEMM_EPI_BUF;
-    uint8_t* ebuf2 = ebuf + 2048;
-    uint64_t* in_bar = &in_bars[warp - 2];
-    uint32_t in_ph = 0;
-    const bool tma_in = p.tma_in != 0 && p.out_kind == OUT_BF16;
-    const bool gelu = p.act == ACT_GELU;
+    const uint32_t tiles = smem_u32(epi_smem) + (warp - 2) * (EPI_TILES * 2048);
+    uint64_t* in_bar = &in_bars[(warp - 2) * 2];
+    uint32_t in_ph[2] = {0, 0};
+    uint32_t rr = 0;   // rotation of the staging tiles (3-tile kinds)
     uint32_t it = 0;
     for (int item = first_item; item < n_items; item += item_stride, ++it) {
       const int split = item / tiles_mn, rem = item - split * tiles_mn;
       const int n0 = (rem / groups_m) * BN, m0 = ((rem % groups_m) * CL + rank) * BM;
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
       const int row0 = m0 + q * 32;
-      const int row = row0 + lane;
-      const bool row_ok = row < p.M;
       const int colg = n0 + cg * 64;
       const uint32_t tmem_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + cg * 64);
-      auto issue_in = [&](int col) {   // TMA: [32 rows x 32 cols] bf16 input tile -> second staging tile
-        if (lane == 0) {
-          mbar_arrive_expect_tx(in_bar, 2048);
-          tma_load_2d(ebuf2, &tmAux, in_bar, col, row0);
-        }
-      };
       auto release_tmem = [&]() {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (lane == 0) {
+          if (CL == 1 || rank == 0) mbar_arrive(&tmem_empty[as]); else mbar_arrive_cluster(&tmem_empty[as], 0);
+        }
       };
-      auto staging_free = [&]() {   // the previous TMA stores have finished READING the staging tiles
-        if (lane == 0 && !(p.dbg & 2)) tma_store_wait_read();
+      const bool have0 = colg < p.N, have1 = colg + 32 < p.N;   // warp-uniform
+      // staging tiles of the two 32-column halves
+      uint32_t t_sub[2] = {tiles, tiles}, t_aux[2] = {tiles, tiles};
+      if (EPI == EPI_GELU) {            // stores in order: aux0 -> rr, out0 -> rr+1, aux1 -> rr+2, out1 -> rr+3 (= rr)
+        t_aux[0] = tiles + (rr % 3) * 2048;       t_sub[0] = tiles + ((rr + 1) % 3) * 2048;
+        t_aux[1] = tiles + ((rr + 2) % 3) * 2048; t_sub[1] = tiles + (rr % 3) * 2048;
+        rr += 4;
+      } else if (EPI == EPI_GELU_BWD) {  // stores go round the three tiles: a tile's previous store is 3 stores old
+        t_sub[0] = tiles + (rr % 3) * 2048;
+        t_sub[1] = tiles + ((rr + 1) % 3) * 2048;
+        rr += 2;
+      } else if (EPI == EPI_STORE || EPI == EPI_ADD) {
+        t_sub[1] = tiles + 2048;
+      }
+      if (EPI != EPI_GENERIC && have0 && p.bias != nullptr && lane < 2 && colg + 32 * lane < p.N) prefetch_l1(p.bias + colg + 32 * lane);
+      if (EPI == EPI_ADD || EPI == EPI_GELU_BWD) {   // input tiles land while the MMAs of this tile are still running
+        if (lane == 0 && have0) {
+          tma_store_wait_read_n<1>();   // the tile(s) below were last read by stores that are at least 2 groups old
+          mbar_arrive_expect_tx(&in_bar[0], 2048);
+          tma_load_2d_a(t_sub[0], &tmAux, &in_bar[0], colg, row0);
+          if (have1) {
+            if (EPI == EPI_ADD) tma_store_wait_read_n<0>();   // two tiles only: tile 1 carried the most recent store
+            mbar_arrive_expect_tx(&in_bar[1], 2048);
+            tma_load_2d_a(t_sub[1], &tmAux, &in_bar[1], colg + 32, row0);
+          }
+        }
         __syncwarp();
-      };
-      if (tma_in && colg < p.N) issue_in(colg);   // overlaps the wait for the MMAs
+      }
       mbar_wait(&tmem_full[as], aph);
+      if (it == 0 && warp == 2) mark(6);
       tc_fence_after();
+      if (!have0) {   // nothing to write: only keep the TMEM protocol alive
+        release_tmem();
+        continue;
+      }
 #pragma unroll 1
       for (int sub = 0; sub < 2; ++sub) {
         const int col0 = colg + sub * 32;
+        if (sub == 1 && !have1) {
+          release_tmem();
+          break;
+        }
         uint32_t r[32];
-        __syncwarp();
-        if (!(p.dbg & 4)) tmem_ld32(tmem_row + uint32_t(sub * 32), r);
-        float v[32];
-        if (col0 >= p.N) {   // nothing to write (uniform): only keep the TMEM protocol alive
-          tmem_ld_wait();
-          if (sub == 1) release_tmem();
+        tmem_ld32(tmem_row + uint32_t(sub * 32), r);
+        if (EPI == EPI_ADD || EPI == EPI_GELU_BWD) {
+          mbar_wait(&in_bar[sub], in_ph[sub]);
+          in_ph[sub] ^= 1;
+        }
+        tmem_ld_wait();
+        if (it == 0 && warp == 2 && sub == 0) mark(7);
+        if (sub == 1) release_tmem();
+        if (EPI == EPI_GENERIC) {
+          const int row = row0 + lane;
+          if (row < p.M) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            const bool vec_ok = ((p.ldc & 7) == 0) && ((p.N & 7) == 0) && (p.addend == nullptr || (p.ld_addend & 7) == 0) &&
+                                (p.aux == nullptr || (p.ld_aux & 7) == 0);
+            gemm_epilogue_chunk(p, row, col0, v, vec_ok);
+          }
           continue;
         }
-        if (p.tma_store && p.out_kind == OUT_BF16) {
-          float in_vals[32];
-          if (tma_in) {
-            mbar_wait(in_bar, in_ph);
-            in_ph ^= 1;
-            unstage_bf16(ebuf2, lane, in_vals);
-            __syncwarp();
-            if (sub == 0 && col0 + 32 < p.N) issue_in(col0 + 32);   // prefetch the second half's input tile
-          }
-          tmem_ld_wait();
-          if (sub == 1) release_tmem();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          gemm_epilogue_math(p, row, col0, row_ok, tma_in ? in_vals : nullptr, v);
-          staging_free();
-          if (gelu) {   // pre-activation to the second tile, activation to the first
-            stage_bf16(ebuf2, lane, v);
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) gelu_pair(v[j], v[j + 1]);
-          }
-          stage_bf16(ebuf, lane, v);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0 && !(p.dbg & 1)) {
-            if (gelu) tma_store_2d(&tmAux, ebuf2, col0, row0);
-            tma_store_2d(&tmC, ebuf, col0, row0);
-            tma_store_commit();
-          }
-        } else if (p.tma_store) {   // fp32 tile: plain store or L2 reduce-add (split-K weight gradients)
-          tmem_ld_wait();
-          if (sub == 1) release_tmem();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          gemm_epilogue_math(p, row, col0, row_ok, nullptr, v);
-          staging_free();
-          stage_f32(ebuf, lane, v);
-          fence_proxy_async();
-          __syncwarp();
+        // the staging tile(s) of this half are free once the bulk stores that last read them have done so
+        if (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_F32) {
           if (lane == 0) {
-            if (p.out_kind == OUT_F32_ATOMIC) tma_reduce_add_2d(&tmC, ebuf, col0, row0); else tma_store_2d(&tmC, ebuf, col0, row0);
+            if (EPI == EPI_F32) tma_store_wait_read_n<0>(); else tma_store_wait_read_n<1>();
+          }
+          __syncwarp();
+        }
+        gemm_epilogue_sub<EPI>(p, col0, lane, r, t_sub[sub], t_aux[sub]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (EPI == EPI_GELU) {   // one bulk group per store: the rotation waits on "all but the latest"
+            tma_store_2d_a(&tmAux, t_aux[sub], col0, row0);
             tma_store_commit();
           }
-        } else {   // layouts a tensor map cannot describe (unaligned pitch): direct global accesses
-          tmem_ld_wait();
-          if (sub == 1) release_tmem();
-          if (!row_ok) continue;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          gemm_epilogue_chunk(p, row, col0, v, vec_ok);
+          if (EPI == EPI_F32 && p.out_kind == OUT_F32_ATOMIC) tma_reduce_add_2d_a(&tmC, t_sub[sub], col0, row0);
+          else tma_store_2d_a(&tmC, t_sub[sub], col0, row0);
+          tma_store_commit();
         }
+        if (it == 0 && warp == 2 && sub == 0) mark(8);
       }
     }
-    if (p.tma_store && lane == 0) tma_store_wait_all();   // global writes complete before the CTA exits
+    if (warp == 2) mark(9);
+    if (EPI != EPI_GENERIC && lane == 0) tma_store_wait_all();   // global writes complete before the CTA exits
+    if (warp == 2) mark(10);
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // no CTA exits while its peer may still multicast into it / signal its barriers
-  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (CL > 1) cluster_sync_all();   // no CTA exits while its peer may still read its shared memory / signal its barriers
+  if (warp == 0) mark(11);
+  if (warp == 1) {
+    if (CL == 1) tmem_dealloc<TMEM_COLS>(tmem_base); else tmem_dealloc_cg2<TMEM_COLS>(tmem_base);
+  }
 }
 
 // ---------------------------------------------------------------- host side

@@ -72,6 +72,15 @@ def main():
         times.sort()
         med = times[len(times) // 2]
         fl = 2.0 * m * n * k
+        if os.environ.get("KIT_GEMM_TRACE"):
+            import ctypes
+            buf = (ctypes.c_longlong * 16)()
+            lib.kit_gemm_trace_read.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
+            if lib.kit_gemm_trace_read(buf) == 0:
+                t0 = buf[0]
+                names = ["entry", "setup_done", "pdl_done", "tma_first", "full_first", "mma_item0_done", "epi_tmem_full",
+                         "epi_ld_done", "epi_store_issued", "epi_loop_end", "epi_store_drained", "exit"]
+                print("   trace(cycles): " + " ".join(f"{n}={buf[i] - t0}" for i, n in enumerate(names)))
         print(f"{name:20s} M={m:6d} N={n:5d} K={k:6d}  {med * 1e3:8.1f} us  {fl / (med * 1e-3) / 1e12:7.1f} TFLOP/s", flush=True)
 
 
