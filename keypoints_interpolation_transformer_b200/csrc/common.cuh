@@ -98,9 +98,13 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   return r;
 }
 __device__ __forceinline__ float tanh_approx(float x) {
+#ifdef KIT_EXP_NO_MUFU
+  return fmaf(x, 0.25f, 0.1f);   // timing experiment only
+#else
   float r;
   asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+#endif
 }
 // GELU (activation="gelu" at model.py:87, the erf form) evaluated through 0.5 x (1 + tanh(c0 x + c1 x^3)), c0 = sqrt(2/pi),
 // c1 = 0.044715 c0: within 4.8e-4 absolute of the erf form (plus 2^-11 relative from MUFU.TANH) -- below the bf16 rounding of

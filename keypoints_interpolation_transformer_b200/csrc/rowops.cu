@@ -213,14 +213,37 @@ __global__ void add_ln_fwd_kernel(const bf16* __restrict__ a, const bf16* __rest
 }
 
 // dx = LN_bwd(dy) (+ addend);  dgamma += sum_rows dy*xhat;  dbeta += sum_rows dy
-template <int NV>
-__global__ void ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ s_saved,
-                              const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                              const float* __restrict__ gamma, const bf16* __restrict__ addend,
-                              bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                              float* __restrict__ dxsum, int64_t M, int H) {
+// One block per SM-slot with WARPS warps; every warp walks rows two at a time (two independent load -> reduce -> store
+// chains in flight), keeps the three column accumulators in registers and the block folds them with ONE atomic per column
+// (grid-way contention per address instead of M/32-way).
+template <int NV, int WARPS>
+__device__ __forceinline__ void ln_bwd_cols(const RowVec<NV>& acc, float* out, int H, float (*buf)[NV * 256]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    if (c < H) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) buf[warp][c + u] = acc.v[i][u];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) t += buf[w][c];
+    atomicAdd(out + c, t);
+  }
+}
+template <int NV, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ s_saved,
+                                                            const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                            const float* __restrict__ gamma, const bf16* __restrict__ addend,
+                                                            bf16* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, float* __restrict__ dxsum, int64_t M, int H) {
   pdl_grid_sync();
-  __shared__ float s_buf[ROW_WARPS][NV * 256];
+  __shared__ float s_buf[WARPS][NV * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RowVec<NV> accg, accb, accx, gm;
 #pragma unroll
@@ -235,47 +258,60 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restric
     }
     if (c < H) load8(gamma + c, gm.v[i]);
   }
-  for (int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp; row < M; row += (int64_t)gridDim.x * ROW_WARPS) {
-    RowVec<NV> x, g;
-    row_load(x, s_saved + row * H, H, lane);
-    row_load(g, dy + row * H, H, lane);
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    float s1 = 0.f, s2 = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * WARPS;
+  for (int64_t row0 = (int64_t)blockIdx.x * WARPS + warp; row0 < M; row0 += 2 * stride) {
+    const int64_t rows[2] = {row0, row0 + stride};
+    const bool has1 = rows[1] < M;
+    RowVec<NV> x[2], g[2];
+    float mean[2], rstd[2];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (lane + 32 * i) * 8;
-      const bool ok = c < H;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float xh = ok ? (x.v[i][u] - mean) * rstd : 0.f;
-        const float d = g.v[i][u];
-        accg.v[i][u] += d * xh;
-        accb.v[i][u] += d;
-        const float gg = d * gm.v[i][u];
-        s1 += gg;
-        s2 += gg * xh;
-        x.v[i][u] = xh;
-        g.v[i][u] = gg;
-      }
+    for (int k = 0; k < 2; ++k) {
+      if (k == 1 && !has1) break;
+      row_load(x[k], s_saved + rows[k] * H, H, lane);
+      row_load(g[k], dy + rows[k] * H, H, lane);
+      mean[k] = mean_in[rows[k]];
+      rstd[k] = rstd_in[rows[k]];
     }
-    s1 = warp_sum(s1) / (float)H;
-    s2 = warp_sum(s2) / (float)H;
-    RowVec<NV> ad;
-    if (addend != nullptr) row_load(ad, addend + row * H, H, lane);
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
+    for (int k = 0; k < 2; ++k) {
+      if (k == 1 && !has1) break;
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        float r = rstd * (g.v[i][u] - s1 - x.v[i][u] * s2);
-        accx.v[i][u] += r;   // column sums of the LN-input gradient = bias gradient of the producing Linear
-        if (addend != nullptr) r += ad.v[i][u];
-        g.v[i][u] = r;
+      for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 8;
+        const bool ok = c < H;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float xh = ok ? (x[k].v[i][u] - mean[k]) * rstd[k] : 0.f;
+          const float d = g[k].v[i][u];
+          accg.v[i][u] += d * xh;
+          accb.v[i][u] += d;
+          const float gg = d * gm.v[i][u];
+          s1 += gg;
+          s2 += gg * xh;
+          x[k].v[i][u] = xh;
+          g[k].v[i][u] = gg;
+        }
       }
-    row_store(g, dx + row * H, H, lane);
+      s1 = warp_sum(s1) / (float)H;
+      s2 = warp_sum(s2) / (float)H;
+      RowVec<NV> ad;
+      if (addend != nullptr) row_load(ad, addend + rows[k] * H, H, lane);
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float r = rstd[k] * (g[k].v[i][u] - s1 - x[k].v[i][u] * s2);
+          accx.v[i][u] += r;   // column sums of the LN-input gradient = bias gradient of the producing Linear
+          if (addend != nullptr) r += ad.v[i][u];
+          g[k].v[i][u] = r;
+        }
+      row_store(g[k], dx + rows[k] * H, H, lane);
+    }
   }
-  block_col_reduce_atomic<NV>(accg, dgamma, H, s_buf);
-  block_col_reduce_atomic<NV>(accb, dbeta, H, s_buf);
-  if (dxsum != nullptr) block_col_reduce_atomic<NV>(accx, dxsum, H, s_buf);
+  ln_bwd_cols<NV, WARPS>(accg, dgamma, H, s_buf);
+  ln_bwd_cols<NV, WARPS>(accb, dbeta, H, s_buf);
+  if (dxsum != nullptr) ln_bwd_cols<NV, WARPS>(accx, dxsum, H, s_buf);
 }
 
 // ---------------------------------------------------------------- SwiGLU gate (model.py:18-22)
@@ -532,8 +568,21 @@ int ln_bwd(const bf16* dy, const bf16* s_saved, const float* mean, const float* 
            const bf16* addend, bf16* dx, float* dgamma, float* dbeta, float* dxsum, int64_t M, int H, cudaStream_t st) {
   int rc = check_h(H);
   if (rc) return rc;
-  KIT_NV_DISPATCH(H, (launch_kernel(ln_bwd_kernel<NV>, dim3(reduce_blocks(M)), dim3(256), 0, st, dy, s_saved, mean, rstd, gamma, addend, dx,
-                                                                         dgamma, dbeta, dxsum, M, H)));
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  if (H <= 256) {   // 16 warps x 16 KB of column partials; one block per SM (103 registers x 512 threads)
+    const int64_t want = ceil_div(M, 16 * 2);
+    const unsigned grid = (unsigned)(want < sms ? (want < 1 ? 1 : want) : sms);
+    launch_kernel(ln_bwd_kernel<1, 16>, dim3(grid), dim3(512), 0, st, dy, s_saved, mean, rstd, gamma, addend, dx, dgamma, dbeta, dxsum, M, H);
+  } else {
+    KIT_NV_DISPATCH(H, (launch_kernel(ln_bwd_kernel<NV, ROW_WARPS>, dim3(reduce_blocks(M)), dim3(256), 0, st, dy, s_saved, mean, rstd, gamma,
+                                      addend, dx, dgamma, dbeta, dxsum, M, H)));
+  }
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
