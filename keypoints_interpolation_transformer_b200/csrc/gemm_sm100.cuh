@@ -281,20 +281,22 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
   const int tiles_mn = groups_m * p.tiles_n;
   const int n_items = tiles_mn * p.splits;
 
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    if (EPI != EPI_GENERIC) tma_prefetch_desc(&tmC);
-    if (EPI == EPI_ADD || EPI == EPI_GELU || EPI == EPI_GELU_BWD) tma_prefetch_desc(&tmAux);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);    // CL = 2: only the leader's is used; it collects the bytes of both CTAs
-      mbar_init(&empty[s], 1);   // one tcgen05.commit arrival (multicast to both CTAs when CL = 2)
+  if (warp == 0) {   // one barrier per lane: a single thread initialising ~45 barriers costs ~1.5k cycles per launch
+    pdl_launch_dependents();   // the next kernel's CTAs may be scheduled as soon as SMs free up
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      if (EPI != EPI_GENERIC) tma_prefetch_desc(&tmC);
+      if (EPI == EPI_ADD || EPI == EPI_GELU || EPI == EPI_GELU_BWD) tma_prefetch_desc(&tmAux);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], EPI_WARPS * CL);   // CL = 2: the peer's epilogue warps arrive on the leader's barrier
+    // full[s]: the producer's arrive.expect_tx (CL = 2: only the leader's is used; it collects the bytes of both CTAs);
+    // empty[s], tmem_full[s]: one tcgen05.commit arrival (multicast to both CTAs when CL = 2);
+    // tmem_empty[s]: every epilogue warp (CL = 2: the peer's warps arrive on the leader's barrier); in_bars: one TMA load
+    constexpr int N_BARS = 2 * STAGES + 4 + 2 * EPI_WARPS;
+    for (int i = lane; i < N_BARS; i += 32) {
+      const bool is_tmem_empty = i >= 2 * STAGES + 2 && i < 2 * STAGES + 4;
+      mbar_init(&full[i], is_tmem_empty ? EPI_WARPS * CL : 1);
     }
-    for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(&in_bars[s], 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -307,8 +309,9 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) mark(1);
-  pdl_grid_sync();   // everything above overlapped the previous kernel; operands / outputs are touched only below
-  if (warp == 0) mark(2);
+  // Everything above overlapped the previous kernel.  Only the threads that touch global memory wait for it to complete
+  // (pdl_wait below: the producer before its first TMA load, the epilogue warps before their first global access), after
+  // the index arithmetic of their first work item.
 
   if (warp == 0) {
     if (lane == 0) {
@@ -323,7 +326,10 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
           const int s = cnt % STAGES;
           const uint32_t ph = (cnt / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          if (cnt == 0) mark(3);
+          if (cnt == 0) {
+            pdl_wait();
+            mark(3);
+          }
           if (rank == 0) mbar_arrive_expect_tx(&full[s], STAGE_BYTES * CL);
           uint8_t* sA = smem + s * STAGE_BYTES;
           uint8_t* sB = sA + A_BYTES;
@@ -415,6 +421,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
         }
       };
       const bool have0 = colg < p.N, have1 = colg + 32 < p.N;   // warp-uniform
+      if (it == 0) pdl_wait();
       // staging tiles of the two 32-column halves
       uint32_t t_sub[2] = {tiles, tiles}, t_aux[2] = {tiles, tiles};
       if (EPI == EPI_GELU) {            // stores in order: aux0 -> rr, out0 -> rr+1, aux1 -> rr+2, out1 -> rr+3 (= rr)
