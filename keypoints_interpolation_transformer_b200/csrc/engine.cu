@@ -370,21 +370,22 @@ static void prof_reset(KitEngine* e) {
 // GEMM through the per-engine plan cache (tensor maps are built once per call site).
 static int eg(KitEngine* e, int mode, const bf16* A, int64_t lda, const bf16* Bm, int64_t ldb, void* C, int64_t ldc, int M,
               int N, int K, const float* bias, const bf16* addend, int64_t ld_add, int out_kind, int act, bf16* aux,
-              int64_t ld_aux) {
+              int64_t ld_aux, float* bias_grad = nullptr, bool* bias_grad_fused = nullptr) {
   std::vector<GemmPlan>& plans = *e->active;
   if (e->cursor >= plans.size()) {
     GemmPlan p;
     int rc = gemm_plan(&p, mode, A, lda, Bm, ldb, C, ldc, M, N, K, bias, addend, ld_add, out_kind, act, aux, ld_aux,
-                       mode == 1 ? 0 : 1);
+                       mode == 1 ? 0 : 1, bias_grad);
     if (rc) return rc;
     plans.push_back(p);
   }
   GemmPlan& p = plans[e->cursor++];
   if (p.p.C != C) {  // caller memory moved (pred): the output tensor map must be rebuilt
     int rc = gemm_plan(&p, mode, A, lda, Bm, ldb, C, ldc, M, N, K, bias, addend, ld_add, out_kind, act, aux, ld_aux,
-                       mode == 1 ? 0 : 1);
+                       mode == 1 ? 0 : 1, bias_grad);
     if (rc) return rc;
   }
+  if (bias_grad_fused != nullptr) *bias_grad_fused = p.p.bias_grad != nullptr;
   e->launches++;
   prof_begin(e, mode == 0 ? KIT_PROF_GEMM_TN : KIT_PROF_GEMM_WGRAD, 2.0 * (double)M * (double)N * (double)K);
   const int rc = gemm_launch(&p, e->st);
@@ -434,9 +435,10 @@ static int linear_dgrad(KitEngine* e, const bf16* dy, int64_t ld_dy, const Linea
 // dW[row0:row0+nrows, :] += dy^T x ; db[row0:...] += colsum(dy)
 static int linear_wgrad(KitEngine* e, const bf16* dy, int64_t ld_dy, const bf16* x, int64_t ldx, const LinearW& w, int row0,
                         int nrows, bool bias_done = false) {
+  bool fused = false;   // db = column sums of dy: from the same GEMM (all-ones MMA) whenever its epilogue kind allows
   KIT_TRY(eg(e, 1, dy, ld_dy, x, ldx, e->grads + w.w + (int64_t)row0 * w.cols, w.cols, nrows, w.cols, (int)e->M, nullptr,
-             nullptr, 0, OUT_F32_ATOMIC, ACT_NONE, nullptr, 0));
-  if (bias_done) return KIT_OK;   // the LayerNorm backward that produced dy already summed its columns
+             nullptr, 0, OUT_F32_ATOMIC, ACT_NONE, nullptr, 0, bias_done ? nullptr : e->grads + w.b + row0, &fused));
+  if (bias_done || fused) return KIT_OK;   // (bias_done: the LayerNorm backward that produced dy already summed its columns)
   e->launches++;
   return colsum(dy, ld_dy, e->grads + w.b + row0, e->M, (int)up8(nrows), e->st);
 }

@@ -67,6 +67,7 @@ static long long* g_trace_buf = nullptr;
   X(128, 0, EPI_STORE) X(128, 0, EPI_ADD) X(128, 0, EPI_GELU) X(128, 0, EPI_GELU_BWD) X(128, 0, EPI_F32) X(128, 0, EPI_GENERIC) \
   X(256, 0, EPI_STORE) X(256, 0, EPI_ADD) X(256, 0, EPI_GELU) X(256, 0, EPI_GELU_BWD) X(256, 0, EPI_F32) X(256, 0, EPI_GENERIC) \
   X(128, 1, EPI_F32) X(128, 1, EPI_GENERIC) X(256, 1, EPI_F32) X(256, 1, EPI_GENERIC)
+#define KIT_GEMM_KERNEL_BG(BN) gemm_tcgen05_kernel<BN, 1, ((BN) == 256 ? 2 : 1), EPI_F32, true>
 
 int gemm_init_attributes() {
   static int status = 1;
@@ -84,6 +85,11 @@ int gemm_init_attributes() {
   }
     KIT_GEMM_FOR_ALL(KIT_SET_ATTR)
 #undef KIT_SET_ATTR
+    if (cudaFuncSetAttribute(KIT_GEMM_KERNEL_BG(128), cudaFuncAttributeMaxDynamicSharedMemorySize, KIT_GEMM_SMEM(128, EPI_F32)) != cudaSuccess ||
+        cudaFuncSetAttribute(KIT_GEMM_KERNEL_BG(256), cudaFuncAttributeMaxDynamicSharedMemorySize, KIT_GEMM_SMEM(256, EPI_F32)) != cudaSuccess) {
+      status = -1;
+      set_error("cudaFuncSetAttribute(max dynamic smem) failed for the bias-gradient weight-gradient kernels");
+    }
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -98,7 +104,7 @@ static bool aligned16(const void* ptr, int64_t ld_elems, size_t esize) {
 
 int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, void* C, int64_t ldc,
               int M, int N, int K, const float* bias, const bf16* addend, int64_t ld_addend, int out_kind, int act,
-              bf16* aux, int64_t ld_aux, int split_k) {
+              bf16* aux, int64_t ld_aux, int split_k, float* bias_grad) {
   KIT_REQUIRE(mode == 0 || mode == 1, "gemm mode must be 0 (TN) or 1 (wgrad)");
   KIT_REQUIRE(M > 0 && N > 0 && K > 0, "gemm dims must be positive (M=%d N=%d K=%d)", M, N, K);
   KIT_REQUIRE(act == ACT_NONE || aux != nullptr, "gelu epilogues need the aux tensor");
@@ -154,6 +160,7 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
     }
   }
   plan->epi = epi;
+  p.bias_grad = (mode == 1 && epi == EPI_F32) ? bias_grad : nullptr;   // else the caller sums the columns of dy itself
   plan->tmC = plan->tmA;
   plan->tmAux = plan->tmA;
   if (epi == EPI_F32) {
@@ -198,6 +205,11 @@ static int launch_one(KernelT kernel, int grid, int threads, int smem, int clust
 }
 
 int gemm_launch(const GemmPlan* plan, cudaStream_t stream) {
+  if (plan->p.bias_grad != nullptr) {
+    if (plan->bn == 128)
+      return launch_one(KIT_GEMM_KERNEL_BG(128), plan->grid, gemm_threads<128>(), KIT_GEMM_SMEM(128, EPI_F32), 1, stream, plan);
+    return launch_one(KIT_GEMM_KERNEL_BG(256), plan->grid, gemm_threads<256>(), KIT_GEMM_SMEM(256, EPI_F32), 2, stream, plan);
+  }
 #define KIT_DISPATCH(BN, MODE, EPI)                                                                                          \
   if (plan->bn == BN && plan->mode == MODE && plan->epi == EPI)                                                              \
     return launch_one(KIT_GEMM_KERNEL(BN, MODE, EPI), plan->grid, gemm_threads<BN>(), KIT_GEMM_SMEM(BN, EPI), (BN) == 256 ? 2 : 1, \

@@ -50,6 +50,7 @@ struct GemmParams {
   int out_kind, act;
   int kb_per_split;  // 64-wide k-blocks per work item
   int tiles_m, tiles_n, splits;
+  float* bias_grad;   // MODE 1, BG kernels: bias_grad[m] += sum_k A[k, m] (column sums of dy), else null
   long long* trace;   // experiments only (KIT_GEMM_TRACE): clock64 marks of CTA 0, see kit_gemm_trace_read
 };
 
@@ -64,7 +65,7 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_MAX_EPI_WARPS = 16;
 constexpr int GEMM_SMEM_LIMIT = 232448;   // 227 KB per CTA
-constexpr int GEMM_SMEM_TAIL = 2048;      // barriers + 1024-byte alignment slack
+constexpr int GEMM_SMEM_TAIL = 3072;      // barriers (1 KB) + all-ones operand tile (1 KB, BG kernels) + 1024-byte alignment slack
 
 template <int BN>
 constexpr int gemm_epi_warps() { return BN / 16; }
@@ -244,7 +245,11 @@ __device__ __forceinline__ void gemm_epilogue_sub(const GemmParams& p, int col0,
   }
 }
 
-template <int BN, int MODE, int CL, int EPI>
+// BG (MODE 1 only): the bias gradient of the same Linear -- the column sums of dy, i.e. the row sums of the A^T operand --
+// comes out of the tensor pipe too: every k-step issues one more MMA of the A tile against an all-ones [16 x 16] B tile
+// into 16 spare accumulator columns (one accumulator stage instead of two: weight-gradient work items are one per CTA
+// pair), and the epilogue of the first n tile adds column 0 of it to bias_grad.  This replaces a separate pass over dy.
+template <int BN, int MODE, int CL, int EPI, bool BG = false>
 __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                          const __grid_constant__ CUtensorMap tmB,
                                                                          const __grid_constant__ CUtensorMap tmC,
@@ -258,6 +263,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
   constexpr int EPI_TILES = gemm_epi_tiles<EPI>();
   static_assert(BN == 128 || BN == 256, "BN must give a power-of-two TMEM allocation <= 512");
   static_assert(STAGES >= 3, "operand ring too shallow");
+  static_assert(!BG || (MODE == 1 && EPI == EPI_F32), "the fused bias gradient exists for weight-gradient GEMMs only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
@@ -267,6 +273,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
   uint64_t* in_bars = tmem_empty + 2;     // [EPI_WARPS][2] epilogue input tiles (addend / GELU' pre-activation)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bars + 2 * GEMM_MAX_EPI_WARPS);
+  uint8_t* ones_tile = reinterpret_cast<uint8_t*>(full) + 1024;   // BG: 1 KB of bf16 1.0 (any layout of all-ones is all-ones)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto mark = [&](int slot) {
@@ -302,6 +309,10 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
   }
   if (warp == 1) {
     if (CL == 1) tmem_alloc<TMEM_COLS>(tmem_slot); else tmem_alloc_cg2<TMEM_COLS>(tmem_slot);
+  }
+  if (BG && warp >= 2 && threadIdx.x < 64 + 64) {   // 64 threads x 16 bytes
+    *reinterpret_cast<uint4*>(ones_tile + (threadIdx.x - 64) * 16) = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async();   // read by the tensor core (async proxy)
   }
   tc_fence_before();
   __syncthreads();
@@ -366,10 +377,11 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
         const int split = item / tiles_mn;
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(kb_total, kb_begin + p.kb_per_split);
-        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        const uint32_t as = BG ? 0 : (it & 1), aph = BG ? (it & 1) : ((it >> 1) & 1);
         mbar_wait(&tmem_empty[as], aph ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
+        const bool first_n = BG && ((item - split * tiles_mn) / groups_m) == 0 && p.bias_grad != nullptr;
         for (int kb = kb_begin; kb < kb_end; ++kb, ++cnt) {
           const int s = cnt % STAGES;
           const uint32_t ph = (cnt / STAGES) & 1;
@@ -390,6 +402,12 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
             }
             if (CL == 1) umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
             else umma_bf16_cg2(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            if (BG && first_n) {   // row sums of A^T: same A tile against all-ones, 16 columns at tmem column BN
+              constexpr uint32_t idesc_ones = make_idesc_bf16(BM * CL, 16, true, true);
+              const uint64_t odesc = make_smem_desc_sw128(smem_u32(ones_tile), 0, 0);
+              if (CL == 1) umma_bf16(tmem_base + BN, adesc, odesc, idesc_ones, (kb > kb_begin || k > 0) ? 1u : 0u);
+              else umma_bf16_cg2(tmem_base + BN, adesc, odesc, idesc_ones, (kb > kb_begin || k > 0) ? 1u : 0u);
+            }
           }
           if (CL == 1) umma_commit(&empty[s]); else umma_commit_cg2(&empty[s], (uint16_t)3);   // slot free in both CTAs
         }
@@ -409,7 +427,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
     for (int item = first_item; item < n_items; item += item_stride, ++it) {
       const int split = item / tiles_mn, rem = item - split * tiles_mn;
       const int n0 = (rem / groups_m) * BN, m0 = ((rem % groups_m) * CL + rank) * BM;
-      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      const uint32_t as = BG ? 0 : (it & 1), aph = BG ? (it & 1) : ((it >> 1) & 1);
       const int row0 = m0 + q * 32;
       const int colg = n0 + cg * 64;
       const uint32_t tmem_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + cg * 64);
@@ -464,6 +482,11 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
           break;
         }
         uint32_t r[32];
+        if (BG && sub == 0 && cg == 0 && n0 == 0 && p.bias_grad != nullptr) {   // column 0 of the all-ones product
+          tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(BN), r);
+          tmem_ld_wait();
+          if (row0 + lane < p.M) atomicAdd(p.bias_grad + row0 + lane, __uint_as_float(r[0]));
+        }
         tmem_ld32(tmem_row + uint32_t(sub * 32), r);
         if (EPI == EPI_ADD || EPI == EPI_GELU_BWD) {
           mbar_wait(&in_bar[sub], in_ph[sub]);
@@ -525,7 +548,7 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint6
 // Builds a plan: tensor maps + grid.  split_k <= 0 lets the planner choose (wgrad only).
 int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, void* C, int64_t ldc,
               int M, int N, int K, const float* bias, const bf16* addend, int64_t ld_addend, int out_kind, int act,
-              bf16* aux, int64_t ld_aux, int split_k);
+              bf16* aux, int64_t ld_aux, int split_k, float* bias_grad = nullptr);
 int gemm_launch(const GemmPlan* plan, cudaStream_t stream);
 int gemm_init_attributes();
 
