@@ -392,17 +392,6 @@ __global__ void dq_convert_kernel(const float* __restrict__ acc, bf16* __restric
 // "masked when key > query"}), computed once per unit, so the inner loops carry no per-element flag logic.
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
-  const uint32_t sz = pred ? 16u : 0u;   // src-size 0: the 16 bytes are zero-filled, the address is not dereferenced
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, bool pred) {
-  const uint32_t sz = pred ? 4u : 0u;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

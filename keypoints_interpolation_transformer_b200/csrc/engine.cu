@@ -7,6 +7,7 @@
 
 #include "attention.cuh"
 #include "gemm_sm100.cuh"
+#include "gemm_wgrad_group.cuh"
 #include "rowops.cuh"
 
 namespace kit {
@@ -216,6 +217,8 @@ struct KitEngine {
   uint8_t* ws = nullptr;
   bool bound = false, weights_fresh = false;
   std::vector<GemmPlan> fwd_plans, bwd_plans;
+  std::vector<WgradGroupPlan> group_plans;   // one per layer of the backward (grouped stream-K weight gradients)
+  size_t group_cursor = 0;
   size_t cursor = 0;
   std::vector<GemmPlan>* active = nullptr;
   int64_t launches = 0;
@@ -240,7 +243,7 @@ struct KitEngine {
   float *st_encn, *st_decn;
   std::vector<EncAct> ea;
   std::vector<DecAct> da;
-  bf16 *g0, *g1, *g2, *g3, *gmem, *gff, *gqkv, *gkv, *g2h;
+  bf16 *g0, *g1, *g1b, *g1c, *g2, *g3, *gmem, *gff, *gqkv, *gqc, *gkv, *g2h;
   float* dq_acc;
 
   int64_t alloc(const std::string& name, int64_t elems, int esize, int64_t ld) {
@@ -298,7 +301,7 @@ static void plan_workspace(KitEngine* e) {
   }
   // backward scratch
   const int64_t gm = e->training ? M : 8;
-  for (const char* n : {"g0", "g1", "g2", "g3", "gmem"}) e->alloc(n, gm * H, 2, H);
+  for (const char* n : {"g0", "g1", "g1b", "g1c", "g2", "g3", "gmem", "gqc"}) e->alloc(n, gm * H, 2, H);
   e->alloc("gff", gm * FF, 2, FF);
   e->alloc("gqkv", gm * 3 * H, 2, 3 * H);
   e->alloc("gkv", gm * 2 * H, 2, 2 * H);
@@ -314,7 +317,7 @@ static void resolve_pointers(KitEngine* e) {
 #define KIT_P(n) e->n = wsptr<bf16>(e, #n)
   KIT_P(xe); KIT_P(xd); KIT_P(ei_raw); KIT_P(ei); KIT_P(si12); KIT_P(sig); KIT_P(x0); KIT_P(ef_raw); KIT_P(ef);
   KIT_P(sf12); KIT_P(sfg); KIT_P(y0); KIT_P(mem); KIT_P(dec_out); KIT_P(sd12); KIT_P(sdg); KIT_P(sd); KIT_P(zf); KIT_P(sf);
-  KIT_P(dp); KIT_P(g0); KIT_P(g1); KIT_P(g2); KIT_P(g3); KIT_P(gmem); KIT_P(gff); KIT_P(gqkv); KIT_P(gkv); KIT_P(g2h);
+  KIT_P(dp); KIT_P(g0); KIT_P(g1); KIT_P(g1b); KIT_P(g1c); KIT_P(gqc); KIT_P(g2); KIT_P(g3); KIT_P(gmem); KIT_P(gff); KIT_P(gqkv); KIT_P(gkv); KIT_P(g2h);
 #undef KIT_P
   e->dq_acc = wsptr<float>(e, "dq_acc");
   e->st_encn = wsptr<float>(e, "st_encn");
@@ -443,6 +446,52 @@ static int linear_wgrad(KitEngine* e, const bf16* dy, int64_t ld_dy, const bf16*
   return colsum(dy, ld_dy, e->grads + w.b + row0, e->M, (int)up8(nrows), e->st);
 }
 
+// A weight gradient whose launch is deferred to the end of its layer's backward (its dy buffer stays untouched until then).
+struct PendingW {
+  const bf16* dy;
+  int64_t ld_dy;
+  const bf16* x;
+  int64_t ldx;
+  const LinearW* w;
+  int row0, nrows;
+  bool bias_done;
+};
+// All weight (and bias) gradients of one layer in one grouped stream-K launch (gemm_wgrad_group.cuh); one by one if a
+// pitch rules the tensor maps out.
+static int flush_wgrads(KitEngine* e, std::vector<PendingW>& pend) {
+  if (pend.empty()) return KIT_OK;
+  WgradProblemDesc d[WG_MAX_PROBLEMS];
+  bool ok = pend.size() <= (size_t)WG_MAX_PROBLEMS;
+  double flops = 0.0;
+  for (size_t i = 0; ok && i < pend.size(); ++i) {
+    const PendingW& q = pend[i];
+    d[i].A = q.dy; d[i].lda = q.ld_dy;
+    d[i].B = q.x; d[i].ldb = q.ldx;
+    d[i].C = e->grads + q.w->w + (int64_t)q.row0 * q.w->cols; d[i].ldc = q.w->cols;
+    d[i].M = q.nrows; d[i].N = q.w->cols;
+    d[i].bias_grad = q.bias_done ? nullptr : e->grads + q.w->b + q.row0;
+    ok = wgrad_group_supported(d[i]);
+    flops += 2.0 * (double)e->M * q.nrows * q.w->cols;
+  }
+  if (!ok) {
+    for (const PendingW& q : pend) KIT_TRY(linear_wgrad(e, q.dy, q.ld_dy, q.x, q.ldx, *q.w, q.row0, q.nrows, q.bias_done));
+    pend.clear();
+    return KIT_OK;
+  }
+  if (e->group_cursor >= e->group_plans.size()) {
+    WgradGroupPlan plan;
+    KIT_TRY(wgrad_group_plan(&plan, d, (int)pend.size(), (int)e->M));
+    e->group_plans.push_back(plan);
+  }
+  const WgradGroupPlan& plan = e->group_plans[e->group_cursor++];
+  e->launches++;
+  prof_begin(e, KIT_PROF_GEMM_WGRAD, flops);
+  const int rc = wgrad_group_launch(&plan, e->st);
+  prof_end(e);
+  pend.clear();
+  return rc;
+}
+
 static int swiglu_fwd(KitEngine* e, const bf16* x, const SwiW& s, bf16* x12, bf16* g, bf16* out) {
   const int H = e->L.cfg.hidden;
   KIT_TRY(linear_fwd(e, x, H, s.fc12, 0, 2 * H, x12, 2 * H, nullptr, 0));
@@ -550,7 +599,9 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
   const int nl = L.cfg.layers, half = nl / 2;
   e->active = &e->bwd_plans;
   e->cursor = 0;
+  e->group_cursor = 0;
   e->launches = 0;
+  std::vector<PendingW> pend;
   int bucket = 0;
   auto done = [&]() {
     if (cb) cb(bucket, user);
@@ -574,34 +625,36 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
     const DecW& w = L.dec[l];
     DecAct& a = e->da[l];
     const bf16* y_in = (l == 0) ? e->y0 : e->da[l - 1].y3;
-    // FFN block
+    // FFN block.  Weight gradients are queued (their dy buffers g1 / gff / g1b / gqc / gkv / g1c / gqkv stay untouched
+    // until the end of the layer) and leave in one grouped launch.
     e->launches++;
     KIT_TRY(ln_bwd(dy, a.s3, a.st3, a.st3 + M, e->params + w.n3.g, nullptr, e->g1, e->grads + w.n3.g, e->grads + w.n3.b, e->grads + w.l2.b, M, H, e->st));
-    KIT_TRY(linear_wgrad(e, e->g1, H, a.hh, FF, w.l2, 0, H, true));
+    pend.push_back({e->g1, H, a.hh, FF, &w.l2, 0, H, true});
     KIT_TRY(linear_dgrad(e, e->g1, H, w.l2, 0, H, e->gff, FF, nullptr, 0, ACT_GELU_BWD, a.z, FF));
-    KIT_TRY(linear_wgrad(e, e->gff, FF, a.y2, H, w.l1, 0, FF));
+    pend.push_back({e->gff, FF, a.y2, H, &w.l1, 0, FF, false});
     KIT_TRY(linear_dgrad(e, e->gff, FF, w.l1, 0, FF, e->g2, H, e->g1, H));  // g2 = d y2
     // cross-attention block
     e->launches++;
-    KIT_TRY(ln_bwd(e->g2, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1, e->grads + w.n2.g, e->grads + w.n2.b, e->grads + w.ca.out.b, M, H, e->st));
-    KIT_TRY(linear_wgrad(e, e->g1, H, a.aoc, H, w.ca.out, 0, H, true));
-    KIT_TRY(linear_dgrad(e, e->g1, H, w.ca.out, 0, H, e->g2, H, nullptr, 0));  // g2 = d aoc
-    KIT_TRY(eattn_bwd(e, a.qc, H, a.kvc, 2 * H, a.kvc + H, 2 * H, a.aoc, H, e->g2, H, a.lsec, e->gqkv, H, e->gkv, 2 * H,
-                      e->gkv + H, 2 * H, nullptr));  // gqkv used as [M,H] dq
-    KIT_TRY(linear_wgrad(e, e->gqkv, H, a.y1, H, w.ca.in, 0, H));
-    KIT_TRY(linear_wgrad(e, e->gkv, 2 * H, e->mem, H, w.ca.in, H, 2 * H));
+    KIT_TRY(ln_bwd(e->g2, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1b, e->grads + w.n2.g, e->grads + w.n2.b, e->grads + w.ca.out.b, M, H, e->st));
+    pend.push_back({e->g1b, H, a.aoc, H, &w.ca.out, 0, H, true});
+    KIT_TRY(linear_dgrad(e, e->g1b, H, w.ca.out, 0, H, e->g2, H, nullptr, 0));  // g2 = d aoc
+    KIT_TRY(eattn_bwd(e, a.qc, H, a.kvc, 2 * H, a.kvc + H, 2 * H, a.aoc, H, e->g2, H, a.lsec, e->gqc, H, e->gkv, 2 * H,
+                      e->gkv + H, 2 * H, nullptr));
+    pend.push_back({e->gqc, H, a.y1, H, &w.ca.in, 0, H, false});
+    pend.push_back({e->gkv, 2 * H, e->mem, H, &w.ca.in, H, 2 * H, false});
     KIT_TRY(linear_dgrad(e, e->gkv, 2 * H, w.ca.in, H, 2 * H, e->gmem, H, mem_grad_started ? e->gmem : nullptr, H));
     mem_grad_started = true;
-    KIT_TRY(linear_dgrad(e, e->gqkv, H, w.ca.in, 0, H, e->g2, H, e->g1, H));  // g2 = d y1
+    KIT_TRY(linear_dgrad(e, e->gqc, H, w.ca.in, 0, H, e->g2, H, e->g1b, H));  // g2 = d y1
     // self-attention block
     e->launches++;
-    KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1, e->grads + w.n1.g, e->grads + w.n1.b, e->grads + w.sa.out.b, M, H, e->st));
-    KIT_TRY(linear_wgrad(e, e->g1, H, a.ao, H, w.sa.out, 0, H, true));
-    KIT_TRY(linear_dgrad(e, e->g1, H, w.sa.out, 0, H, e->g2, H, nullptr, 0));  // g2 = d ao
+    KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1c, e->grads + w.n1.g, e->grads + w.n1.b, e->grads + w.sa.out.b, M, H, e->st));
+    pend.push_back({e->g1c, H, a.ao, H, &w.sa.out, 0, H, true});
+    KIT_TRY(linear_dgrad(e, e->g1c, H, w.sa.out, 0, H, e->g2, H, nullptr, 0));  // g2 = d ao
     KIT_TRY(eattn_bwd(e, a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, e->g2, H, a.lse, e->gqkv, 3 * H,
                       e->gqkv + H, 3 * H, e->gqkv + 2 * H, 3 * H, &e->dec_mask));
-    KIT_TRY(linear_wgrad(e, e->gqkv, 3 * H, y_in, H, w.sa.in, 0, 3 * H));
-    KIT_TRY(linear_dgrad(e, e->gqkv, 3 * H, w.sa.in, 0, 3 * H, e->g0, H, e->g1, H));  // g0 = d y_in
+    pend.push_back({e->gqkv, 3 * H, y_in, H, &w.sa.in, 0, 3 * H, false});
+    KIT_TRY(linear_dgrad(e, e->gqkv, 3 * H, w.sa.in, 0, 3 * H, e->g0, H, e->g1c, H));  // g0 = d y_in
+    KIT_TRY(flush_wgrads(e, pend));
     dy = e->g0;
     if (half > 0 && l == half) done();
   }
@@ -625,18 +678,19 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
     const bf16* x_in = (l == 0) ? e->x0 : e->ea[l - 1].x2;
     e->launches++;
     KIT_TRY(ln_bwd(dx, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1, e->grads + w.n2.g, e->grads + w.n2.b, e->grads + w.l2.b, M, H, e->st));
-    KIT_TRY(linear_wgrad(e, e->g1, H, a.hh, FF, w.l2, 0, H, true));
+    pend.push_back({e->g1, H, a.hh, FF, &w.l2, 0, H, true});
     KIT_TRY(linear_dgrad(e, e->g1, H, w.l2, 0, H, e->gff, FF, nullptr, 0, ACT_GELU_BWD, a.z, FF));
-    KIT_TRY(linear_wgrad(e, e->gff, FF, a.x1, H, w.l1, 0, FF));
+    pend.push_back({e->gff, FF, a.x1, H, &w.l1, 0, FF, false});
     KIT_TRY(linear_dgrad(e, e->gff, FF, w.l1, 0, FF, e->g2, H, e->g1, H));  // g2 = d x1
     e->launches++;
-    KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1, e->grads + w.n1.g, e->grads + w.n1.b, e->grads + w.sa.out.b, M, H, e->st));
-    KIT_TRY(linear_wgrad(e, e->g1, H, a.ao, H, w.sa.out, 0, H, true));
-    KIT_TRY(linear_dgrad(e, e->g1, H, w.sa.out, 0, H, e->g2, H, nullptr, 0));
+    KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1b, e->grads + w.n1.g, e->grads + w.n1.b, e->grads + w.sa.out.b, M, H, e->st));
+    pend.push_back({e->g1b, H, a.ao, H, &w.sa.out, 0, H, true});
+    KIT_TRY(linear_dgrad(e, e->g1b, H, w.sa.out, 0, H, e->g2, H, nullptr, 0));
     KIT_TRY(eattn_bwd(e, a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, e->g2, H, a.lse, e->gqkv, 3 * H,
                       e->gqkv + H, 3 * H, e->gqkv + 2 * H, 3 * H, &e->enc_mask));
-    KIT_TRY(linear_wgrad(e, e->gqkv, 3 * H, x_in, H, w.sa.in, 0, 3 * H));
-    KIT_TRY(linear_dgrad(e, e->gqkv, 3 * H, w.sa.in, 0, 3 * H, e->g0, H, e->g1, H));
+    pend.push_back({e->gqkv, 3 * H, x_in, H, &w.sa.in, 0, 3 * H, false});
+    KIT_TRY(linear_dgrad(e, e->gqkv, 3 * H, w.sa.in, 0, 3 * H, e->g0, H, e->g1b, H));
+    KIT_TRY(flush_wgrads(e, pend));
     dx = e->g0;
     if (half > 0 && l == half) done();
   }
@@ -745,6 +799,7 @@ extern "C" int kit_engine_bind(KitEngine* e, float* params, float* grads, void* 
   resolve_pointers(e);
   e->fwd_plans.clear();
   e->bwd_plans.clear();
+  e->group_plans.clear();
   // upload the weight-refresh tables (synchronous, bind time only)
   std::vector<int> prefix(e->L.wdescs.size() + 1, 0);
   for (size_t i = 0; i < e->L.wdescs.size(); ++i) {

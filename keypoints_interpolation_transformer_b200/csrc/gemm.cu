@@ -1,5 +1,7 @@
 // Host side of the tcgen05 GEMM: TMA descriptor construction, planning and launch.
 #include "gemm_sm100.cuh"
+#define KIT_WGRAD_GROUP_IMPL
+#include "gemm_wgrad_group.cuh"
 
 #include <mutex>
 #include <cstdlib>
@@ -218,6 +220,76 @@ int gemm_launch(const GemmPlan* plan, cudaStream_t stream) {
 #undef KIT_DISPATCH
   set_error("gemm_launch: no kernel for bn=%d mode=%d epi=%d", plan->bn, plan->mode, plan->epi);
   return KIT_ERR_INVALID;
+}
+
+// ---------------------------------------------------------------- grouped stream-K weight gradients
+bool wgrad_group_supported(const WgradProblemDesc& d) {
+  return aligned16(d.A, d.lda, 2) && aligned16(d.B, d.ldb, 2) && aligned16(d.C, d.ldc, 4) && d.M > 0 && d.N > 0;
+}
+
+int wgrad_group_plan(WgradGroupPlan* plan, const WgradProblemDesc* probs, int n, int K) {
+  KIT_REQUIRE(n >= 1 && n <= WG_MAX_PROBLEMS, "wgrad group: 1..%d problems (got %d)", WG_MAX_PROBLEMS, n);
+  KIT_REQUIRE(K > 0, "wgrad group: K must be positive");
+  int rc = gemm_init_attributes();
+  if (rc) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, []() {
+    attr_err = cudaFuncSetAttribute(gemm_wgrad_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+  });
+  KIT_REQUIRE(attr_err == cudaSuccess, "wgrad group: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  WgradGroupParams& p = plan->p;
+  p.n_problems = n;
+  p.kb_total = (K + GEMM_BK - 1) / GEMM_BK;
+  int units = 0;
+  for (int i = 0; i < n; ++i) {
+    const WgradProblemDesc& d = probs[i];
+    KIT_REQUIRE(wgrad_group_supported(d), "wgrad group: problem %d violates the TMA alignment rules", i);
+    WgradProblem& q = p.prob[i];
+    q.M = d.M;
+    q.N = d.N;
+    q.groups_m = (d.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+    q.tiles_n = (d.N + WG_BN - 1) / WG_BN;
+    q.unit_begin = units;
+    q.bias_grad = d.bias_grad;
+    units += q.groups_m * q.tiles_n * p.kb_total;
+    if ((rc = make_tensor_map_2d(&plan->maps.a[i], d.A, (uint64_t)d.M, (uint64_t)K, (uint64_t)d.lda * 2, 64, GEMM_BK))) return rc;
+    if ((rc = make_tensor_map_2d(&plan->maps.b[i], d.B, (uint64_t)d.N, (uint64_t)K, (uint64_t)d.ldb * 2, 64, GEMM_BK))) return rc;
+    if ((rc = make_tensor_map_2d_typed(&plan->maps.c[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.C, (uint64_t)d.N, (uint64_t)d.M,
+                                       (uint64_t)d.ldc * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  for (int i = n; i < WG_MAX_PROBLEMS; ++i) {
+    p.prob[i] = p.prob[0];
+    p.prob[i].unit_begin = units;
+    plan->maps.a[i] = plan->maps.a[0];
+    plan->maps.b[i] = plan->maps.b[0];
+    plan->maps.c[i] = plan->maps.c[0];
+  }
+  p.total_units = units;
+  const int max_clusters = g_num_sms / WG_CL;
+  const int clusters = units < max_clusters ? units : max_clusters;
+  p.units_per_cluster = (units + clusters - 1) / clusters;
+  plan->grid = ((units + p.units_per_cluster - 1) / p.units_per_cluster) * WG_CL;
+  return KIT_OK;
+}
+
+int wgrad_group_launch(const WgradGroupPlan* plan, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan->grid);
+  cfg.blockDim = dim3(gemm_threads<WG_BN>());
+  cfg.dynamicSmemBytes = WG_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = WG_CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  KIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_wgrad_group_kernel, plan->maps, plan->p));
+  return KIT_OK;
 }
 
 }  // namespace kit
