@@ -31,17 +31,18 @@ def timeit(fn, iters=10, flush=None):
     return ts[len(ts) // 2]
 
 
-def main():
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = peaks.get("hbm_gbs", 6650.0)
-    dev = "cuda"
+def measure(shapes=((4096, 256, 71), (256, 64, 71)), peak=None, dev="cuda"):
+    """[{kernel, B, T, K, ms, algorithmic_bytes, GBps, frac_of_measured_hbm}] for the pre-pass and the two loss passes."""
+    if peak is None:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out = []
-    for (B, T, K) in [(4096, 256, 71), (256, 64, 71)]:
+    for (B, T, K) in shapes:
         raw = torch.rand(B, T, K, 2, device=dev)
         rs = np.random.RandomState(0)
         pr = random.Random(0)
@@ -98,7 +99,11 @@ def main():
         by = B * (2 * T * K * 8 + T * 4)
         out.append({"kernel": "loss_kernel (masked eval, fwd only)", "B": B, "T": T, "K": K, "ms": ms, "algorithmic_bytes": by,
                     "GBps": by / ms / 1e6, "frac_of_measured_hbm": by / ms / 1e6 / peak})
-    for o in out:
+    return out
+
+
+def main():
+    for o in measure():
         print(json.dumps(o), flush=True)
 
 
