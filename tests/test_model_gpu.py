@@ -121,10 +121,10 @@ def test_autograd_path_matches_fused_step():
     assert (m.flat_params[:n] - after_torch[:n]).abs().max().item() < 2e-6
 
 
-@pytest.mark.parametrize("Kp,B,T", [(71, 8, 64), (54, 3, 100)])
-def test_default_model_matches_oracle(Kp, B, T):
-    """BASELINE config shape (T=64, K=71, default dims) at a batch the CPU oracle finishes in seconds."""
-    H, L, NH = 256, 6, 8
+@pytest.mark.parametrize("Kp,B,T,H,L,NH", [(71, 8, 64, 256, 6, 8), (54, 3, 100, 256, 6, 8), (71, 1, 512, 512, 8, 8)])
+def test_default_model_matches_oracle(Kp, B, T, H, L, NH):
+    """BASELINE config shapes -- configs[1] (T=64, K=71, default dims), a ragged T, and configs[4] (d_model=512, 8 layers,
+    T=512: multi-tile attention, head dim 64) -- at batches the CPU oracle finishes in seconds."""
     m = _build(2 * Kp, H, L, NH)
     m.train()
     inputs, gt, mask = ko.synthetic_batch(B, T, Kp, seed=42)
@@ -148,7 +148,9 @@ def test_default_model_matches_oracle(Kp, B, T):
         if r > worst[0] and gr.norm().item() > 1e-3 * den ** 0.5:
             worst = (r, n)
     assert (num / den) ** 0.5 < TOL, ((num / den) ** 0.5, worst)
-    assert worst[0] < 0.15, worst        # single small tensors; the aggregate bound above is the contract
+    # single small tensors (the aggregate bound above is the contract): 16 bf16 layers deep with one 512-token sequence the
+    # input-embedding gradient -- the far end of the backward chain -- carries more rounding noise than at the default depth
+    assert worst[0] < (0.15 if L <= 6 else 0.4), worst
     # interpolation-MSE parity on the masked frames (A1_train.py:184-186)
     m.eval()
     ev_loss, _ = train.EvalStep(m)(inputs.to(DEV), gt.to(DEV), mask.to(DEV))
@@ -166,3 +168,26 @@ def test_adam_updates_match_torch_over_steps():
     losses = [step(inputs, gt, mask).item() for _ in range(8)]
     assert losses[-1] < losses[0]          # it trains
     assert all(np.isfinite(losses))
+
+
+def test_long_sequence_inference_matches_oracle_and_is_batch_independent():
+    """BASELINE configs[3] shape (inference, T=256): interpolation loss on the masked frames against the oracle on a few
+    sequences, and -- at a batch the oracle could not run -- the size-independent property that a sequence's prediction
+    does not depend on what else is in the batch."""
+    Kp, H, L, NH, T = 71, 256, 6, 8, 256
+    m = _build(2 * Kp, H, L, NH)
+    m.eval()
+    sd = ko.deterministic_state_dict(2 * Kp, H, L)
+    inputs, gt, mask = ko.synthetic_batch(4, T, Kp, seed=11)
+    ev = train.EvalStep(m)
+    loss_small, pred_small = ev(inputs.to(DEV), gt.to(DEV), mask.to(DEV))
+    pred_small = pred_small.clone()
+    with torch.no_grad():
+        ref_eval, ref_pred = ko.eval_forward_loss(sd, inputs, gt, mask, NH)
+    assert abs(loss_small.item() - ref_eval.item()) < TOL * abs(ref_eval.item())
+    big_in, big_gt, big_mask = ko.synthetic_batch(512, T, Kp, seed=12)
+    big_in[:4], big_gt[:4], big_mask[:4] = inputs, gt, mask
+    _, pred_big = train.EvalStep(m)(big_in.to(DEV), big_gt.to(DEV), big_mask.to(DEV))
+    torch.cuda.synchronize()
+    assert torch.isfinite(pred_big).all()
+    assert _rel(pred_big[:4], pred_small) < 5e-3      # same sequences, different tile / pair assignment
