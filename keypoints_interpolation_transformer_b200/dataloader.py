@@ -127,3 +127,63 @@ class KeypointBatcher:
         order = list(range(self.N))
         self.rng.shuffle(order)
         return iter(order)
+
+
+class DevicePrefetcher:
+    """Feeds ``(inputs, sota, mask)`` tuples of PINNED host tensors (what ``DataLoader(pin_memory=True)`` yields for the
+    reference's dataset, A1_train.py:244) to the device one batch ahead: the host->device copy of batch i+1 runs on a side
+    stream while the train step of batch i computes, so the step never waits for PCIe.  Two device-side slots are re-used;
+    a slot is overwritten only after the step that consumed it has finished (event recorded by ``__next__``).
+
+        for inputs, sota, mask in DevicePrefetcher(loader, device):
+            loss = step(inputs, sota, mask)
+    """
+
+    def __init__(self, iterable, device="cuda"):
+        self.it = iter(iterable)
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]
+        self.ready = [None, None]          # copy finished
+        self.released = [None, None]       # consumer finished with the slot
+        self.cur = 0
+        self.h2d_bytes = 0
+        self._pending = self._issue(0)
+
+    def _issue(self, slot):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            return False
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            if self.released[slot] is not None:
+                self.copy_stream.wait_event(self.released[slot])
+            if self.slots[slot] is None or any(d.shape != h.shape for d, h in zip(self.slots[slot], host)):
+                self.copy_stream.wait_stream(main)
+                self.slots[slot] = tuple(torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host)
+            for d, h in zip(self.slots[slot], host):
+                d.copy_(h, non_blocking=True)
+            self.h2d_bytes = sum(h.numel() * h.element_size() for h in host)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+            self.ready[slot] = ev
+        return True
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if not self._pending:
+            raise StopIteration
+        slot = self.cur
+        main = torch.cuda.current_stream(self.device)
+        # everything enqueued on the main stream so far used the OTHER slot: it may be refilled once that work is done
+        other = slot ^ 1
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.released[other] = ev
+        self._pending = self._issue(other)
+        main.wait_event(self.ready[slot])
+        self.cur = other
+        return self.slots[slot]

@@ -189,3 +189,16 @@ def test_flat_adam_matches_torch_adam():
                                       1.0, K.stream_ptr()))
     torch.cuda.synchronize()
     assert torch.allclose(p.cpu(), ref.detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_device_prefetcher_yields_batches_in_order():
+    """dataloader.DevicePrefetcher: batches arrive on the device unchanged and in order while two slots are recycled."""
+    from keypoints_interpolation_transformer_b200 import dataloader
+    host = [tuple(t.pin_memory() for t in (torch.full((4, 9, 5, 2), float(i)), torch.full((4, 8, 5, 2), float(-i)),
+                                           torch.full((4, 9), float(i % 2)))) for i in range(7)]
+    seen = []
+    for inputs, sota, mask in dataloader.DevicePrefetcher(host, "cuda"):
+        assert inputs.is_cuda and sota.is_cuda and mask.is_cuda
+        seen.append((inputs.sum().item(), sota.sum().item(), mask.sum().item()))   # consumed before the slot is refilled
+    want = [(h[0].sum().item(), h[1].sum().item(), h[2].sum().item()) for h in host]
+    assert seen == want
