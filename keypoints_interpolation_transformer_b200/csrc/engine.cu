@@ -373,22 +373,24 @@ static void prof_reset(KitEngine* e) {
 // GEMM through the per-engine plan cache (tensor maps are built once per call site).
 static int eg(KitEngine* e, int mode, const bf16* A, int64_t lda, const bf16* Bm, int64_t ldb, void* C, int64_t ldc, int M,
               int N, int K, const float* bias, const bf16* addend, int64_t ld_add, int out_kind, int act, bf16* aux,
-              int64_t ld_aux, float* bias_grad = nullptr, bool* bias_grad_fused = nullptr) {
+              int64_t ld_aux, float* bias_grad = nullptr, bool* bias_grad_fused = nullptr, const GemmLN* ln = nullptr,
+              bool* ln_fused = nullptr) {
   std::vector<GemmPlan>& plans = *e->active;
   if (e->cursor >= plans.size()) {
     GemmPlan p;
     int rc = gemm_plan(&p, mode, A, lda, Bm, ldb, C, ldc, M, N, K, bias, addend, ld_add, out_kind, act, aux, ld_aux,
-                       mode == 1 ? 0 : 1, bias_grad);
+                       mode == 1 ? 0 : 1, bias_grad, ln);
     if (rc) return rc;
     plans.push_back(p);
   }
   GemmPlan& p = plans[e->cursor++];
   if (p.p.C != C) {  // caller memory moved (pred): the output tensor map must be rebuilt
     int rc = gemm_plan(&p, mode, A, lda, Bm, ldb, C, ldc, M, N, K, bias, addend, ld_add, out_kind, act, aux, ld_aux,
-                       mode == 1 ? 0 : 1, bias_grad);
+                       mode == 1 ? 0 : 1, bias_grad, ln);
     if (rc) return rc;
   }
   if (bias_grad_fused != nullptr) *bias_grad_fused = p.p.bias_grad != nullptr;
+  if (ln_fused != nullptr) *ln_fused = p.epi == EPI_ADD_LN;
   e->launches++;
   prof_begin(e, mode == 0 ? KIT_PROF_GEMM_TN : KIT_PROF_GEMM_WGRAD, 2.0 * (double)M * (double)N * (double)K);
   const int rc = gemm_launch(&p, e->st);
@@ -427,6 +429,20 @@ static int linear_fwd(KitEngine* e, const bf16* x, int64_t ldx, const LinearW& w
                       const bf16* addend, int64_t ld_add, int act = ACT_NONE, bf16* aux = nullptr, int64_t ld_aux = 0) {
   return eg(e, 0, x, ldx, e->wb + w.wb + (int64_t)row0 * w.ld, w.ld, y, ldy, (int)e->M, nrows, w.cols,
             e->params + w.b + row0, addend, ld_add, OUT_BF16, act, aux, ld_aux);
+}
+// s = x W^T + b + addend ; y = LN(s) (torch/nn/modules/transformer.py:956 post-norm): one GEMM with the LayerNorm in its
+// epilogue when the row fits one tile (H = 256), else GEMM + row kernel
+static int linear_add_ln_fwd(KitEngine* e, const bf16* x, int64_t ldx, const LinearW& w, bf16* s, const bf16* addend, const LNW& n,
+                             bf16* y, float* stats) {
+  const int H = e->L.cfg.hidden;
+  const int64_t M = e->M;
+  GemmLN ln{e->params + n.g, e->params + n.b, stats, stats + M, y, H, 1e-5f};
+  bool fused = false;
+  KIT_TRY(eg(e, 0, x, ldx, e->wb + w.wb, w.ld, s, H, (int)M, H, w.cols, e->params + w.b, addend, H, OUT_BF16, ACT_NONE, nullptr, 0,
+             nullptr, nullptr, &ln, &fused));
+  if (fused) return KIT_OK;
+  e->launches++;
+  return add_ln_fwd(s, nullptr, e->params + n.g, e->params + n.b, nullptr, y, stats, stats + M, M, H, e->st);
 }
 // dx = dy W[row0:row0+nrows, :] (+ addend)   (B operand = rows of W^T restricted to those columns)
 static int linear_dgrad(KitEngine* e, const bf16* dy, int64_t ld_dy, const LinearW& w, int row0, int nrows, bf16* dx,
@@ -545,13 +561,9 @@ static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const f
     EncAct& a = e->ea[l];
     KIT_TRY(linear_fwd(e, x, H, w.sa.in, 0, 3 * H, a.qkv, 3 * H, nullptr, 0));
     KIT_TRY(eattn_fwd(e, a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, a.lse, &e->enc_mask));
-    KIT_TRY(linear_fwd(e, a.ao, H, w.sa.out, 0, H, a.s1, H, x, H));
-    e->launches++;
-    KIT_TRY(add_ln_fwd(a.s1, nullptr, e->params + w.n1.g, e->params + w.n1.b, nullptr, a.x1, a.st1, a.st1 + M, M, H, e->st));
+    KIT_TRY(linear_add_ln_fwd(e, a.ao, H, w.sa.out, a.s1, x, w.n1, a.x1, a.st1));
     KIT_TRY(linear_fwd(e, a.x1, H, w.l1, 0, FF, a.hh, FF, nullptr, 0, ACT_GELU, a.z, FF));
-    KIT_TRY(linear_fwd(e, a.hh, FF, w.l2, 0, H, a.s2, H, a.x1, H));
-    e->launches++;
-    KIT_TRY(add_ln_fwd(a.s2, nullptr, e->params + w.n2.g, e->params + w.n2.b, nullptr, a.x2, a.st2, a.st2 + M, M, H, e->st));
+    KIT_TRY(linear_add_ln_fwd(e, a.hh, FF, w.l2, a.s2, a.x1, w.n2, a.x2, a.st2));
     x = a.x2;
   }
   e->launches++;
@@ -564,19 +576,13 @@ static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const f
     DecAct& a = e->da[l];
     KIT_TRY(linear_fwd(e, y, H, w.sa.in, 0, 3 * H, a.qkv, 3 * H, nullptr, 0));
     KIT_TRY(eattn_fwd(e, a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, a.lse, &e->dec_mask));
-    KIT_TRY(linear_fwd(e, a.ao, H, w.sa.out, 0, H, a.s1, H, y, H));
-    e->launches++;
-    KIT_TRY(add_ln_fwd(a.s1, nullptr, e->params + w.n1.g, e->params + w.n1.b, nullptr, a.y1, a.st1, a.st1 + M, M, H, e->st));
+    KIT_TRY(linear_add_ln_fwd(e, a.ao, H, w.sa.out, a.s1, y, w.n1, a.y1, a.st1));
     KIT_TRY(linear_fwd(e, a.y1, H, w.ca.in, 0, H, a.qc, H, nullptr, 0));
     KIT_TRY(linear_fwd(e, e->mem, H, w.ca.in, H, 2 * H, a.kvc, 2 * H, nullptr, 0));
     KIT_TRY(eattn_fwd(e, a.qc, H, a.kvc, 2 * H, a.kvc + H, 2 * H, a.aoc, H, a.lsec, nullptr));
-    KIT_TRY(linear_fwd(e, a.aoc, H, w.ca.out, 0, H, a.s2, H, a.y1, H));
-    e->launches++;
-    KIT_TRY(add_ln_fwd(a.s2, nullptr, e->params + w.n2.g, e->params + w.n2.b, nullptr, a.y2, a.st2, a.st2 + M, M, H, e->st));
+    KIT_TRY(linear_add_ln_fwd(e, a.aoc, H, w.ca.out, a.s2, a.y1, w.n2, a.y2, a.st2));
     KIT_TRY(linear_fwd(e, a.y2, H, w.l1, 0, FF, a.hh, FF, nullptr, 0, ACT_GELU, a.z, FF));
-    KIT_TRY(linear_fwd(e, a.hh, FF, w.l2, 0, H, a.s3, H, a.y2, H));
-    e->launches++;
-    KIT_TRY(add_ln_fwd(a.s3, nullptr, e->params + w.n3.g, e->params + w.n3.b, nullptr, a.y3, a.st3, a.st3 + M, M, H, e->st));
+    KIT_TRY(linear_add_ln_fwd(e, a.hh, FF, w.l2, a.s3, a.y2, w.n3, a.y3, a.st3));
     y = a.y3;
   }
   e->launches++;

@@ -68,6 +68,7 @@ static long long* g_trace_buf = nullptr;
 #define KIT_GEMM_FOR_ALL(X)                                                                                     \
   X(128, 0, EPI_STORE) X(128, 0, EPI_ADD) X(128, 0, EPI_GELU) X(128, 0, EPI_GELU_BWD) X(128, 0, EPI_F32) X(128, 0, EPI_GENERIC) \
   X(256, 0, EPI_STORE) X(256, 0, EPI_ADD) X(256, 0, EPI_GELU) X(256, 0, EPI_GELU_BWD) X(256, 0, EPI_F32) X(256, 0, EPI_GENERIC) \
+  X(256, 0, EPI_ADD_LN)                                                                                          \
   X(128, 1, EPI_F32) X(128, 1, EPI_GENERIC) X(256, 1, EPI_F32) X(256, 1, EPI_GENERIC)
 #define KIT_GEMM_KERNEL_BG(BN) gemm_tcgen05_kernel<BN, 1, ((BN) == 256 ? 2 : 1), EPI_F32, true>
 
@@ -106,7 +107,7 @@ static bool aligned16(const void* ptr, int64_t ld_elems, size_t esize) {
 
 int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, void* C, int64_t ldc,
               int M, int N, int K, const float* bias, const bf16* addend, int64_t ld_addend, int out_kind, int act,
-              bf16* aux, int64_t ld_aux, int split_k, float* bias_grad) {
+              bf16* aux, int64_t ld_aux, int split_k, float* bias_grad, const GemmLN* ln) {
   KIT_REQUIRE(mode == 0 || mode == 1, "gemm mode must be 0 (TN) or 1 (wgrad)");
   KIT_REQUIRE(M > 0 && N > 0 && K > 0, "gemm dims must be positive (M=%d N=%d K=%d)", M, N, K);
   KIT_REQUIRE(act == ACT_NONE || aux != nullptr, "gelu epilogues need the aux tensor");
@@ -156,21 +157,38 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
       if (act == ACT_NONE && addend == nullptr) epi = EPI_F32;
     } else if (mode == 0) {
       if (act == ACT_NONE && addend == nullptr) epi = EPI_STORE;
-      else if (act == ACT_NONE && aligned16(addend, ld_addend, 2)) epi = EPI_ADD;
+      else if (act == ACT_NONE && aligned16(addend, ld_addend, 2)) {
+        epi = EPI_ADD;
+        // LayerNorm of the full row in the same epilogue: one 256-wide tile per row, every pointer TMA / float4 friendly
+        if (ln != nullptr && N == 256 && bn == 256 && aligned16(ln->y, ln->ldy, 2) && aligned16(ln->gamma, 0, 4) &&
+            aligned16(ln->beta, 0, 4) && (bias == nullptr || aligned16(bias, 0, 4)))
+          epi = EPI_ADD_LN;
+      }
       else if (act == ACT_GELU && addend == nullptr && aligned16(aux, ld_aux, 2)) epi = EPI_GELU;
       else if (act == ACT_GELU_BWD && addend == nullptr && aligned16(aux, ld_aux, 2)) epi = EPI_GELU_BWD;
     }
   }
   plan->epi = epi;
   p.bias_grad = (mode == 1 && epi == EPI_F32) ? bias_grad : nullptr;   // else the caller sums the columns of dy itself
+  p.ln_gamma = p.ln_beta = nullptr;
+  p.ln_mean = p.ln_rstd = nullptr;
+  p.ln_eps = 0.f;
+  plan->tmD = plan->tmA;
+  if (epi == EPI_ADD_LN) {
+    p.ln_gamma = ln->gamma; p.ln_beta = ln->beta; p.ln_mean = ln->mean; p.ln_rstd = ln->rstd; p.ln_eps = ln->eps;
+  }
   plan->tmC = plan->tmA;
   plan->tmAux = plan->tmA;
   if (epi == EPI_F32) {
     if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   } else if (epi != EPI_GENERIC) {
     if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-    const bf16* side = (epi == EPI_ADD) ? addend : aux;
-    const int64_t side_ld = (epi == EPI_ADD) ? ld_addend : ld_aux;
+    const bool add_kind = epi == EPI_ADD || epi == EPI_ADD_LN;
+    const bf16* side = add_kind ? addend : aux;
+    const int64_t side_ld = add_kind ? ld_addend : ld_aux;
+    if (epi == EPI_ADD_LN) {
+      if ((rc = make_tensor_map_2d_typed(&plan->tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, ln->y, (uint64_t)N, (uint64_t)M, (uint64_t)ln->ldy * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    }
     if (epi != EPI_STORE) {
       if ((rc = make_tensor_map_2d_typed(&plan->tmAux, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, side, (uint64_t)N, (uint64_t)M, (uint64_t)side_ld * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     }
@@ -202,7 +220,7 @@ static int launch_one(KernelT kernel, int grid, int threads, int smem, int clust
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  KIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->p));
+  KIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, plan->tmA, plan->tmB, plan->tmC, plan->tmAux, plan->tmD, plan->p));
   return KIT_OK;
 }
 

@@ -35,7 +35,9 @@ enum {
   EPI_GELU_BWD = 3,  // bf16 C = acc * gelu'(aux)                  (aux tile by TMA, result written in place)
   EPI_F32 = 4,       // fp32 C = acc (+ bias): TMA store or TMA reduce-add (split-K weight gradients)
   EPI_GENERIC = 5,   // any combination through direct global accesses (pitches / extents a tensor map cannot describe)
-  EPI_KINDS = 6
+  EPI_ADD_LN = 6,    // EPI_ADD + LayerNorm of the sum over the full row (N = BN = 256): s = acc + bias + addend -> C (bf16),
+                     // y = LN(s) * gamma + beta -> D (bf16), mean / rstd of the bf16-rounded s (what the backward reads)
+  EPI_KINDS = 7
 };
 
 struct GemmParams {
@@ -50,12 +52,17 @@ struct GemmParams {
   int out_kind, act;
   int kb_per_split;  // 64-wide k-blocks per work item
   int tiles_m, tiles_n, splits;
+  const float* ln_gamma;   // EPI_ADD_LN: LayerNorm weight / bias [N], per-row statistics out [M]
+  const float* ln_beta;
+  float* ln_mean;
+  float* ln_rstd;
+  float ln_eps;
   float* bias_grad;   // MODE 1, BG kernels: bias_grad[m] += sum_k A[k, m] (column sums of dy), else null
   long long* trace;   // experiments only (KIT_GEMM_TRACE): clock64 marks of CTA 0, see kit_gemm_trace_read
 };
 
 struct GemmPlan {
-  CUtensorMap tmA, tmB, tmC, tmAux;
+  CUtensorMap tmA, tmB, tmC, tmAux, tmD;
   GemmParams p;
   int mode, bn, epi;
   int grid;
@@ -66,6 +73,7 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_MAX_EPI_WARPS = 16;
 constexpr int GEMM_SMEM_LIMIT = 232448;   // 227 KB per CTA
 constexpr int GEMM_SMEM_TAIL = 3072;      // barriers (1 KB) + all-ones operand tile (1 KB, BG kernels) + 1024-byte alignment slack
+constexpr int GEMM_LN_STATS = 4096;       // EPI_ADD_LN: [4 column groups][128 rows] float2 partial row statistics
 
 template <int BN>
 constexpr int gemm_epi_warps() { return BN / 16; }
@@ -74,17 +82,19 @@ constexpr int gemm_threads() { return 64 + 32 * gemm_epi_warps<BN>(); }
 // 2 KB staging tiles ([32 rows x 64 B] bf16, or half of a [32 x 128 B] fp32 tile) per epilogue warp
 template <int EPI>
 constexpr int gemm_epi_tiles() { return EPI == EPI_GENERIC ? 0 : (EPI == EPI_GELU || EPI == EPI_GELU_BWD) ? 3 : 2; }
+template <int EPI>
+constexpr int gemm_tail_bytes() { return GEMM_SMEM_TAIL + (EPI == EPI_ADD_LN ? GEMM_LN_STATS : 0); }
 template <int BN, int CL>
 constexpr int gemm_stage_bytes() { return GEMM_BM * GEMM_BK * 2 + (BN / CL) * GEMM_BK * 2; }
 template <int BN, int CL, int EPI>
 constexpr int gemm_stages() {
-  const int avail = GEMM_SMEM_LIMIT - GEMM_SMEM_TAIL - gemm_epi_warps<BN>() * gemm_epi_tiles<EPI>() * 2048;
+  const int avail = GEMM_SMEM_LIMIT - gemm_tail_bytes<EPI>() - gemm_epi_warps<BN>() * gemm_epi_tiles<EPI>() * 2048;
   const int s = avail / gemm_stage_bytes<BN, CL>();
   return s > 6 ? 6 : s;
 }
 template <int BN, int CL, int EPI>
 constexpr int gemm_smem_bytes() {
-  return gemm_stages<BN, CL, EPI>() * gemm_stage_bytes<BN, CL>() + gemm_epi_warps<BN>() * gemm_epi_tiles<EPI>() * 2048 + GEMM_SMEM_TAIL;
+  return gemm_stages<BN, CL, EPI>() * gemm_stage_bytes<BN, CL>() + gemm_epi_warps<BN>() * gemm_epi_tiles<EPI>() * 2048 + gemm_tail_bytes<EPI>();
 }
 
 // ---------------------------------------------------------------- shared-space accesses / TMA by 32-bit shared address
@@ -254,6 +264,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
                                                                          const __grid_constant__ CUtensorMap tmB,
                                                                          const __grid_constant__ CUtensorMap tmC,
                                                                          const __grid_constant__ CUtensorMap tmAux,
+                                                                         const __grid_constant__ CUtensorMap tmD,
                                                                          const GemmParams p) {
   constexpr int BM = GEMM_BM, BK = GEMM_BK;
   constexpr int STAGES = gemm_stages<BN, CL, EPI>();
@@ -274,6 +285,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
   uint64_t* in_bars = tmem_empty + 2;     // [EPI_WARPS][2] epilogue input tiles (addend / GELU' pre-activation)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bars + 2 * GEMM_MAX_EPI_WARPS);
   uint8_t* ones_tile = reinterpret_cast<uint8_t*>(full) + 1024;   // BG: 1 KB of bf16 1.0 (any layout of all-ones is all-ones)
+  float2* ln_stats = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(full) + 2048);   // EPI_ADD_LN: [4][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto mark = [&](int slot) {
@@ -294,7 +306,8 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
       if (EPI != EPI_GENERIC) tma_prefetch_desc(&tmC);
-      if (EPI == EPI_ADD || EPI == EPI_GELU || EPI == EPI_GELU_BWD) tma_prefetch_desc(&tmAux);
+      if (EPI == EPI_ADD || EPI == EPI_GELU || EPI == EPI_GELU_BWD || EPI == EPI_ADD_LN) tma_prefetch_desc(&tmAux);
+      if (EPI == EPI_ADD_LN) tma_prefetch_desc(&tmD);
     }
     // full[s]: the producer's arrive.expect_tx (CL = 2: only the leader's is used; it collects the bytes of both CTAs);
     // empty[s], tmem_full[s]: one tcgen05.commit arrival (multicast to both CTAs when CL = 2);
@@ -450,17 +463,17 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
         t_sub[0] = tiles + (rr % 3) * 2048;
         t_sub[1] = tiles + ((rr + 1) % 3) * 2048;
         rr += 2;
-      } else if (EPI == EPI_STORE || EPI == EPI_ADD) {
+      } else if (EPI == EPI_STORE || EPI == EPI_ADD || EPI == EPI_ADD_LN) {
         t_sub[1] = tiles + 2048;
       }
       if (EPI != EPI_GENERIC && have0 && p.bias != nullptr && lane < 2 && colg + 32 * lane < p.N) prefetch_l1(p.bias + colg + 32 * lane);
-      if (EPI == EPI_ADD || EPI == EPI_GELU_BWD) {   // input tiles land while the MMAs of this tile are still running
+      if (EPI == EPI_ADD || EPI == EPI_GELU_BWD || EPI == EPI_ADD_LN) {   // input tiles land while the MMAs of this tile are still running
         if (lane == 0 && have0) {
           tma_store_wait_read_n<1>();   // the tile(s) below were last read by stores that are at least 2 groups old
           mbar_arrive_expect_tx(&in_bar[0], 2048);
           tma_load_2d_a(t_sub[0], &tmAux, &in_bar[0], colg, row0);
           if (have1) {
-            if (EPI == EPI_ADD) tma_store_wait_read_n<0>();   // two tiles only: tile 1 carried the most recent store
+            if (EPI == EPI_ADD || EPI == EPI_ADD_LN) tma_store_wait_read_n<0>();   // two tiles only: tile 1 carried the most recent store
             mbar_arrive_expect_tx(&in_bar[1], 2048);
             tma_load_2d_a(t_sub[1], &tmAux, &in_bar[1], colg + 32, row0);
           }
@@ -472,6 +485,106 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
       tc_fence_after();
       if (!have0) {   // nothing to write: only keep the TMEM protocol alive
         release_tmem();
+        continue;
+      }
+      if (EPI == EPI_ADD_LN) {   // N = BN = 256: the four warps with this warp's TMEM quadrant hold complete rows between them
+        uint32_t sreg[2][16];   // the bf16-rounded sum, two columns per register
+        float rsum = 0.f;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          uint32_t r[32];
+          tmem_ld32(tmem_row + uint32_t(sub * 32), r);
+          mbar_wait(&in_bar[sub], in_ph[sub]);
+          in_ph[sub] ^= 1;
+          tmem_ld_wait();
+          if (sub == 1) release_tmem();
+          const int col0 = colg + sub * 32;
+          const uint32_t row64 = t_sub[sub] + lane * 64, sw64 = (lane >> 1) & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[8 * i + u]);
+            if (p.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * i));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * i + 4));
+              add_pair(v[0], v[1], b0.x, b0.y); add_pair(v[2], v[3], b0.z, b0.w);
+              add_pair(v[4], v[5], b1.x, b1.y); add_pair(v[6], v[7], b1.z, b1.w);
+            }
+            const uint32_t off = (i ^ sw64) << 4;
+            const uint4 in = lds128(row64 + off);
+            const float2 a = unpack_bf16(in.x), b = unpack_bf16(in.y), c = unpack_bf16(in.z), d = unpack_bf16(in.w);
+            add_pair(v[0], v[1], a.x, a.y); add_pair(v[2], v[3], b.x, b.y);
+            add_pair(v[4], v[5], c.x, c.y); add_pair(v[6], v[7], d.x, d.y);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t pk = pack_bf16(v[2 * u], v[2 * u + 1]);
+              sreg[sub][4 * i + u] = pk;
+              const float2 f = unpack_bf16(pk);   // statistics of the values the backward will read
+              rsum += f.x + f.y;
+            }
+            sts128(row64 + off, sreg[sub][4 * i], sreg[sub][4 * i + 1], sreg[sub][4 * i + 2], sreg[sub][4 * i + 3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d_a(&tmC, t_sub[sub], col0, row0);
+            tma_store_commit();
+          }
+        }
+        // row statistics across the four column groups (two-pass, like add_ln_fwd_kernel): named barrier 1 + q, 128 threads
+        const int rl = q * 32 + lane;
+        ln_stats[cg * 128 + rl].x = rsum;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+        const float mean = (ln_stats[rl].x + ln_stats[128 + rl].x + ln_stats[256 + rl].x + ln_stats[384 + rl].x) * (1.f / 256.f);
+        float rsq = 0.f;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const float2 f = unpack_bf16(sreg[sub][u]);
+            const float dx = f.x - mean, dy = f.y - mean;
+            rsq = fmaf(dx, dx, fmaf(dy, dy, rsq));
+          }
+        ln_stats[cg * 128 + rl].y = rsq;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+        const float var = (ln_stats[rl].y + ln_stats[128 + rl].y + ln_stats[256 + rl].y + ln_stats[384 + rl].y) * (1.f / 256.f);
+        const float rstd = rsqrtf(var + p.ln_eps);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");   // everyone has read the partials: the slots may be reused
+        if (cg == 0 && row0 + lane < p.M) {
+          p.ln_mean[row0 + lane] = mean;
+          p.ln_rstd[row0 + lane] = rstd;
+        }
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const int col0 = colg + sub * 32;
+          const uint32_t row64 = t_sub[sub] + lane * 64, sw64 = (lane >> 1) & 3;
+          if (lane == 0) tma_store_wait_read_n<1>();   // the store of s from this tile has read it
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 f = unpack_bf16(sreg[sub][4 * i + u]);
+              v[2 * u] = (f.x - mean) * rstd;
+              v[2 * u + 1] = (f.y - mean) * rstd;
+            }
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + 8 * i));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + 8 * i + 4));
+            const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col0 + 8 * i));
+            const float4 e1 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col0 + 8 * i + 4));
+            v[0] = fmaf(v[0], g0.x, e0.x); v[1] = fmaf(v[1], g0.y, e0.y); v[2] = fmaf(v[2], g0.z, e0.z); v[3] = fmaf(v[3], g0.w, e0.w);
+            v[4] = fmaf(v[4], g1.x, e1.x); v[5] = fmaf(v[5], g1.y, e1.y); v[6] = fmaf(v[6], g1.z, e1.z); v[7] = fmaf(v[7], g1.w, e1.w);
+            sts128(row64 + ((i ^ sw64) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d_a(&tmD, t_sub[sub], col0, row0);
+            tma_store_commit();
+          }
+        }
         continue;
       }
 #pragma unroll 1
@@ -546,9 +659,19 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
 int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_pitch_bytes,
                        uint32_t box_inner, uint32_t box_outer);
 // Builds a plan: tensor maps + grid.  split_k <= 0 lets the planner choose (wgrad only).
+// Optional LayerNorm behind a +residual GEMM (EPI_ADD_LN): y = LN(C) * gamma + beta, statistics of the bf16-rounded C.
+struct GemmLN {
+  const float* gamma;
+  const float* beta;
+  float* mean;
+  float* rstd;
+  bf16* y;
+  int64_t ldy;
+  float eps;
+};
 int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, void* C, int64_t ldc,
               int M, int N, int K, const float* bias, const bf16* addend, int64_t ld_addend, int out_kind, int act,
-              bf16* aux, int64_t ld_aux, int split_k, float* bias_grad = nullptr);
+              bf16* aux, int64_t ld_aux, int split_k, float* bias_grad = nullptr, const GemmLN* ln = nullptr);
 int gemm_launch(const GemmPlan* plan, cudaStream_t stream);
 int gemm_init_attributes();
 
