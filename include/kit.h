@@ -188,6 +188,11 @@ int kit_get_mask(const float* frame_mask, int32_t size, int32_t matrix_type, flo
  * no amsgrad).  step is 1-based.  grad_scale multiplies the gradient first (1/world for DP). */
 int kit_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream);
+/* Same update with the step count and the learning rate on the device, so that the step can be captured in a CUDA graph.
+ * state: 16 bytes, 16-byte aligned: {int32 completed_steps; float lr; float step_size; float inv_sqrt_bc2} -- the host
+ * writes completed_steps (checkpoint restore) and lr (A1_train.py:42-54); the call advances completed_steps by one. */
+int kit_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, void* state,
+                      float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Building blocks exposed for unit tests (tests/ call these through the same ABI)

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "kit_loss_fwd_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P]),
     "kit_get_mask": (C.c_int, [_P, _I32, _I32, _P, _P]),
     "kit_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P]),
+    "kit_adam_step_dev": (C.c_int, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _P]),
     "kit_gemm_bf16": (C.c_int, [_I32, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P, _I64, _I32, _I32, _P,
                                 _I64, _I32, _P]),
     "kit_attention_fwd": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I32, _I32, _I32, _I32, _I32,

@@ -7,8 +7,15 @@ from . import _lib as K
 
 
 class FlatAdam:
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    """``capturable=True`` keeps the step count and the learning rate in a 16-byte device record (kit_adam_step_dev) so
+    that ``train.TrainStep(use_graph=True)`` can replay the whole step as one CUDA graph; ``param_groups[0]['lr']`` is
+    still honoured (copied to the device when it changes)."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
         self.model = model
+        self.capturable = capturable
+        self._dev_state = None
+        self._dev_lr = None
         self.param_groups = [{"lr": lr, "betas": betas, "eps": eps, "params": list(model.parameters())}]
         self.step_count = 0
         self.exp_avg = None
@@ -27,12 +34,38 @@ class FlatAdam:
         g = self.model.ensure_flat_grads()
         g.zero_()
 
+    def _device_state(self):
+        """[completed_steps:int32, lr, step_size, inv_sqrt_bc2] on the device; lr re-uploaded when the host value changed."""
+        dev = self.model.flat_params.device
+        if self._dev_state is None or self._dev_state.device != dev:
+            self._dev_state = torch.zeros(4, dtype=torch.float32, device=dev)
+            self._dev_state.view(torch.int32)[0] = self.step_count
+            self._dev_lr = None
+        lr = float(self.param_groups[0]["lr"])
+        if self._dev_lr != lr:
+            self._dev_state[1] = lr
+            self._dev_lr = lr
+        return self._dev_state
+
+    def sync_host_values(self):
+        """Push lr (and nothing else) to the device record; call before replaying a captured step."""
+        if self.capturable:
+            self._device_state()
+
     @torch.no_grad()
     def step(self):
         n = self._state()
         g = self.model.ensure_flat_grads()
         grp = self.param_groups[0]
+        st = self._device_state() if self.capturable else None   # (created from the count BEFORE this step)
         self.step_count += 1
+        if self.capturable:
+            K.check(K.lib().kit_adam_step_dev(K.ptr(self.model.flat_params), K.ptr(g), K.ptr(self.exp_avg),
+                                              K.ptr(self.exp_avg_sq), n, K.ptr(st), float(grp["betas"][0]),
+                                              float(grp["betas"][1]), float(grp["eps"]), float(self.grad_scale),
+                                              K.stream_ptr()))
+            self.model.mark_dirty()
+            return
         K.check(K.lib().kit_adam_step(K.ptr(self.model.flat_params), K.ptr(g), K.ptr(self.exp_avg),
                                       K.ptr(self.exp_avg_sq), n, float(grp["lr"]), float(grp["betas"][0]),
                                       float(grp["betas"][1]), float(grp["eps"]), self.step_count,
@@ -47,6 +80,8 @@ class FlatAdam:
     def load_state_dict(self, sd):
         self._state()
         self.step_count = int(sd["step"])
+        if self._dev_state is not None:
+            self._dev_state.view(torch.int32)[0] = self.step_count
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.param_groups[0].update(sd["param_groups"][0])

@@ -25,9 +25,14 @@ class TrainStep:
     criterion: "mse" (A1_train.py:254) or "euclid" (A4_train_with_pretrained.py:259).
     zero_masked: A4_train_with_pretrained.py:107-108.  reducer: parallel.BucketReducer or None."""
 
-    def __init__(self, model, optimizer=None, criterion="mse", zero_masked=False, reducer=None, lr=5e-6):
+    def __init__(self, model, optimizer=None, criterion="mse", zero_masked=False, reducer=None, lr=5e-6, use_graph=False):
         self.model = model
-        self.optimizer = optimizer if optimizer is not None else FlatAdam(model, lr=lr)
+        self.use_graph = use_graph and reducer is None
+        self.optimizer = optimizer if optimizer is not None else FlatAdam(model, lr=lr, capturable=self.use_graph)
+        if self.use_graph and not getattr(self.optimizer, "capturable", False):
+            raise ValueError("use_graph=True needs FlatAdam(capturable=True): the step count must live on the device")
+        self._graphs = {}        # (input pointers, shape) -> (CUDAGraph, static loss)
+        self._eager_calls = 0
         self.kind = {"mse": K.LOSS_MSE, "euclid": K.LOSS_EUCLID}[criterion]
         self.zero_masked = zero_masked
         self.reducer = reducer
@@ -60,11 +65,36 @@ class TrainStep:
         self.last_launches = eng.fwd_launches + eng.bwd_launches + 3
         return loss
 
-    def __call__(self, inputs, sota, mask):
+    def _eager(self, inputs, sota, mask):
         loss = self.forward_backward(inputs, sota, mask)
         self.optimizer.step()                                    # A1_train.py:135
         self.last_launches += 2                                  # adam + weight refresh at next forward
         return loss
+
+    def __call__(self, inputs, sota, mask):
+        """use_graph: the whole step (weight refresh, forward, loss, zero grads, backward, Adam -- ~280 kernel launches
+        with their programmatic-dependency edges) is captured once per distinct set of input buffers (e.g. the two slots of
+        ``dataloader.DevicePrefetcher``) and replayed; the returned loss is the graph's static 0-dim tensor."""
+        if not self.use_graph:
+            return self._eager(inputs, sota, mask)
+        key = (inputs.data_ptr(), sota.data_ptr(), mask.data_ptr(), tuple(inputs.shape))
+        entry = self._graphs.get(key)
+        if entry is None:
+            if self._eager_calls < 2 or len(self._graphs) >= 8:   # plans / attributes are set up by eager steps first
+                self._eager_calls += 1
+                return self._eager(inputs, sota, mask)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            steps_before = self.optimizer.step_count
+            with torch.cuda.graph(graph):
+                loss = self._eager(inputs, sota, mask)
+            self.optimizer.step_count = steps_before              # capture enqueues nothing
+            entry = (graph, loss, (inputs, sota, mask))           # keep the buffers alive
+            self._graphs[key] = entry
+        self.optimizer.sync_host_values()
+        entry[0].replay()
+        self.optimizer.step_count += 1
+        return entry[1]
 
 
 class EvalStep:

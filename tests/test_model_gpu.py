@@ -191,3 +191,29 @@ def test_long_sequence_inference_matches_oracle_and_is_batch_independent():
     torch.cuda.synchronize()
     assert torch.isfinite(pred_big).all()
     assert _rel(pred_big[:4], pred_small) < 5e-3      # same sequences, different tile / pair assignment
+
+
+def test_graph_replayed_step_matches_eager_step():
+    """train.TrainStep(use_graph=True): the captured step (device-side Adam step count / lr) updates the parameters
+    exactly like the eager step, honours a learning-rate change between replays, and works across two input slots."""
+    Kp, H, L, NH, B, T = 54, 64, 2, 4, 4, 16
+    batches = [tuple(t.to(DEV) for t in ko.synthetic_batch(B, T, Kp, seed=20 + i)) for i in range(2)]
+    results = []
+    for use_graph in (False, True):
+        m = _build(2 * Kp, H, L, NH)
+        m.train()
+        opt = optim.FlatAdam(m, lr=1e-3, capturable=use_graph)
+        step = train.TrainStep(m, opt, criterion="mse", use_graph=use_graph)
+        losses = []
+        for i in range(9):
+            if i == 6:
+                opt.param_groups[0]["lr"] = 3e-4
+            losses.append(step(*batches[i % 2]).item())
+        torch.cuda.synchronize()
+        if use_graph:
+            assert len(step._graphs) == 2 and opt.step_count == 9
+            assert int(opt._dev_state.view(torch.int32)[0].item()) == 9
+        results.append((losses, m.flat_params[:m.layout.trainable].clone()))
+    (l0, p0), (l1, p1) = results
+    assert np.allclose(l0, l1, rtol=2e-3, atol=1e-6), (l0, l1)
+    assert _rel(p1, p0) < 1e-4        # same kernels, same order; atomics in the weight gradients reorder fp32 sums
