@@ -27,6 +27,7 @@ class TrainStep:
 
     def __init__(self, model, optimizer=None, criterion="mse", zero_masked=False, reducer=None, lr=5e-6, use_graph=False):
         self.model = model
+        # data parallel: kernel by kernel (a graph holding NCCL collectives hung process-group teardown on 2 x B200)
         self.use_graph = use_graph and reducer is None
         self.optimizer = optimizer if optimizer is not None else FlatAdam(model, lr=lr, capturable=self.use_graph)
         if self.use_graph and not getattr(self.optimizer, "capturable", False):
