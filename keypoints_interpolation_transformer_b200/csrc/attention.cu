@@ -545,6 +545,153 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_tile_kernel(const bf16* _
   cp_async_wait<0>();
 }
 
+// Longer sequences: the same persistent double-buffered scheme over (batch, head, 64-query tile) units, each streaming its
+// 64-key tiles through an online softmax (flash-style); one "step" = one (unit, key tile), and step s+1 is in flight while
+// step s computes, across unit boundaries too.
+template <int D>
+__global__ void __launch_bounds__(AT_THREADS) attn_fwd_stream_kernel(const bf16* __restrict__ q, int64_t ldq,
+                                                                     const bf16* __restrict__ k, int64_t ldk,
+                                                                     const bf16* __restrict__ v, int64_t ldv,
+                                                                     bf16* __restrict__ out, int64_t ldo,
+                                                                     float* __restrict__ lse, int NH, int Sq, int Sk,
+                                                                     int q_tiles, int k_tiles, int units, float scale,
+                                                                     MaskDev mask) {
+  pdl_grid_sync();
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  FwdTile<D>* tiles = reinterpret_cast<FwdTile<D>*>(smem_raw);
+  constexpr int KS = D / 16, NT = D / 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int q0 = warp * 16;
+  const float sl2 = scale * LOG2E;
+  // step -> (unit, key tile); unit -> (batch*head, query tile)
+  auto issue = [&](int unit, int kt, FwdTile<D>& s) {
+    const int bh = unit / q_tiles, qt = unit - bh * q_tiles;
+    const int b = bh / NH, h = bh % NH;
+    const int qrow = qt * AT, krow = kt * AT;
+    async_tile<D>(s.Q, q + ((int64_t)b * Sq + qrow) * ldq + h * D, ldq, Sq - qrow);
+    async_tile<D>(s.K, k + ((int64_t)b * Sk + krow) * ldk + h * D, ldk, Sk - krow);
+    async_tile<D>(s.V, v + ((int64_t)b * Sk + krow) * ldv + h * D, ldv, Sk - krow);
+    if (threadIdx.x < AT) s.kinfo[threadIdx.x] = key_info(mask, b, krow + threadIdx.x, Sk);
+  };
+  int unit = blockIdx.x, kt = 0, buf = 0;
+  if (unit < units) issue(unit, 0, tiles[0]);
+  cp_async_commit();
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float o[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  while (unit < units) {
+    FwdTile<D>& s = tiles[buf];
+    // next step
+    int nunit = unit, nkt = kt + 1;
+    if (nkt == k_tiles) {
+      nkt = 0;
+      nunit = unit + gridDim.x;
+    }
+    if (nunit < units) issue(nunit, nkt, tiles[buf ^ 1]);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const int bh = unit / q_tiles, qt = unit - bh * q_tiles;
+    const int b = bh / NH, h = bh % NH;
+    uint32_t aq[KS][4];
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+      const int c = kk * 16 + 2 * t;
+      aq[kk][0] = lds_pair<D>(s.Q, q0 + g, c);     aq[kk][1] = lds_pair<D>(s.Q, q0 + g + 8, c);
+      aq[kk][2] = lds_pair<D>(s.Q, q0 + g, c + 8); aq[kk][3] = lds_pair<D>(s.Q, q0 + g + 8, c + 8);
+    }
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        mma16816(acc[j], aq[kk], lds_pair<D>(s.K, j * 8 + g, kk * 16 + 2 * t), lds_pair<D>(s.K, j * 8 + g, kk * 16 + 2 * t + 8));
+    // key (kt*64 + j*8 + 2t + c) is masked for query (qt*64 + q0 + g + 8r) iff it lies after it and kinfo.y != 0
+    const int dq = 2 * t - g - q0 + AT * (kt - qt);
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 ki = *reinterpret_cast<const float4*>(&s.kinfo[j * 8 + 2 * t]);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float x0 = fmaf(acc[j][2 * r], sl2, ki.x), x1 = fmaf(acc[j][2 * r + 1], sl2, ki.z);
+        if (ki.y != 0.f && dq > 8 * r - 8 * j) x0 = -INFINITY;
+        if (ki.w != 0.f && dq + 1 > 8 * r - 8 * j) x1 = -INFINITY;
+        acc[j][2 * r] = x0;
+        acc[j][2 * r + 1] = x1;
+        mx[r] = fmaxf(mx[r], fmaxf(x0, x1));
+      }
+    }
+    float corr[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);
+      const float m_ref = (m_new == -INFINITY) ? 0.f : m_new;
+      corr[r] = ex2_approx(m_run[r] - m_ref);
+      float rs = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p0 = ex2_approx(acc[j][2 * r] - m_ref), p1 = ex2_approx(acc[j][2 * r + 1] - m_ref);
+        acc[j][2 * r] = p0;
+        acc[j][2 * r + 1] = p1;
+        rs += p0 + p1;
+      }
+      l_run[r] = l_run[r] * corr[r] + rs;   // per-thread partial; quad-reduced at the end of the unit
+      m_run[r] = m_new;
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      o[j][0] *= corr[0]; o[j][1] *= corr[0];
+      o[j][2] *= corr[1]; o[j][3] *= corr[1];
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {   // 16 keys per step
+      uint32_t ap[4];
+      ap[0] = pack_bf16(acc[2 * kk][0], acc[2 * kk][1]);
+      ap[1] = pack_bf16(acc[2 * kk][2], acc[2 * kk][3]);
+      ap[2] = pack_bf16(acc[2 * kk + 1][0], acc[2 * kk + 1][1]);
+      ap[3] = pack_bf16(acc[2 * kk + 1][2], acc[2 * kk + 1][3]);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, &s.V[kk * 16 + (lane & 15)][j * 8]);
+        mma16816(o[j], ap, b0, b1);
+      }
+    }
+    if (kt + 1 == k_tiles) {   // unit complete: normalise, stage through this buffer's Q rows, coalesced store
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float l = l_run[r];
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        const float inv = 1.f / l;
+        const int ql = q0 + g + 8 * r, qi = qt * AT + ql;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          *reinterpret_cast<uint32_t*>(&s.Q[ql][j * 8 + 2 * t]) = pack_bf16(o[j][2 * r] * inv, o[j][2 * r + 1] * inv);
+          o[j][2 * r] = o[j][2 * r + 1] = 0.f;
+        }
+        if (t == 0 && lse != nullptr && qi < Sq) lse[((int64_t)b * NH + h) * Sq + qi] = (m_run[r] + log2f(l)) * LN2;
+        m_run[r] = -INFINITY;
+        l_run[r] = 0.f;
+      }
+      __syncthreads();
+      store_tile<D>(out + ((int64_t)b * Sq + qt * AT) * ldo + h * D, ldo, s.Q, Sq - qt * AT);
+    }
+    __syncthreads();   // this buffer is refilled by the next iteration's prefetch
+    unit = nunit;
+    kt = nkt;
+    buf ^= 1;
+  }
+  cp_async_wait<0>();
+}
+
 template <int D>
 struct BwdTile {
   bf16 Q[AT][D + 8];    // later: dK staging
@@ -759,6 +906,27 @@ static int fwd_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, co
     const int grid1 = units < sms * ctas_per_sm ? units : sms * ctas_per_sm;
     launch_kernel(attn_fwd_tile_kernel<D>, dim3(grid1), dim3(AT_THREADS), smem, st, q, ldq, k, ldk, v, ldv, out, ldo, lse, NH, Sq, Sk,
                   units, rsqrtf((float)D), md);
+    KIT_LAUNCH_CHECK();
+    return KIT_OK;
+  }
+  if (md.bias == nullptr) {   // longer sequences without an explicit additive mask: persistent streaming kernel
+    static int ctas_per_sm = 0, sms = 0;
+    constexpr int smem = 2 * (int)sizeof(FwdTile<D>);
+    if (ctas_per_sm == 0) {
+      KIT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_stream_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      KIT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, attn_fwd_stream_kernel<D>, AT_THREADS, smem));
+      int dev = 0;
+      KIT_CHECK_CUDA(cudaGetDevice(&dev));
+      KIT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      KIT_REQUIRE(ctas_per_sm > 0, "attention forward streaming kernel does not fit on an SM");
+    }
+    const int q_tiles = (Sq + AT - 1) / AT, k_tiles = (Sk + AT - 1) / AT;
+    const int64_t units64 = (int64_t)B * NH * q_tiles;
+    KIT_REQUIRE(units64 < (1ll << 31), "attention forward: too many (batch, head, query tile) units");
+    const int units = (int)units64;
+    const int grid1 = units < sms * ctas_per_sm ? units : sms * ctas_per_sm;
+    launch_kernel(attn_fwd_stream_kernel<D>, dim3(grid1), dim3(AT_THREADS), smem, st, q, ldq, k, ldk, v, ldv, out, ldo, lse, NH, Sq, Sk,
+                  q_tiles, k_tiles, units, rsqrtf((float)D), md);
     KIT_LAUNCH_CHECK();
     return KIT_OK;
   }
