@@ -87,8 +87,16 @@ class TrainStep:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             steps_before = self.optimizer.step_count
-            with torch.cuda.graph(graph):
-                loss = self._eager(inputs, sota, mask)
+            try:
+                with torch.cuda.graph(graph):
+                    loss = self._eager(inputs, sota, mask)
+            except Exception as exc:   # noqa: BLE001 -- a failed capture must not cost the step: fall back to launches
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the train step failed ({exc!r}); continuing kernel by kernel")
+                self.use_graph = False
+                self.optimizer.step_count = steps_before
+                torch.cuda.synchronize()
+                return self._eager(inputs, sota, mask)
             self.optimizer.step_count = steps_before              # capture enqueues nothing
             entry = (graph, loss, (inputs, sota, mask))           # keep the buffers alive
             self._graphs[key] = entry
