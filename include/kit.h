@@ -181,6 +181,18 @@ int kit_loss_fwd_bwd(const float* pred, const float* target, const float* frame_
                      int32_t K, int32_t loss_kind, float grad_scale, float* loss_out, float* dpred,
                      float* partials, void* stream);
 
+/* put_missing_frames' block policy (dataloader.py:364-434, the non-random mode every trainer uses) drawn ON THE DEVICE for a
+ * whole batch: per sequence the quartiles of `samples` normals of each statistic, the block count, lengths and offsets, and
+ * the hold-fill index map -- Philox stream (seed, offset), i.e. the reference's distribution, not its draws.  Outputs feed
+ * kit_prepass directly.  blocks [B, 64, 2] / n_blocks [B] (optional, both or neither): the (start, end) pairs drawn. */
+typedef struct KitMissingStats {
+  float mean_consecutive_missing, std_consecutive_missing;   /* dataset_config.json */
+  float mean_number_missing_blocks, std_number_missing_blocks;
+  int32_t samples;
+} KitMissingStats;
+int kit_draw_missing(const KitMissingStats* stats, int32_t B, int32_t T, uint64_t seed, uint64_t offset,
+                     int32_t* src_index, float* frame_missing, int32_t* blocks, int32_t* n_blocks, void* stream);
+
 /* model.get_mask (model.py:172-209) on the device: frame_mask [size] -> out [size,size]. */
 int kit_get_mask(const float* frame_mask, int32_t size, int32_t matrix_type, float* out, void* stream);
 

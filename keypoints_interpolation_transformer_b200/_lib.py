@@ -43,6 +43,12 @@ class KitPrepassConfig(C.Structure):
                 ("zero_masked_enc", C.c_int32), ("k2p", C.c_int32)]
 
 
+class KitMissingStats(C.Structure):
+    _fields_ = [("mean_consecutive_missing", C.c_float), ("std_consecutive_missing", C.c_float),
+                ("mean_number_missing_blocks", C.c_float), ("std_number_missing_blocks", C.c_float),
+                ("samples", C.c_int32)]
+
+
 BUCKET_CALLBACK = C.CFUNCTYPE(None, C.c_int32, C.c_void_p)
 
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -71,6 +77,7 @@ _SIGNATURES = {
     "kit_loss_partials": (_I64, [_I64, _I32]),
     "kit_loss_fwd_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P]),
     "kit_get_mask": (C.c_int, [_P, _I32, _I32, _P, _P]),
+    "kit_draw_missing": (C.c_int, [C.POINTER(KitMissingStats), _I32, _I32, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P]),
     "kit_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P]),
     "kit_adam_step_dev": (C.c_int, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _P]),
     "kit_gemm_bf16": (C.c_int, [_I32, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P, _I64, _I32, _I32, _P,

@@ -94,3 +94,25 @@ def draw_sources(T, is_random_missing, dataset_name, rng=_pyrandom, nprng=np.ran
     if is_random_missing:
         return random_sources(T, rng)
     return blocks_to_sources(T, draw_blocks(T, dataset_name, rng, nprng, config))
+
+
+def draw_sources_device(B, T, dataset_name, seed, offset=0, device="cuda", config=None, return_blocks=False):
+    """The non-random policy of ``draw_sources`` for a whole batch on the device (kit_draw_missing): the same procedure
+    (quartiles of ``samples`` normals per statistic, block count / lengths / offsets, hold-fill chase) on a Philox stream --
+    the reference's distribution, not its draws.  ~20 us per batch instead of ~0.8 ms per SEQUENCE on the host.
+    Returns (src [B,T] int32, mask [B,T] float32[, blocks [B,64,2] int32, n_blocks [B] int32]) on ``device``."""
+    import ctypes as C
+
+    import torch
+
+    from . import _lib as K
+    cfg = (config or load_configuration("dataset_config"))[dataset_name]
+    st = K.KitMissingStats(cfg["mean_consecutive_missing"], cfg["std_consecutive_missing"],
+                           cfg["mean_number_missing_blocks"], cfg["std_number_missing_blocks"], int(cfg["samples"]))
+    src = torch.empty(B, T, dtype=torch.int32, device=device)
+    mask = torch.empty(B, T, dtype=torch.float32, device=device)
+    blocks = torch.empty(B, 64, 2, dtype=torch.int32, device=device) if return_blocks else None
+    nb = torch.empty(B, dtype=torch.int32, device=device) if return_blocks else None
+    K.check(K.lib().kit_draw_missing(C.byref(st), B, T, int(seed), int(offset), K.ptr(src), K.ptr(mask), K.ptr(blocks),
+                                     K.ptr(nb), K.stream_ptr()))
+    return (src, mask, blocks, nb) if return_blocks else (src, mask)

@@ -202,3 +202,43 @@ def test_device_prefetcher_yields_batches_in_order():
         seen.append((inputs.sum().item(), sota.sum().item(), mask.sum().item()))   # consumed before the slot is refilled
     want = [(h[0].sum().item(), h[1].sum().item(), h[2].sum().item()) for h in host]
     assert seen == want
+
+
+def test_device_missing_block_policy_structure_and_statistics():
+    """kit_draw_missing (dataloader.py:364-434 on a Philox stream): the index map / mask are EXACTLY what the reference's
+    sequential hold-fill makes of the drawn blocks, the blocks obey the policy's constraints, draws are reproducible, and
+    block count / masked-frame statistics agree with the host policy (reference RNG) within sampling error."""
+    from keypoints_interpolation_transformer_b200 import missing
+    B, T = 1024, 64
+    src, mask, blocks, nb = missing.draw_sources_device(B, T, "AUTSL", seed=7, device=DEV, config=missing.DATASET_CONFIG,
+                                                        return_blocks=True)
+    src2, mask2 = missing.draw_sources_device(B, T, "AUTSL", seed=7, device=DEV, config=missing.DATASET_CONFIG)
+    assert torch.equal(src, src2) and torch.equal(mask, mask2)                    # same (seed, offset) -> same draws
+    src3, _ = missing.draw_sources_device(B, T, "AUTSL", seed=7, offset=1, device=DEV, config=missing.DATASET_CONFIG)
+    assert not torch.equal(src, src3)
+    src, mask, blocks, nb = src.cpu().numpy(), mask.cpu().numpy(), blocks.cpu().numpy(), nb.cpu().numpy()
+    for b in range(B):
+        bl = [(int(a), int(e)) for a, e in blocks[b, :nb[b]]]
+        assert all(0 <= a < T and a <= e <= T - 1 for a, e in bl)
+        assert all(bl[i][0] >= bl[i - 1][0] for i in range(1, len(bl)))         # one block per section, in order
+        ref_src, ref_mask = missing.blocks_to_sources(T, bl)
+        assert np.array_equal(src[b], ref_src) and np.array_equal(mask[b], ref_mask)
+    pr, rs = random.Random(3), np.random.RandomState(3)
+    host = [missing.draw_blocks(T, "AUTSL", pr, rs, missing.DATASET_CONFIG) for _ in range(400)]
+    host_nb = np.array([len(h) for h in host], dtype=np.float64)
+    host_masked = np.array([missing.blocks_to_sources(T, h)[1].sum() for h in host])
+    assert abs(nb.mean() - host_nb.mean()) < 0.35, (nb.mean(), host_nb.mean())
+    assert abs(mask.sum(1).mean() - host_masked.mean()) < 2.0, (mask.sum(1).mean(), host_masked.mean())
+    assert set(np.unique(nb)) <= set(range(1, 65)) and nb.min() >= host_nb.min() - 1 and nb.max() <= host_nb.max() + 1
+
+
+def test_keypoint_batcher_device_policy_feeds_the_step():
+    from keypoints_interpolation_transformer_b200 import dataloader as dl
+    raw = torch.rand(8, 32, 12, 2)
+    bt = dl.KeypointBatcher(raw, have_augmentation=False, normalize=False, seed=5, device_policy=True)
+    inputs, sota, mask = bt.batch(list(range(8)))
+    assert inputs.shape == (8, 33, 12, 2) and sota.shape == (8, 32, 12, 2) and mask.shape == (8, 33)
+    assert torch.equal(sota.cpu(), raw)
+    m = mask[:, 1:].bool().cpu()
+    assert m.any() and (inputs[:, 0] == 1).all() and (mask[:, 0] == 0).all()
+    assert torch.equal(inputs[:, 1:].cpu()[~m], raw[~m])                         # untouched frames pass through
