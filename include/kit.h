@@ -27,7 +27,7 @@ extern "C" {
 #define KIT_ERR_CUDA (-2)
 #define KIT_ERR_UNSUPPORTED (-3)
 
-#define KIT_ABI_VERSION 1
+#define KIT_ABI_VERSION 2
 
 /* attention-mask synthesis flags (model.py:172-209 + torch/nn/functional.py:6620) */
 #define KIT_MASK_NONE 0
@@ -38,6 +38,7 @@ extern "C" {
 /* loss kinds */
 #define KIT_LOSS_EUCLID 0 /* euclidean_loss.py:8-17  mean_points sum_xy (o-t)^2                    */
 #define KIT_LOSS_MSE 1    /* A1_train.py:254 torch.nn.MSELoss (= EUCLID / 2)                       */
+#define KIT_LOSS_DISTANCE 2 /* euclidean_loss.py:19-37 EuclideanDistanceLoss: sum_points ||o-t||_2 (A4 validation) */
 
 /* get_mask matrix types (model.py:172) */
 #define KIT_MATRIX_TRIANGLE 0
@@ -64,8 +65,14 @@ typedef struct KitModelConfig {
   int32_t layers;     /* encoder layers == decoder layers */
   int32_t heads;      /* H / heads in {16, 32, 64, 128} */
   int32_t ff;         /* dim_feedforward (2048) */
-  int32_t max_len;    /* rows of the trig positional table (2048) */
+  int32_t max_len;    /* rows of the trig positional table (2048; 512 in KeypointCompleterCycle, model.py:226-227) */
+  int32_t variant;    /* KIT_MODEL_* */
+  int32_t reserved;
 } KitModelConfig;
+#define KIT_MODEL_COMPLETER 0 /* model.py:60-170  KeypointCompleter */
+#define KIT_MODEL_CYCLE 1     /* model.py:212-321 KeypointCompleterCycle: the token-norm output enters the position sum twice
+                               * (:279-284: PositionalEncoding already returns norm + pe), and tgt_pad_mask reaches
+                               * nn.Transformer (:294) -- pass it as dec_mask.frame_mask with KIT_MASK_KEYPAD_ADD */
 
 /* All parameters live in ONE fp32 arena (and their gradients in a second arena of the same layout)
  * so that the optimiser is one kernel and the data-parallel all-reduce is a few large contiguous

@@ -8,7 +8,8 @@ LIB_PATH = os.path.join(HERE, "libkit_b200.so")
 
 KIT_OK = 0
 MASK_NONE, MASK_REPEAT_INC, MASK_KEYPAD_ADD, MASK_TRIANGLE = 0, 1, 2, 4
-LOSS_EUCLID, LOSS_MSE = 0, 1
+LOSS_EUCLID, LOSS_MSE, LOSS_DISTANCE = 0, 1, 2
+MODEL_COMPLETER, MODEL_CYCLE = 0, 1
 MATRIX_TYPES = {"triangle": 0, "repeat": 1, "repeat-inc": 2, "all": 3}
 AUG_NONE, AUG_ROTATE, AUG_SHEAR, AUG_ARM_ROTATE = 0, 1, 2, 3
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC = 0, 1, 2
@@ -21,7 +22,8 @@ class KitError(RuntimeError):
 
 class KitModelConfig(C.Structure):
     _fields_ = [("input_size", C.c_int32), ("hidden", C.c_int32), ("layers", C.c_int32),
-                ("heads", C.c_int32), ("ff", C.c_int32), ("max_len", C.c_int32)]
+                ("heads", C.c_int32), ("ff", C.c_int32), ("max_len", C.c_int32), ("variant", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class KitAttnMask(C.Structure):

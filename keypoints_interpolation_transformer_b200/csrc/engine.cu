@@ -110,6 +110,7 @@ static int build_layout(const KitModelConfig* c, Layout& L) {
   KIT_REQUIRE(d == 16 || d == 32 || d == 64, "head dim %d unsupported (16, 32, 64)", d);
   KIT_REQUIRE(c->input_size > 0 && c->input_size % 2 == 0, "input_size must be 2*K");
   KIT_REQUIRE(c->layers > 0 && c->ff > 0 && c->ff % 8 == 0 && c->max_len > 0, "bad layers/ff/max_len");
+  KIT_REQUIRE(c->variant == KIT_MODEL_COMPLETER || c->variant == KIT_MODEL_CYCLE, "unknown model variant %d", c->variant);
   L.cfg = *c;
   const int H = c->hidden, IN = c->input_size, FF = c->ff;
   LayoutBuilder lb(L);
@@ -550,8 +551,9 @@ static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const f
   KIT_TRY(eg(e, 0, e->xd, e->K2p, e->wb + L.emb_f.wb, L.emb_f.ld, e->ef_raw, H, (int)M, H, e->K2p, e->params + L.emb_f.b,
              nullptr, 0, OUT_BF16, ACT_NONE, nullptr, 0));
   e->launches += 2;
-  KIT_TRY(embed_post_fwd(e->ei_raw, e->params + L.pe_i, e->params + L.learned_i, e->ei, M, H, T, e->st));
-  KIT_TRY(embed_post_fwd(e->ef_raw, e->params + L.pe_f, e->params + L.learned_f, e->ef, M, H, T, e->st));
+  const float ns = L.cfg.variant == KIT_MODEL_CYCLE ? 2.f : 1.f;   // model.py:283-284
+  KIT_TRY(embed_post_fwd(e->ei_raw, e->params + L.pe_i, e->params + L.learned_i, e->ei, M, H, T, ns, e->st));
+  KIT_TRY(embed_post_fwd(e->ef_raw, e->params + L.pe_f, e->params + L.learned_f, e->ef, M, H, T, ns, e->st));
   KIT_TRY(swiglu_fwd(e, e->ei, L.swi_i, e->si12, e->sig, e->x0));
   KIT_TRY(swiglu_fwd(e, e->ef, L.swi_f, e->sf12, e->sfg, e->y0));
   // encoder (torch/nn/modules/transformer.py:956 post-norm layers + final norm :137)
@@ -668,7 +670,8 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
   // filled branch: SwiGLU, token-norm/PE, embedding  (g3 = residual gradient from the head)
   KIT_TRY(swiglu_bwd(e, dy, e->ef, L.swi_f, e->sf12, e->sfg, e->g1, e->g2));  // g2 = d ef
   e->launches++;
-  KIT_TRY(embed_post_bwd(e->g2, e->ef_raw, e->g3, e->g1, e->grads + L.learned_f, M, H, e->st));  // g1 = d ef_raw
+  const float ns = L.cfg.variant == KIT_MODEL_CYCLE ? 2.f : 1.f;
+  KIT_TRY(embed_post_bwd(e->g2, e->ef_raw, e->g3, e->g1, e->grads + L.learned_f, M, H, ns, e->st));  // g1 = d ef_raw
   KIT_TRY(eg(e, 1, e->g1, H, e->xd, e->K2p, e->grads + L.emb_f.w, IN, H, IN, (int)M, nullptr, nullptr, 0, OUT_F32_ATOMIC,
              ACT_NONE, nullptr, 0));
   e->launches++;
@@ -703,7 +706,7 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
   // input branch
   KIT_TRY(swiglu_bwd(e, dx, e->ei, L.swi_i, e->si12, e->sig, e->g1, e->g2));
   e->launches++;
-  KIT_TRY(embed_post_bwd(e->g2, e->ei_raw, nullptr, e->g1, e->grads + L.learned_i, M, H, e->st));
+  KIT_TRY(embed_post_bwd(e->g2, e->ei_raw, nullptr, e->g1, e->grads + L.learned_i, M, H, ns, e->st));
   KIT_TRY(eg(e, 1, e->g1, H, e->xe, e->K2p, e->grads + L.emb_i.w, IN, H, IN, (int)M, nullptr, nullptr, 0, OUT_F32_ATOMIC,
              ACT_NONE, nullptr, 0));
   e->launches++;

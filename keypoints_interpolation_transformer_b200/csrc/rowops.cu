@@ -91,7 +91,7 @@ __device__ __forceinline__ void block_col_reduce_atomic(const RowVec<NV>& acc, f
 template <int NV>
 __global__ void embed_post_fwd_kernel(const bf16* __restrict__ raw, const float* __restrict__ pe,
                                       const float* __restrict__ learned, bf16* __restrict__ out, int64_t M, int H,
-                                      int T) {
+                                      int T, float norm_scale) {
   pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
@@ -100,6 +100,7 @@ __global__ void embed_post_fwd_kernel(const bf16* __restrict__ raw, const float*
   row_load(x, raw + row * H, H, lane);
   float mean, rstd;
   row_stats(x, H, lane, mean, rstd, 1e-5f);
+  rstd *= norm_scale;
   const int t = (int)(row % T);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -119,7 +120,7 @@ __global__ void embed_post_fwd_kernel(const bf16* __restrict__ raw, const float*
 template <int NV>
 __global__ void embed_post_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ raw,
                                       const bf16* __restrict__ addend, bf16* __restrict__ draw,
-                                      float* __restrict__ dlearned, int64_t M, int H) {
+                                      float* __restrict__ dlearned, int64_t M, int H, float norm_scale) {
   pdl_grid_sync();
   __shared__ float s_acc[ROW_WARPS][NV * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -154,7 +155,7 @@ __global__ void embed_post_bwd_kernel(const bf16* __restrict__ dout, const bf16*
     for (int i = 0; i < NV; ++i)
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        float g = rstd * (dy.v[i][u] - s1 - x.v[i][u] * s2);
+        float g = rstd * norm_scale * (dy.v[i][u] - s1 - x.v[i][u] * s2);
         if (addend != nullptr) g += ad.v[i][u];
         dy.v[i][u] = g;
       }
@@ -541,18 +542,18 @@ static inline unsigned reduce_blocks(int64_t M) {
 }
 
 int embed_post_fwd(const bf16* raw, const float* pe, const float* learned, bf16* out, int64_t M, int H, int T,
-                   cudaStream_t st) {
+                   float norm_scale, cudaStream_t st) {
   int rc = check_h(H);
   if (rc) return rc;
-  KIT_NV_DISPATCH(H, (launch_kernel(embed_post_fwd_kernel<NV>, dim3(row_blocks(M)), dim3(256), 0, st, raw, pe, learned, out, M, H, T)));
+  KIT_NV_DISPATCH(H, (launch_kernel(embed_post_fwd_kernel<NV>, dim3(row_blocks(M)), dim3(256), 0, st, raw, pe, learned, out, M, H, T, norm_scale)));
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }
 int embed_post_bwd(const bf16* dout, const bf16* raw, const bf16* addend, bf16* draw, float* dlearned, int64_t M, int H,
-                   cudaStream_t st) {
+                   float norm_scale, cudaStream_t st) {
   int rc = check_h(H);
   if (rc) return rc;
-  KIT_NV_DISPATCH(H, (launch_kernel(embed_post_bwd_kernel<NV>, dim3(reduce_blocks(M)), dim3(256), 0, st, dout, raw, addend, draw, dlearned, M, H)));
+  KIT_NV_DISPATCH(H, (launch_kernel(embed_post_bwd_kernel<NV>, dim3(reduce_blocks(M)), dim3(256), 0, st, dout, raw, addend, draw, dlearned, M, H, norm_scale)));
   KIT_LAUNCH_CHECK();
   return KIT_OK;
 }

@@ -15,10 +15,11 @@ struct WeightDesc {
   int dstT_ld;
 };
 
+// norm_scale: weight of the token-norm term in the position sum (1; 2 in KeypointCompleterCycle, model.py:283-284)
 int embed_post_fwd(const bf16* raw, const float* pe, const float* learned, bf16* out, int64_t M, int H, int T,
-                   cudaStream_t st);
+                   float norm_scale, cudaStream_t st);
 int embed_post_bwd(const bf16* dout, const bf16* raw, const bf16* addend, bf16* draw, float* dlearned, int64_t M, int H,
-                   cudaStream_t st);
+                   float norm_scale, cudaStream_t st);
 int add_ln_fwd(const bf16* a, const bf16* b, const float* gamma, const float* beta, bf16* sum_out, bf16* y, float* mean,
                float* rstd, int64_t M, int H, cudaStream_t st);
 int ln_bwd(const bf16* dy, const bf16* s_saved, const float* mean, const float* rstd, const float* gamma,

@@ -10,8 +10,8 @@ class ModelLayout:
     """Parameter-arena layout of one model configuration (names = the reference's state_dict keys,
     SURVEY.md section 8b)."""
 
-    def __init__(self, input_size, hidden, layers, heads, ff=2048, max_len=2048):
-        self.cfg = K.KitModelConfig(input_size, hidden, layers, heads, ff, max_len)
+    def __init__(self, input_size, hidden, layers, heads, ff=2048, max_len=2048, variant=0):
+        self.cfg = K.KitModelConfig(input_size, hidden, layers, heads, ff, max_len, variant, 0)
         lib = K.lib()
         n = lib.kit_layout_num_entries(C.byref(self.cfg))
         if n < 0:

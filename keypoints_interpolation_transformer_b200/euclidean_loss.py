@@ -72,5 +72,4 @@ class EuclideanDistanceLoss(nn.Module):
     """euclidean_loss.py:19-37 (A4 validation criterion): sum over points of the L2 distance."""
 
     def forward(self, output, target):
-        d = output.reshape(-1, 2) - target.reshape(-1, 2)
-        return torch.linalg.vector_norm(d, dim=1).sum()
+        return _LossFn.apply(output, target, None, K.LOSS_DISTANCE)

@@ -56,11 +56,13 @@ class _CompleterFn(torch.autograd.Function):
 class KeypointCompleter(nn.Module):
     FF = 2048          # nn.Transformer default dim_feedforward (model.py:84-90)
     MAX_LEN = 512 * 4  # model.py:74-75
+    VARIANT = K.MODEL_COMPLETER
+    USES_TGT_PAD = False   # model.py:143: tgt_pad_mask never reaches nn.Transformer
 
     def __init__(self, input_size, hidden_dim, num_layers, num_heads):
         super().__init__()
         self.input_size, self.hidden_dim, self.num_layers, self.num_heads = input_size, hidden_dim, num_layers, num_heads
-        self.layout = ModelLayout(input_size, hidden_dim, num_layers, num_heads, self.FF, self.MAX_LEN)
+        self.layout = ModelLayout(input_size, hidden_dim, num_layers, num_heads, self.FF, self.MAX_LEN, self.VARIANT)
         flat = torch.zeros(self.layout.total)
         self._param_names, self._param_slices, self._buffer_names = [], [], []
         object.__setattr__(self, "flat_params", flat)
@@ -239,18 +241,23 @@ class KeypointCompleter(nn.Module):
         if frame_masks is not None:
             xm, ym = as_frame(frame_masks[0]), as_frame(frame_masks[1])
             enc_mask = make_mask(xm, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD)
-            dec_mask = make_mask(ym, K.MASK_REPEAT_INC)
+            dec_mask = make_mask(ym, K.MASK_REPEAT_INC | (K.MASK_KEYPAD_ADD if self.USES_TGT_PAD else 0))
         else:
             sb, sbb, sbh = as_bias(src_mask)
             tb, tbb, tbh = as_bias(tgt_mask)
-            pad = None
-            if src_pad_mask is not None:
-                pad = src_pad_mask.to(dev)
+
+            def as_pad(pad):
+                if pad is None:
+                    return None
+                pad = pad.to(dev)
                 if pad.dtype == torch.bool:
                     pad = torch.zeros(pad.shape, device=dev).masked_fill(pad, float("-inf"))
-                pad = as_frame(pad)
+                return as_frame(pad)
+
+            pad = as_pad(src_pad_mask)
+            tpad = as_pad(tgt_pad_mask) if self.USES_TGT_PAD else None
             enc_mask = make_mask(pad, K.MASK_KEYPAD_ADD if pad is not None else 0, sb, sbb, sbh)
-            dec_mask = make_mask(None, 0, tb, tbb, tbh)
+            dec_mask = make_mask(tpad, K.MASK_KEYPAD_ADD if tpad is not None else 0, tb, tbb, tbh)
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         eng = self.engine_for(B, T, training=need_grad)
         out_shape = (B, T, K2 // 2, 2)
@@ -286,3 +293,16 @@ class KeypointCompleter(nn.Module):
             return rep
         out = torch.where(rep == 1, torch.tensor(float("-inf")), rep)
         return out.masked_fill(j <= i, 0.0)
+
+
+class KeypointCompleterCycle(KeypointCompleter):
+    """model.py:212-321 -- the second-stage model of A2_train_cycle.py.  Same parameters and kernels as
+    ``KeypointCompleter`` with three differences: the trig tables have 512 rows (:226-227); the token-norm output
+    enters the position sum twice (:279-284: ``PositionalEncoding`` already returns ``norm + pe``, then ``norm`` is
+    added again); and ``tgt_pad_mask`` IS handed to nn.Transformer (:294), i.e. added to the decoder self-attention
+    logits.  A2_train_cycle.py:111-115 calls it with "all" masks and all-ones pad masks (a constant shift of every
+    logit), and feeds it the first model's prediction as ``filled``; only this model's parameters are stepped
+    (A2_train_cycle.py:241), so no gradient flows back into ``inputs`` / ``filled`` here."""
+    MAX_LEN = 512
+    VARIANT = K.MODEL_CYCLE
+    USES_TGT_PAD = True

@@ -120,8 +120,10 @@ def get_mask(mask: torch.Tensor, size: int, matrix_type: str = "triangle") -> to
 
 
 def completer_forward(p, inputs, filled, nh, src_pad=None, src_bias=None, tgt_bias=None,
-                      return_aux=False):
-    """model.py:100-170, batch-first restatement.
+                      return_aux=False, cycle=False, tgt_pad=None):
+    """model.py:100-170, batch-first restatement.  ``cycle=True``: KeypointCompleterCycle (model.py:212-321) -- the
+    token-norm output enters the position sum TWICE (:283-284, the trig encoder already adds it) and ``tgt_pad`` [B,T]
+    is handed to nn.Transformer as tgt_key_padding_mask (:294), i.e. ADDED to the decoder self-attention logits.
 
     inputs, filled : [B,T,K,2] fp32 (encoder input x, decoder input x_no_sota)
     src_pad        : [B,T] float key-padding mask, ADDED to encoder self-attn logits (fact 3)
@@ -142,8 +144,11 @@ def completer_forward(p, inputs, filled, nh, src_pad=None, src_bias=None, tgt_bi
     filled_emb = linear(x_fl, p["filled_embedding.weight"], p["filled_embedding.bias"])  # :121
     pe_i = p["trig_input_positional_encoder.pos_encoding"].reshape(-1, H)[:T]
     pe_f = p["trig_filled_positional_encoder.pos_encoding"].reshape(-1, H)[:T]
-    x = token_norm(input_emb) + pe_i + p["learned_input_positional_encoder"].view(1, 1, H)   # :124-131
-    y = token_norm(filled_emb) + pe_f + p["learned_filled_positional_encoder"].view(1, 1, H)  # :125-132
+    ns = 2.0 if cycle else 1.0
+    x = ns * token_norm(input_emb) + pe_i + p["learned_input_positional_encoder"].view(1, 1, H)   # :124-131 / :283
+    y = ns * token_norm(filled_emb) + pe_f + p["learned_filled_positional_encoder"].view(1, 1, H)  # :125-132 / :284
+    if cycle and tgt_pad is not None:
+        tgt_bias = (tgt_bias if tgt_bias is not None else torch.zeros(B, T, T)) + tgt_pad.float().view(B, 1, T)
     x = swiglu(x, p, "swiGlu_input_prev")      # :136
     y = swiglu(y, p, "swiGlu_filled_prev")     # :137
 
@@ -193,6 +198,11 @@ def euclidean_loss(output, target):
     o = output.reshape(-1, 2)
     t = target.reshape(-1, 2)
     return torch.sum((o - t) ** 2, dim=1).mean()
+
+
+def euclidean_distance_loss(output, target):
+    """euclidean_loss.py:19-37 (A4 validation criterion) -- SUM over points of the L2 distance."""
+    return torch.norm(output.reshape(-1, 2) - target.reshape(-1, 2), dim=1).sum()
 
 
 def mse_loss(output, target):

@@ -96,6 +96,51 @@ def completer_case(name, K, H, L, NH, T, B, seed, grads_full):
     print(name, "pred", out["pred"].shape, "loss", out["loss_mse"])
 
 
+def cycle_case(name="cycle_small_k54", K=54, H=64, L=2, NH=4, T=12, B=2, seed=9):
+    """KeypointCompleterCycle (model.py:212-321) called like the second model of A2_train_cycle.py:111-115 ("all" masks,
+    all-ones pad masks) and like its first model (:105-109, repeat-inc masks + frame pad masks); gradients w.r.t. the
+    parameters AND the two inputs (the cycle feeds one model's output into the other)."""
+    sd = ko.deterministic_state_dict(2 * K, H, L)
+    sd = {k: (v[:512] if k.endswith("pos_encoding") else v) for k, v in sd.items()}       # max_len = 512 (:226-227)
+    m = ref_model.KeypointCompleterCycle(input_size=2 * K, hidden_dim=H, num_layers=L, num_heads=NH)
+    m.load_state_dict(sd, strict=True)
+    gm = ref_model.KeypointCompleter(input_size=2 * K, hidden_dim=16, num_layers=1, num_heads=2).get_mask   # A2:99-103
+    inputs, gt, mask = ko.synthetic_batch(B, T, K, seed=seed)
+    out = {"K": K, "H": H, "L": L, "NH": NH, "T": T, "B": B, "seed": seed,
+           "inputs": inputs.numpy(), "gt": gt.numpy(), "mask": mask.numpy()}
+    for mode in ("second", "first"):
+        m.zero_grad()
+        preds, dxs, dfs, total = [], [], [], 0.0
+        for b in range(B):
+            x = inputs[b, :-1].clone().requires_grad_(True)
+            xf = inputs[b, 1:].clone().requires_grad_(True)
+            xm, ym = mask[b, :-1].clone(), mask[b, 1:].clone()
+            if mode == "second":
+                pred = m(x, xf, src_pad_mask=torch.ones_like(xm.unsqueeze(0)), tgt_pad_mask=torch.ones_like(ym.unsqueeze(0)),
+                         src_mask=gm(xm, T, "all"), tgt_mask=gm(ym, T, "all"))
+            else:
+                pred = m(x, xf, src_pad_mask=xm.unsqueeze(0), tgt_pad_mask=ym.unsqueeze(0),
+                         src_mask=gm(xm, T, "repeat-inc"), tgt_mask=gm(ym, T, "repeat-inc"))
+            loss = torch.nn.MSELoss()(pred, gt[b]) / B
+            loss.backward()
+            total += loss.item()
+            preds.append(pred.detach())
+            dxs.append(x.grad.clone())
+            dfs.append(xf.grad.clone())
+        out[mode + "_pred"] = torch.stack(preds).numpy()
+        out[mode + "_loss"] = np.float32(total)
+        out[mode + "_dinputs"] = torch.stack(dxs).numpy()
+        out[mode + "_dfilled"] = torch.stack(dfs).numpy()
+        names = [n for n, _ in m.named_parameters()]
+        out["grad_names"] = np.array(names)
+        out[mode + "_grad_norms"] = np.array([p.grad.norm().item() for _, p in m.named_parameters()], dtype=np.float64)
+        for n in ("input_embedding.weight", "fc_final.weight", "transformer.decoder.layers.0.self_attn.in_proj_weight",
+                  "learned_filled_positional_encoder"):
+            out[mode + "_grad::" + n] = dict(m.named_parameters())[n].grad.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "losses", out["second_loss"], out["first_loss"])
+
+
 def get_mask_case():
     m = ref_model.KeypointCompleter(input_size=108, hidden_dim=16, num_layers=1, num_heads=2)
     rs = np.random.RandomState(3)
@@ -226,6 +271,12 @@ def loss_case():
            "euclid": ref_loss.EuclideanLoss()(o, t).numpy(),
            "mse": torch.nn.MSELoss()(o, t).numpy(),
            "euclid_dist": ref_loss.EuclideanDistanceLoss()(o[0], t[0]).numpy()}
+    od = o[0].clone()
+    od[3, 5] = t[0, 3, 5]                      # one zero distance: torch.norm's backward gives 0 there
+    od.requires_grad_(True)
+    d = ref_loss.EuclideanDistanceLoss()(od, t[0])
+    d.backward()
+    out.update({"distance_o": od.detach().numpy(), "distance": d.detach().numpy(), "distance_grad": od.grad.numpy()})
     np.savez_compressed(os.path.join(HERE, "loss.npz"), **out)
 
 
@@ -235,6 +286,7 @@ if __name__ == "__main__":
     augment_case()
     missing_case()
     loss_case()
+    cycle_case()
     small_full = ["learned_input_positional_encoder", "input_embedding.bias", "fc_final.weight", "fc_final.bias",
                   "transformer.encoder.layers.0.self_attn.in_proj_bias",
                   "transformer.decoder.layers.1.multihead_attn.out_proj.weight",

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in kit.h but not exported"
     assert declared == set(K.exported_symbols())
-    assert lib.kit_version() == 1
+    assert lib.kit_version() == 2
 
 
 @pytest.mark.parametrize("K2,H,L,NH", [(108, 256, 6, 8), (142, 256, 6, 8), (142, 512, 8, 8), (108, 64, 2, 4)])

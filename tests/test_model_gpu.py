@@ -219,3 +219,77 @@ def test_graph_replayed_step_matches_eager_step():
     (l0, p0), (l1, p1) = results
     assert np.allclose(l0, l1, rtol=2e-3, atol=1e-6), (l0, l1)
     assert _rel(p1, p0) < 1e-4        # same kernels, same order; atomics in the weight gradients reorder fp32 sums
+
+
+def test_cycle_model_matches_reference_golden(golden_dir):
+    """model.KeypointCompleterCycle (model.py:212-321) through the A2_train_cycle.py call surface, one sequence per call:
+    the second-model call (:111-115, "all" masks + all-ones pad masks) and a first-model style call (repeat-inc masks, frame
+    pad masks on both stacks) against outputs and parameter gradients of the reference module; then batched with
+    ``frame_masks`` (masks synthesised in-kernel)."""
+    g = _load(golden_dir, "cycle_small_k54")
+    Kp, H, L, NH, B, T = (int(g[k]) for k in ("K", "H", "L", "NH", "B", "T"))
+    sd = ko.deterministic_state_dict(2 * Kp, H, L)
+    sd = {k: (v[:512] if k.endswith("pos_encoding") else v) for k, v in sd.items()}
+    m = model.KeypointCompleterCycle(2 * Kp, H, L, NH)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    m.train()
+    inputs, gt, mask = (torch.from_numpy(g[k]).to(DEV) for k in ("inputs", "gt", "mask"))
+    names = [str(n) for n in g["grad_names"]]
+    crit = euclidean_loss.MSELoss()
+    for mode in ("second", "first"):
+        m.zero_grad(set_to_none=True)
+        total = 0.0
+        preds = []
+        for b in range(B):
+            x, xf = inputs[b, :-1], inputs[b, 1:]
+            xm, ym = mask[b, :-1].clone(), mask[b, 1:].clone()
+            if mode == "second":
+                pred = m(x, xf, src_pad_mask=torch.ones_like(xm.unsqueeze(0)), tgt_pad_mask=torch.ones_like(ym.unsqueeze(0)),
+                         src_mask=m.get_mask(xm, T, "all").to(DEV), tgt_mask=m.get_mask(ym, T, "all").to(DEV))
+            else:
+                pred = m(x, xf, src_pad_mask=xm.unsqueeze(0), tgt_pad_mask=ym.unsqueeze(0),
+                         src_mask=m.get_mask(xm, T, "repeat-inc").to(DEV), tgt_mask=m.get_mask(ym, T, "repeat-inc").to(DEV))
+            loss = crit(pred, gt[b]) / B
+            loss.backward()
+            total += loss.item()
+            preds.append(pred.detach())
+        ref_pred = torch.from_numpy(g[mode + "_pred"])
+        assert _rel(torch.stack(preds), ref_pred) < TOL, mode
+        assert abs(total - float(g[mode + "_loss"])) < TOL * abs(float(g[mode + "_loss"])), mode
+        got = dict(m.named_parameters())
+        ref_norms = g[mode + "_grad_norms"]
+        tot_ref = float(np.sqrt((ref_norms ** 2).sum()))
+        tot_got = float(torch.sqrt(sum((got[n].grad.double() ** 2).sum() for n in names)))
+        assert abs(tot_got - tot_ref) < TOL * tot_ref, mode
+        for key in g.files:
+            if key.startswith(mode + "_grad::"):
+                n = key.split("::", 1)[1]
+                assert _rel(got[n].grad, torch.from_numpy(g[key])) < 0.1, (mode, n)
+    # batched, masks synthesised from the frame masks (decoder key padding included: USES_TGT_PAD)
+    m.eval()
+    with torch.no_grad():
+        batched = m(inputs[:, :-1], inputs[:, 1:], frame_masks=(mask[:, :-1], mask[:, 1:]))
+    assert _rel(batched, torch.from_numpy(g["first_pred"])) < TOL
+    # the base model ignores tgt_pad_mask (model.py:143), the cycle model must not (model.py:294)
+    with torch.no_grad():
+        xm, ym = mask[0, :-1].clone(), mask[0, 1:].clone()
+        kw = dict(src_pad_mask=xm.unsqueeze(0), src_mask=m.get_mask(xm, T, "repeat-inc").to(DEV),
+                  tgt_mask=m.get_mask(ym, T, "repeat-inc").to(DEV))
+        with_pad = m(inputs[0, :-1], inputs[0, 1:], tgt_pad_mask=ym.unsqueeze(0), **kw)
+        without = m(inputs[0, :-1], inputs[0, 1:], tgt_pad_mask=None, **kw)
+    assert ym.sum() > 0 and (with_pad - without).abs().max().item() > 1e-4
+
+
+def test_euclidean_distance_loss_kernel(golden_dir):
+    """EuclideanDistanceLoss (euclidean_loss.py:19-37, the A4 validation criterion) on the fused loss kernel: value and
+    gradient against the reference's own outputs, zero distance included (gradient 0 there, as torch.norm's backward)."""
+    g = _load(golden_dir, "loss")
+    o = torch.from_numpy(g["distance_o"]).to(DEV).requires_grad_(True)
+    t = torch.from_numpy(g["t"][0]).to(DEV)
+    d = euclidean_loss.EuclideanDistanceLoss()(o, t)
+    d.backward()
+    assert abs(d.item() - float(g["distance"])) <= 1e-5 * float(g["distance"])
+    np.testing.assert_allclose(o.grad.cpu().numpy(), g["distance_grad"], rtol=1e-5, atol=1e-6)
+    assert o.grad[3, 5].abs().max().item() == 0.0

@@ -49,6 +49,43 @@ def test_completer_forward_loss_and_grads(golden_dir, name):
             assert err <= 2e-4 * max(ref.abs().max().item(), 1e-3), (n, err)
 
 
+def test_cycle_model_matches_reference(golden_dir):
+    """KeypointCompleterCycle (model.py:212-321) as A2_train_cycle.py calls it: second model ("all" masks, all-ones pad masks)
+    and first-model style (repeat-inc masks + frame pad masks on BOTH stacks); parameters' and inputs' gradients."""
+    g = _load(golden_dir, "cycle_small_k54")
+    K, H, L, NH, B, T = (int(g[k]) for k in ("K", "H", "L", "NH", "B", "T"))
+    sd = ko.deterministic_state_dict(2 * K, H, L)
+    sd = {k: (v[:512] if k.endswith("pos_encoding") else v) for k, v in sd.items()}
+    inputs, gt, mask = (torch.from_numpy(g[k]) for k in ("inputs", "gt", "mask"))
+    names = [str(n) for n in g["grad_names"]]
+    for mode in ("second", "first"):
+        params = {k: v.clone().requires_grad_(not k.endswith("pos_encoding")) for k, v in sd.items()}
+        x = inputs[:, :-1].clone().requires_grad_(True)
+        xf = inputs[:, 1:].clone().requires_grad_(True)
+        xm, ym = mask[:, :-1], mask[:, 1:]
+        if mode == "second":
+            pred = ko.completer_forward(params, x, xf, NH, src_pad=torch.ones_like(xm), tgt_pad=torch.ones_like(ym), cycle=True)
+        else:
+            pred = ko.completer_forward(params, x, xf, NH, src_pad=xm, src_bias=ko.repeat_inc_bias(xm),
+                                        tgt_bias=ko.repeat_inc_bias(ym), tgt_pad=ym, cycle=True)
+        ref_pred = torch.from_numpy(g[mode + "_pred"])
+        assert (pred - ref_pred).abs().max().item() <= 1e-4 * max(1.0, ref_pred.abs().max().item())
+        loss = sum(ko.mse_loss(pred[b], gt[b]) / B for b in range(B))       # make_golden: per-sequence MSE / B
+        assert abs(loss.item() - float(g[mode + "_loss"])) <= 1e-5 * max(1.0, abs(loss.item()))
+        loss.backward()
+        for n, ref_norm in zip(names, g[mode + "_grad_norms"]):
+            got = params[n].grad.norm().item()
+            assert abs(got - ref_norm) <= 2e-4 * max(ref_norm, 1e-3), (mode, n, got, ref_norm)
+        for key in g.files:
+            if key.startswith(mode + "_grad::"):
+                n = key.split("::", 1)[1]
+                ref = torch.from_numpy(g[key])
+                assert (params[n].grad - ref).abs().max().item() <= 2e-4 * max(ref.abs().max().item(), 1e-3), (mode, n)
+        for got, key in ((x.grad, "_dinputs"), (xf.grad, "_dfilled")):
+            ref = torch.from_numpy(g[mode + key])
+            assert (got - ref).abs().max().item() <= 2e-4 * max(ref.abs().max().item(), 1e-6), (mode, key)
+
+
 def test_get_mask_bit_exact(golden_dir):
     g = _load(golden_dir, "get_mask")
     for n, T in enumerate([1, 2, 7, 16, 33]):
@@ -144,3 +181,9 @@ def test_losses_match_reference(golden_dir):
     assert abs(ko.euclidean_loss(o, t).item() - float(g["euclid"])) <= 1e-6 * float(g["euclid"])
     assert abs(ko.mse_loss(o, t).item() - float(g["mse"])) <= 1e-6 * float(g["mse"])
     assert abs(ko.euclidean_loss(o, t).item() - 2 * ko.mse_loss(o, t).item()) < 1e-5
+    if "distance" in g.files:      # EuclideanDistanceLoss (euclidean_loss.py:19-37) and its gradient
+        oo = torch.from_numpy(g["distance_o"]).requires_grad_(True)
+        d = ko.euclidean_distance_loss(oo, t[0])
+        assert abs(d.item() - float(g["distance"])) <= 1e-6 * float(g["distance"])
+        d.backward()
+        np.testing.assert_allclose(oo.grad.numpy(), g["distance_grad"], rtol=1e-5, atol=1e-7)
