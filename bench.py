@@ -157,7 +157,7 @@ def gpu_run(args):
         opt.grad_scale = 1.0 / world
         dist.broadcast(m.flat_params, src=0)
     # single GPU: the step is captured once per input slot as a CUDA graph and replayed (train.TrainStep use_graph)
-    step = train.TrainStep(m, opt, criterion="mse", reducer=reducer, use_graph=use_graph)
+    step = train.TrainStep(m, opt, criterion="mse", reducer=reducer, use_graph=use_graph, streams=args.streams)
 
     # a ring of distinct synthetic batches (pinned host copies + device-resident copies)
     ring = 4
@@ -222,8 +222,9 @@ def gpu_run(args):
     eng.set_profiling(True)
     prof_steps = 3
     acc = {}
+    prof_step = step if args.streams == 1 else train.TrainStep(m, opt, criterion="mse", reducer=reducer, use_graph=False)
     for i in range(prof_steps):
-        step._eager(*devb[i % ring])   # kernel by kernel: the events sit between the launches
+        prof_step._eager(*devb[i % ring])   # kernel by kernel, one stream: the events sit between the launches
         torch.cuda.synchronize()
         for k, (pms, n, fl) in eng.profile().items():
             a = acc.setdefault(k, [0.0, 0, 0.0])
@@ -266,7 +267,7 @@ def gpu_run(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"A1 train step (fwd+loss+bwd+Adam), B={B_PER_GPU}/GPU x T={T} x K={KP}, H={H} L={L}+{L} "
                                f"heads={NH} ff=2048, random missing blocks (AUTSL stats), BASELINE configs[1]",
-                   "parallelism": f"dp{world}", "global_batch": B_PER_GPU * world, "cuda_graph": bool(use_graph),
+                   "parallelism": f"dp{world}", "global_batch": B_PER_GPU * world, "cuda_graph": bool(use_graph), "streams": args.streams,
                    "l2": "no flush needed: each step streams ~3 GB of activations/weights (>> 126 MB L2); a ring of "
                          f"{ring} distinct device-resident batches",
                    "model_flops_per_seq": flops_per_seq_train(),
@@ -302,6 +303,7 @@ def main():
     ap.add_argument("--impl", default="kit", choices=["kit", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs under ncu)")
     ap.add_argument("--no-framepass", action="store_true", help="skip the pre-pass / loss HBM roofline leg")
+    ap.add_argument("--streams", type=int, default=1, help="concurrent sub-batch chains per step (train.TrainStep streams)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying its CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -225,6 +225,14 @@ int kit_gemm_bf16(int32_t mode, const void* A, int64_t lda, const void* B, int64
                   int32_t M, int32_t N, int32_t K, const float* bias, const void* addend, int64_t ld_addend,
                   int32_t out_kind, int32_t act, void* aux, int64_t ld_aux, int32_t split_k, void* stream);
 
+/* The feed-forward block of a post-norm layer in one kernel (torch/nn/modules/transformer.py:956-959):
+ * s = x + linear2(gelu(linear1(x))), y = LayerNorm(s) * gamma + beta, per-row mean / rstd of s.  H must be 256, FF a
+ * multiple of 128.  x, s, y: bf16 [M,H]; w1 [FF,H], w2 [H,FF] bf16 row-major; store_zh != 0 also writes the
+ * pre-activation z and the activation hh (bf16 [M,FF]) that the backward pass reads. */
+int kit_ffn_fwd(const void* x, const void* w1, const void* w2, const float* b1, const float* b2, const float* gamma,
+                const float* beta, void* z, void* hh, void* s, void* y, float* mean, float* rstd, int32_t M, int32_t H,
+                int32_t FF, int32_t store_zh, void* stream);
+
 /* softmax(Q K^T / sqrt(d) + mask) V for B*NH heads.  q/k/v: bf16, element (b, t, h, c) at
  * ptr + (b*S + t)*ld + h*d + c.  out: bf16 [B*Sq, NH*d] (ld_o).  lse: fp32 [B, NH, Sq]. */
 int kit_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,

@@ -8,6 +8,7 @@
 #include "attention.cuh"
 #include "gemm_sm100.cuh"
 #include "gemm_wgrad_group.cuh"
+#include "ffn_fused.cuh"
 #include "rowops.cuh"
 
 namespace kit {
@@ -220,6 +221,9 @@ struct KitEngine {
   std::vector<GemmPlan> fwd_plans, bwd_plans;
   std::vector<WgradGroupPlan> group_plans;   // one per layer of the backward (grouped stream-K weight gradients)
   size_t group_cursor = 0;
+  std::vector<FfnPlan> ffn_plans;            // one per layer of the forward (fused feed-forward block)
+  size_t ffn_cursor = 0;
+  bool fuse_ffn = true;
   size_t cursor = 0;
   std::vector<GemmPlan>* active = nullptr;
   int64_t launches = 0;
@@ -509,6 +513,30 @@ static int flush_wgrads(KitEngine* e, std::vector<PendingW>& pend) {
   return rc;
 }
 
+// s = x + linear2(gelu(linear1(x))) ; y = LN(s): one fused kernel (ffn_fused.cuh) when the shape allows, else two GEMMs.
+// z / hh (pre-activation / activation, [M, FF]) are written only when the engine keeps activations for a backward pass.
+static int ffn_block_fwd(KitEngine* e, const bf16* x, const LinearW& l1, const LinearW& l2, bf16* z, bf16* hh, bf16* s,
+                         const LNW& n, bf16* y, float* stats) {
+  const int H = e->L.cfg.hidden, FF = e->L.cfg.ff;
+  const int64_t M = e->M;
+  if (e->fuse_ffn && ffn_fwd_supported(H, FF)) {
+    if (e->ffn_cursor >= e->ffn_plans.size()) {
+      FfnPlan plan;
+      KIT_TRY(ffn_fwd_plan(&plan, x, H, e->wb + l1.wb, l1.ld, e->wb + l2.wb, l2.ld, e->params + l1.b, e->params + l2.b, z, hh, FF,
+                           s, H, y, H, e->params + n.g, e->params + n.b, stats, stats + M, 1e-5f, (int)M, H, FF, e->training));
+      e->ffn_plans.push_back(plan);
+    }
+    const FfnPlan& plan = e->ffn_plans[e->ffn_cursor++];
+    e->launches++;
+    prof_begin(e, KIT_PROF_GEMM_TN, 4.0 * (double)M * H * FF);
+    const int rc = ffn_fwd_launch(&plan, e->st);
+    prof_end(e);
+    return rc;
+  }
+  KIT_TRY(linear_fwd(e, x, H, l1, 0, FF, hh, FF, nullptr, 0, ACT_GELU, z, FF));
+  return linear_add_ln_fwd(e, hh, FF, l2, s, x, n, y, stats);
+}
+
 static int swiglu_fwd(KitEngine* e, const bf16* x, const SwiW& s, bf16* x12, bf16* g, bf16* out) {
   const int H = e->L.cfg.hidden;
   KIT_TRY(linear_fwd(e, x, H, s.fc12, 0, 2 * H, x12, 2 * H, nullptr, 0));
@@ -536,6 +564,7 @@ static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const f
   const int64_t M = e->M;
   e->active = &e->fwd_plans;
   e->cursor = 0;
+  e->ffn_cursor = 0;
   e->launches = 0;
   prof_reset(e);
   e->enc_mask = em ? *em : KitAttnMask{};
@@ -564,8 +593,7 @@ static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const f
     KIT_TRY(linear_fwd(e, x, H, w.sa.in, 0, 3 * H, a.qkv, 3 * H, nullptr, 0));
     KIT_TRY(eattn_fwd(e, a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, a.lse, &e->enc_mask));
     KIT_TRY(linear_add_ln_fwd(e, a.ao, H, w.sa.out, a.s1, x, w.n1, a.x1, a.st1));
-    KIT_TRY(linear_fwd(e, a.x1, H, w.l1, 0, FF, a.hh, FF, nullptr, 0, ACT_GELU, a.z, FF));
-    KIT_TRY(linear_add_ln_fwd(e, a.hh, FF, w.l2, a.s2, a.x1, w.n2, a.x2, a.st2));
+    KIT_TRY(ffn_block_fwd(e, a.x1, w.l1, w.l2, a.z, a.hh, a.s2, w.n2, a.x2, a.st2));
     x = a.x2;
   }
   e->launches++;
@@ -583,8 +611,7 @@ static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const f
     KIT_TRY(linear_fwd(e, e->mem, H, w.ca.in, H, 2 * H, a.kvc, 2 * H, nullptr, 0));
     KIT_TRY(eattn_fwd(e, a.qc, H, a.kvc, 2 * H, a.kvc + H, 2 * H, a.aoc, H, a.lsec, nullptr));
     KIT_TRY(linear_add_ln_fwd(e, a.aoc, H, w.ca.out, a.s2, a.y1, w.n2, a.y2, a.st2));
-    KIT_TRY(linear_fwd(e, a.y2, H, w.l1, 0, FF, a.hh, FF, nullptr, 0, ACT_GELU, a.z, FF));
-    KIT_TRY(linear_add_ln_fwd(e, a.hh, FF, w.l2, a.s3, a.y2, w.n3, a.y3, a.st3));
+    KIT_TRY(ffn_block_fwd(e, a.y2, w.l1, w.l2, a.z, a.hh, a.s3, w.n3, a.y3, a.st3));
     y = a.y3;
   }
   e->launches++;
@@ -809,6 +836,11 @@ extern "C" int kit_engine_bind(KitEngine* e, float* params, float* grads, void* 
   e->fwd_plans.clear();
   e->bwd_plans.clear();
   e->group_plans.clear();
+  e->ffn_plans.clear();
+  {
+    const char* v = getenv("KIT_FUSE_FFN");   // KIT_FUSE_FFN=0: the two-GEMM path (A/B measurements)
+    e->fuse_ffn = !(v != nullptr && v[0] == '0');
+  }
   // upload the weight-refresh tables (synchronous, bind time only)
   std::vector<int> prefix(e->L.wdescs.size() + 1, 0);
   for (size_t i = 0; i < e->L.wdescs.size(); ++i) {
@@ -886,6 +918,17 @@ extern "C" int kit_engine_profile_read(KitEngine* e, int32_t category, float* ms
   if (launches) *launches = e->cat_launches[category];
   if (flops) *flops = e->cat_flops[category];
   return KIT_OK;
+}
+
+// The fused feed-forward block on its own (tests): x [M,256] bf16, w1 [FF,256], w2 [256,FF] bf16 row-major,
+// s / y [M,256] bf16, z / hh [M,FF] bf16 (written when store_zh), mean / rstd [M] fp32.
+extern "C" int kit_ffn_fwd(const void* x, const void* w1, const void* w2, const float* b1, const float* b2, const float* gamma,
+                           const float* beta, void* z, void* hh, void* s, void* y, float* mean, float* rstd, int32_t M,
+                           int32_t H, int32_t FF, int32_t store_zh, void* stream) {
+  FfnPlan plan;
+  KIT_TRY(ffn_fwd_plan(&plan, (const bf16*)x, H, (const bf16*)w1, H, (const bf16*)w2, FF, b1, b2, (bf16*)z, (bf16*)hh, FF, (bf16*)s,
+                       H, (bf16*)y, H, gamma, beta, mean, rstd, 1e-5f, M, H, FF, store_zh));
+  return ffn_fwd_launch(&plan, (cudaStream_t)stream);
 }
 
 extern "C" int kit_gemm_bf16(int32_t mode, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,

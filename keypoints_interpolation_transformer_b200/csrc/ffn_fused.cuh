@@ -1,0 +1,469 @@
+// Fused feed-forward block of a post-norm transformer layer (torch/nn/modules/transformer.py:956-959, 1147-1153):
+//
+//     s = x + linear2(gelu(linear1(x)));   y = LayerNorm(s)
+//
+// in ONE kernel for the model width H = 256: the [rows, FF] hidden activation never makes the HBM round trip between the two
+// GEMMs.  A CTA pair owns 256 token rows (128 per CTA, tcgen05.mma.cta_group::2).  The x tile [128 x 256] stays in shared
+// memory for the whole item: it is the A operand of GEMM1 and the residual of the final epilogue.  The hidden dimension is
+// walked in chunks of 128 columns:
+//
+//     GEMM1(c):  acc1[c & 1] (TMEM, 128 columns, double-buffered) = x . W1[c]^T                 K = 256
+//     EPI1(c):   16 epilogue warps: tcgen05.ld -> + b1 -> GELU -> bf16 -> shared memory in the 128B-swizzled K-major layout
+//                the tensor core reads (the chunk is the A operand of GEMM2); when the step trains, the same tiles (and the
+//                pre-activation z) leave by TMA store for the backward pass
+//     GEMM2(c):  acc2 (TMEM, 256 columns) += h[c] . W2[:, c]^T                                   K = 128
+//
+// issued as GEMM1(c+1) before GEMM2(c) so that EPI1(c) overlaps GEMM1(c+1) on the tensor pipe.  Both weight streams come
+// through one ring of 16 KB slots (each CTA stages HALF of every B tile).  The final epilogue is the EPI_ADD_LN epilogue of
+// gemm_sm100.cuh (bias + residual, bf16 sum out, two-pass row statistics across the four column-group warps, LayerNorm out).
+// Persistent over 256-row items.
+#pragma once
+#include "gemm_sm100.cuh"
+
+namespace kit {
+
+constexpr int FFN_H = 256;
+constexpr int FFN_FC = 128;
+constexpr int FFN_HBUFS = 1;   // h chunk buffers: what bounds the kernel is the depth of the weight ring (TMA latency), not EPI1 -> GEMM2
+constexpr int FFN_RING = FFN_HBUFS == 1 ? 5 : 3;
+constexpr int FFN_SLOT = 16384;
+constexpr int FFN_X_BYTES = 65536;   // [128 x 256] bf16: four [128 x 64] k-blocks
+constexpr int FFN_HC_BYTES = 32768;  // [128 x 128] bf16: two [128 x 64] k-blocks
+constexpr int FFN_STATS = 4096;
+constexpr int FFN_EPI_WARPS = 16;
+constexpr int FFN_THREADS = 64 + 32 * FFN_EPI_WARPS;
+constexpr int FFN_SMEM = FFN_X_BYTES + FFN_RING * FFN_SLOT + (FFN_HBUFS + 1) * FFN_HC_BYTES + FFN_STATS + 1024 + 1024;   // h[HBUFS], z
+
+struct FfnParams {
+  int M, FF, n_items;
+  const float* b1;
+  const float* b2;
+  const float* ln_gamma;
+  const float* ln_beta;
+  float* ln_mean;
+  float* ln_rstd;
+  float ln_eps;
+  int store_zh;   // training: the pre-activation z and the activation h leave for the backward pass
+  int dbg;            // experiments only (KIT_FFN_DBG bit mask: parts of the kernel switched off for timing)
+  long long* trace;   // experiments only (KIT_FFN_TRACE): clock64 marks of CTA 0, first item; see kit_ffn_trace_read
+};
+struct FfnPlan {
+  CUtensorMap tmX, tmW1, tmW2, tmZ, tmHh, tmS, tmY;
+  FfnParams p;
+  int grid;
+};
+
+#ifdef KIT_FFN_IMPL   // the kernel is compiled into gemm.cu only
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// acquire at cluster scope: the arrivals come from the peer CTA after it wrote ITS shared memory
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 24)) {
+      printf("kit: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+// relaxed remote arrive: the data the barrier guards is ordered by tcgen05 fences (TMEM) or by fence.proxy.async (this CTA's
+// shared memory, read by the tensor core) -- a release fence at cluster scope per arrival costs ~1000 cycles per warp per chunk
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+__global__ void __launch_bounds__(FFN_THREADS, 1) ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                 const __grid_constant__ CUtensorMap tmW1,
+                                                                 const __grid_constant__ CUtensorMap tmW2,
+                                                                 const __grid_constant__ CUtensorMap tmZ,
+                                                                 const __grid_constant__ CUtensorMap tmHh,
+                                                                 const __grid_constant__ CUtensorMap tmS,
+                                                                 const __grid_constant__ CUtensorMap tmY, const FfnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* x_s = smem;
+  uint8_t* ring = x_s + FFN_X_BYTES;
+  uint8_t* h_s = ring + FFN_RING * FFN_SLOT;
+  uint8_t* z_s = h_s + FFN_HBUFS * FFN_HC_BYTES;   // h is double-buffered: EPI1(c + 1) does not wait for GEMM2(c)
+  float2* ln_stats = reinterpret_cast<float2*>(z_s + FFN_HC_BYTES);
+  uint64_t* ring_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ln_stats) + FFN_STATS);
+  uint64_t* ring_empty = ring_full + FFN_RING;
+  uint64_t* x_full = ring_empty + FFN_RING;
+  uint64_t* x_empty = x_full + 1;
+  uint64_t* acc1_full = x_empty + 1;    // [2]
+  uint64_t* acc1_empty = acc1_full + 2; // [2]
+  uint64_t* h_full = acc1_empty + 2;    // [2]
+  uint64_t* h_empty = h_full + 2;       // [2]
+  uint64_t* acc2_full = h_empty + 2;
+  uint64_t* acc2_empty = acc2_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
+  constexpr int N_BARS = 2 * FFN_RING + 12;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int first_item = blockIdx.x >> 1, item_stride = gridDim.x >> 1;
+  const int NC = p.FF / FFN_FC;
+  auto mark = [&](int slot) {
+    if (p.trace != nullptr && blockIdx.x < 2 && lane == 0 && slot < 128) p.trace[blockIdx.x * 128 + slot] = clock64();
+  };
+  if (warp == 0) mark(0);
+
+  if (warp == 0) {
+    pdl_launch_dependents();
+    if (lane == 0) {
+      tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+      tma_prefetch_desc(&tmS); tma_prefetch_desc(&tmY);
+      if (p.store_zh) { tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmHh); }
+    }
+    for (int i = lane; i < N_BARS; i += 32) {
+      uint64_t* b = &ring_full[i];
+      uint32_t count = 1;
+      if (b == x_empty) count = FFN_EPI_WARPS;
+      else if (b == acc1_empty || b == acc1_empty + 1 || b == h_full || b == h_full + 1 || b == acc2_empty) count = 2 * FFN_EPI_WARPS;
+      mbar_init(b, count);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc_cg2<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer: the x tile, then the two weight streams
+    if (lane == 0) {
+      uint32_t cnt = 0, it = 0;
+      auto slot_acquire = [&](uint32_t& s) {
+        s = cnt % FFN_RING;
+        mbar_wait(&ring_empty[s], ((cnt / FFN_RING) & 1) ^ 1);
+        if (rank == 0) mbar_arrive_expect_tx(&ring_full[s], 2 * FFN_SLOT);
+        ++cnt;
+      };
+      auto load_w1 = [&](int c) {   // W1 rows [c*128 + rank*64, +64), two 64-wide k-blocks per slot
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint32_t s;
+          slot_acquire(s);
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            tma_load_2d_cg2(ring + s * FFN_SLOT + kk * 8192, &tmW1, &ring_full[s], (2 * j + kk) * 64, c * FFN_FC + rank * 64);
+        }
+      };
+      auto load_w2 = [&](int c) {   // W2 rows [rank*128, +128), k columns [c*128 + j*64, +64)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint32_t s;
+          slot_acquire(s);
+          tma_load_2d_cg2(ring + s * FFN_SLOT, &tmW2, &ring_full[s], c * FFN_FC + j * 64, rank * 128);
+        }
+      };
+      for (int item = first_item; item < p.n_items; item += item_stride, ++it) {
+        const int m0 = (item * 2 + rank) * 128;
+        mbar_wait(x_empty, (it & 1) ^ 1);   // the final epilogue of the previous item has read the residual
+        if (it == 0) pdl_wait();
+        if (rank == 0) mbar_arrive_expect_tx(x_full, 2 * FFN_X_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d_cg2(x_s + kb * 16384, &tmX, x_full, kb * 64, m0);
+        load_w1(0);
+        for (int c = 0; c < NC; ++c) {
+          if (c + 1 < NC) load_w1(c + 1);
+          load_w2(c);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc1 = make_idesc_bf16(256, FFN_FC, false, false);
+      constexpr uint32_t idesc2 = make_idesc_bf16(256, FFN_H, false, false);
+      const uint32_t x_base = smem_u32(x_s), h_base = smem_u32(h_s), ring_base = smem_u32(ring);
+      uint32_t cnt = 0, gc = 0, hc = 0, it = 0;
+      auto slot_wait = [&](uint32_t& s) {
+        s = cnt % FFN_RING;
+        mbar_wait(&ring_full[s], (cnt / FFN_RING) & 1);
+        tc_fence_after();
+        ++cnt;
+      };
+      auto gemm2 = [&](int c) {
+        if (c == 0) {
+          mbar_wait(acc2_empty, (it & 1) ^ 1);   // the final epilogue of the previous item has drained acc2
+          tc_fence_after();
+        }
+        const uint32_t hb = FFN_HBUFS == 2 ? (hc & 1) : 0;
+        mbar_wait_cluster(&h_full[hb], (FFN_HBUFS == 2 ? (hc >> 1) : hc) & 1);   // both CTAs' epilogue warps have written (and fenced) their half of h[c]
+        tc_fence_after();
+        if (it == 0) mark(17 + c);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint32_t s;
+          slot_wait(s);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(h_base + hb * FFN_HC_BYTES + j * 16384 + k * 32, 0, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(ring_base + s * FFN_SLOT + k * 32, 0, 1024);
+            if (!(p.dbg & 2)) umma_bf16_cg2(tmem_base + 256, adesc, bdesc, idesc2, (c > 0 || j > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_cg2(&ring_empty[s], (uint16_t)3);
+        }
+        umma_commit_cg2(&h_empty[hb], (uint16_t)3);
+        ++hc;
+      };
+      for (int item = first_item; item < p.n_items; item += item_stride, ++it) {
+        mbar_wait(x_full, it & 1);
+        tc_fence_after();
+        for (int c = 0; c < NC; ++c, ++gc) {
+          const uint32_t b = gc & 1;
+          mbar_wait(&acc1_empty[b], ((gc >> 1) & 1) ^ 1);   // EPI1 two chunks ago has drained this accumulator
+          tc_fence_after();
+          if (it == 0) mark(1 + c);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint32_t s;
+            slot_wait(s);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const int kb = 2 * j + kk;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t adesc = make_smem_desc_sw128(x_base + kb * 16384 + k * 32, 0, 1024);
+                const uint64_t bdesc = make_smem_desc_sw128(ring_base + s * FFN_SLOT + kk * 8192 + k * 32, 0, 1024);
+                if (!(p.dbg & 4)) umma_bf16_cg2(tmem_base + b * FFN_FC, adesc, bdesc, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit_cg2(&ring_empty[s], (uint16_t)3);
+          }
+          umma_commit_cg2(&acc1_full[b], (uint16_t)3);
+          if (c >= 1) gemm2(c - 1);
+        }
+        gemm2(NC - 1);
+        umma_commit_cg2(acc2_full, (uint16_t)3);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;            // TMEM lane quadrant: rows [32q, 32q + 32) of this CTA's tile
+    const int cg = (warp - 2) >> 2;    // EPI1: 32-column group of the chunk; final epilogue: 64-column group of the row
+    const int row = q * 32 + lane;
+    const uint32_t sw = row & 7;
+    const int pair_bar = 1 + q * 2 + (cg >> 1);     // the two warps that fill one [32 x 64] tile of h / z
+    const bool issuer = (cg & 1) == 0;
+    const uint32_t hz_off = (cg >> 1) * 16384 + row * 128;   // this lane's row in the chunk's k-block tile
+    const uint32_t tile_off = (cg >> 1) * 16384 + q * 4096;  // the [32 x 64] tile this warp pair fills
+    const uint32_t h_u32 = smem_u32(h_s), z_u32 = smem_u32(z_s), x_u32 = smem_u32(x_s);
+    uint32_t gc = 0, it = 0;
+    for (int item = first_item; item < p.n_items; item += item_stride, ++it) {
+      const int m0 = (item * 2 + rank) * 128;
+      const int row0 = m0 + q * 32;
+      if (it == 0) pdl_wait();
+      for (int c = 0; c < NC; ++c, ++gc) {
+        const uint32_t b = gc & 1;
+        mbar_wait(&acc1_full[b], (gc >> 1) & 1);
+        tc_fence_after();
+        if (it == 0 && warp == 2) mark(33 + c);
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(b * FFN_FC + cg * 32), r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(&acc1_empty[b]); else mbar_arrive_cluster_relaxed(&acc1_empty[b], 0);
+        }
+        const int col0 = c * FFN_FC + cg * 32;   // hidden unit of r[0]
+        uint32_t zp[16], hp[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[8 * i + u]);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b1 + col0 + 8 * i));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.b1 + col0 + 8 * i + 4));
+          add_pair(v[0], v[1], b0.x, b0.y); add_pair(v[2], v[3], b0.z, b0.w);
+          add_pair(v[4], v[5], b1.x, b1.y); add_pair(v[6], v[7], b1.z, b1.w);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) zp[4 * i + u] = pack_bf16(v[2 * u], v[2 * u + 1]);
+          if (!(p.dbg & 1)) { gelu_pair(v[0], v[1]); gelu_pair(v[2], v[3]); gelu_pair(v[4], v[5]); gelu_pair(v[6], v[7]); }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) hp[4 * i + u] = pack_bf16(v[2 * u], v[2 * u + 1]);
+        }
+        if (it == 0 && warp == 2) mark(49 + c);
+        const uint32_t hb = FFN_HBUFS == 2 ? b : 0;
+        mbar_wait(&h_empty[hb], ((FFN_HBUFS == 2 ? (gc >> 1) : gc) & 1) ^ 1);   // the GEMM2 that last read this h buffer is done
+        if (it == 0 && warp == 2) mark(65 + c);
+        if (p.store_zh) {   // ... and so have the TMA stores of the previous chunk's h / z tiles
+          if (issuer && lane == 0) tma_store_wait_read_n<0>();
+          named_bar_sync(pair_bar, 64);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t off = hz_off + ((uint32_t((cg & 1) * 4 + i) ^ sw) << 4);
+          if (!(p.dbg & 8)) sts128(h_u32 + hb * FFN_HC_BYTES + off, hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]);
+          if (p.store_zh) sts128(z_u32 + off, zp[4 * i], zp[4 * i + 1], zp[4 * i + 2], zp[4 * i + 3]);
+        }
+        if (!(p.dbg & 16)) fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(&h_full[hb]); else mbar_arrive_cluster_relaxed(&h_full[hb], 0);
+        }
+        if (it == 0 && warp == 2) mark(81 + c);
+        if (it == 0 && warp == 17) mark(101 + c);
+        if (p.store_zh) {
+          named_bar_sync(pair_bar, 64);
+          if (issuer && lane == 0) {
+            const int gcol = c * FFN_FC + (cg >> 1) * 64;
+            tma_store_2d_a(&tmHh, h_u32 + hb * FFN_HC_BYTES + tile_off, gcol, row0);
+            tma_store_2d_a(&tmZ, z_u32 + tile_off, gcol, row0);
+            tma_store_commit();
+          }
+        }
+      }
+      // ---- final epilogue: s = acc2 + b2 + x ; y = LN(s)   (cg = 64-column group of the 256-wide row)
+      mbar_wait(acc2_full, it & 1);
+      tc_fence_after();
+      if (it == 0 && warp == 2) mark(97);
+      if (p.store_zh && issuer && lane == 0) tma_store_wait_read_n<0>();
+      named_bar_sync(13, 32 * FFN_EPI_WARPS);   // every h / z tile has been read: the region becomes the staging tiles
+      const uint32_t t_sub[2] = {h_u32 + uint32_t(warp - 2) * 4096, h_u32 + uint32_t(warp - 2) * 4096 + 2048};
+      const uint32_t tmem_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(256 + cg * 64);
+      const int colg = cg * 64;
+      uint32_t sreg[2][16];
+      float rsum = 0.f;
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        uint32_t r[32];
+        tmem_ld32(tmem_row + uint32_t(sub * 32), r);
+        tmem_ld_wait();
+        if (sub == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(acc2_empty); else mbar_arrive_cluster_relaxed(acc2_empty, 0);
+          }
+        }
+        const int col0 = colg + sub * 32;
+        const uint32_t row64 = t_sub[sub] + lane * 64, sw64 = (lane >> 1) & 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[8 * i + u]);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b2 + col0 + 8 * i));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.b2 + col0 + 8 * i + 4));
+          add_pair(v[0], v[1], b0.x, b0.y); add_pair(v[2], v[3], b0.z, b0.w);
+          add_pair(v[4], v[5], b1.x, b1.y); add_pair(v[6], v[7], b1.z, b1.w);
+          // residual: x[row, col0 + 8i ..] sits in k-block cg of the x tile, 16-byte chunk sub*4 + i of the 128-byte row
+          const uint4 in = lds128(x_u32 + cg * 16384 + row * 128 + ((uint32_t(sub * 4 + i) ^ sw) << 4));
+          const float2 a = unpack_bf16(in.x), bb = unpack_bf16(in.y), cc = unpack_bf16(in.z), d = unpack_bf16(in.w);
+          add_pair(v[0], v[1], a.x, a.y); add_pair(v[2], v[3], bb.x, bb.y);
+          add_pair(v[4], v[5], cc.x, cc.y); add_pair(v[6], v[7], d.x, d.y);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t pk = pack_bf16(v[2 * u], v[2 * u + 1]);
+            sreg[sub][4 * i + u] = pk;
+            const float2 f = unpack_bf16(pk);
+            rsum += f.x + f.y;
+          }
+          sts128(row64 + ((i ^ sw64) << 4), sreg[sub][4 * i], sreg[sub][4 * i + 1], sreg[sub][4 * i + 2], sreg[sub][4 * i + 3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d_a(&tmS, t_sub[sub], col0, row0);
+          tma_store_commit();
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_empty);   // the residual has been read: the producer may load the next item's x
+      const int rl = q * 32 + lane;
+      ln_stats[cg * 128 + rl].x = rsum;
+      named_bar_sync(9 + q, 128);
+      const float mean = (ln_stats[rl].x + ln_stats[128 + rl].x + ln_stats[256 + rl].x + ln_stats[384 + rl].x) * (1.f / 256.f);
+      float rsq = 0.f;
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float2 f = unpack_bf16(sreg[sub][u]);
+          const float dx = f.x - mean, dy = f.y - mean;
+          rsq = fmaf(dx, dx, fmaf(dy, dy, rsq));
+        }
+      ln_stats[cg * 128 + rl].y = rsq;
+      named_bar_sync(9 + q, 128);
+      const float var = (ln_stats[rl].y + ln_stats[128 + rl].y + ln_stats[256 + rl].y + ln_stats[384 + rl].y) * (1.f / 256.f);
+      const float rstd = rsqrtf(var + p.ln_eps);
+      named_bar_sync(9 + q, 128);
+      if (cg == 0 && row0 + lane < p.M) {
+        p.ln_mean[row0 + lane] = mean;
+        p.ln_rstd[row0 + lane] = rstd;
+      }
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int col0 = colg + sub * 32;
+        const uint32_t row64 = t_sub[sub] + lane * 64, sw64 = (lane >> 1) & 3;
+        if (lane == 0) tma_store_wait_read_n<1>();   // the store of s from this tile has read it
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 f = unpack_bf16(sreg[sub][4 * i + u]);
+            v[2 * u] = (f.x - mean) * rstd;
+            v[2 * u + 1] = (f.y - mean) * rstd;
+          }
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + 8 * i));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + 8 * i + 4));
+          const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col0 + 8 * i));
+          const float4 e1 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col0 + 8 * i + 4));
+          v[0] = fmaf(v[0], g0.x, e0.x); v[1] = fmaf(v[1], g0.y, e0.y); v[2] = fmaf(v[2], g0.z, e0.z); v[3] = fmaf(v[3], g0.w, e0.w);
+          v[4] = fmaf(v[4], g1.x, e1.x); v[5] = fmaf(v[5], g1.y, e1.y); v[6] = fmaf(v[6], g1.z, e1.z); v[7] = fmaf(v[7], g1.w, e1.w);
+          sts128(row64 + ((i ^ sw64) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d_a(&tmY, t_sub[sub], col0, row0);
+          tma_store_commit();
+        }
+      }
+      // the staging tiles go back to being h / z: their stores must have read them before the next item's EPI1 writes
+      if (item + item_stride < p.n_items) {
+        if (lane == 0) tma_store_wait_read_n<0>();
+        named_bar_sync(13, 32 * FFN_EPI_WARPS);
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+    if (warp == 2) mark(98);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_cg2<512>(tmem_base);
+  if (warp == 0) mark(99);
+}
+
+#endif  // KIT_FFN_IMPL
+
+int ffn_fwd_plan(FfnPlan* plan, const bf16* x, int64_t ldx, const bf16* w1, int64_t ldw1, const bf16* w2, int64_t ldw2,
+                 const float* b1, const float* b2, bf16* z, bf16* hh, int64_t ldzh, bf16* s, int64_t lds, bf16* y, int64_t ldy,
+                 const float* gamma, const float* beta, float* mean, float* rstd, float eps, int M, int H, int FF, int store_zh);
+bool ffn_fwd_supported(int H, int FF);
+int ffn_fwd_launch(const FfnPlan* plan, cudaStream_t stream);
+
+}  // namespace kit

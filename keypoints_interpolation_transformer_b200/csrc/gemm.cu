@@ -2,6 +2,8 @@
 #include "gemm_sm100.cuh"
 #define KIT_WGRAD_GROUP_IMPL
 #include "gemm_wgrad_group.cuh"
+#define KIT_FFN_IMPL
+#include "ffn_fused.cuh"
 
 #include <mutex>
 #include <cstdlib>
@@ -310,7 +312,78 @@ int wgrad_group_launch(const WgradGroupPlan* plan, cudaStream_t stream) {
   return KIT_OK;
 }
 
+// ---------------------------------------------------------------- fused feed-forward block (ffn_fused.cuh)
+static long long* g_ffn_trace = nullptr;
+bool ffn_fwd_supported(int H, int FF) { return H == FFN_H && FF >= FFN_FC && FF % FFN_FC == 0; }
+
+int ffn_fwd_plan(FfnPlan* plan, const bf16* x, int64_t ldx, const bf16* w1, int64_t ldw1, const bf16* w2, int64_t ldw2,
+                 const float* b1, const float* b2, bf16* z, bf16* hh, int64_t ldzh, bf16* s, int64_t lds, bf16* y, int64_t ldy,
+                 const float* gamma, const float* beta, float* mean, float* rstd, float eps, int M, int H, int FF, int store_zh) {
+  KIT_REQUIRE(ffn_fwd_supported(H, FF), "fused FFN: H must be %d and FF a multiple of %d (got %d, %d)", FFN_H, FFN_FC, H, FF);
+  KIT_REQUIRE(M > 0 && x && w1 && w2 && b1 && b2 && s && y && gamma && beta && mean && rstd, "fused FFN: null argument");
+  KIT_REQUIRE(!store_zh || (z != nullptr && hh != nullptr), "fused FFN: training needs the z and h output tensors");
+  KIT_REQUIRE(aligned16(b1, 0, 4) && aligned16(b2, 0, 4) && aligned16(gamma, 0, 4) && aligned16(beta, 0, 4),
+              "fused FFN: bias / LayerNorm vectors must be 16-byte aligned");
+  int rc = gemm_init_attributes();
+  if (rc) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, []() { attr_err = cudaFuncSetAttribute(ffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FFN_SMEM); });
+  KIT_REQUIRE(attr_err == cudaSuccess, "fused FFN: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  if ((rc = make_tensor_map_2d(&plan->tmX, x, (uint64_t)H, (uint64_t)M, (uint64_t)ldx * 2, 64, 128))) return rc;
+  if ((rc = make_tensor_map_2d(&plan->tmW1, w1, (uint64_t)H, (uint64_t)FF, (uint64_t)ldw1 * 2, 64, 64))) return rc;
+  if ((rc = make_tensor_map_2d(&plan->tmW2, w2, (uint64_t)FF, (uint64_t)H, (uint64_t)ldw2 * 2, 64, 128))) return rc;
+  plan->tmZ = plan->tmX;
+  plan->tmHh = plan->tmX;
+  if (store_zh) {
+    if ((rc = make_tensor_map_2d(&plan->tmZ, z, (uint64_t)FF, (uint64_t)M, (uint64_t)ldzh * 2, 64, 32))) return rc;
+    if ((rc = make_tensor_map_2d(&plan->tmHh, hh, (uint64_t)FF, (uint64_t)M, (uint64_t)ldzh * 2, 64, 32))) return rc;
+  }
+  if ((rc = make_tensor_map_2d_typed(&plan->tmS, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, s, (uint64_t)H, (uint64_t)M, (uint64_t)lds * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_tensor_map_2d_typed(&plan->tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, y, (uint64_t)H, (uint64_t)M, (uint64_t)ldy * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  FfnParams& p = plan->p;
+  p.M = M; p.FF = FF; p.n_items = (M + 255) / 256;
+  p.b1 = b1; p.b2 = b2; p.ln_gamma = gamma; p.ln_beta = beta; p.ln_mean = mean; p.ln_rstd = rstd; p.ln_eps = eps;
+  p.store_zh = store_zh;
+  p.trace = nullptr;
+  p.dbg = getenv("KIT_FFN_DBG") != nullptr ? atoi(getenv("KIT_FFN_DBG")) : 0;
+  if (getenv("KIT_FFN_TRACE") != nullptr) {
+    if (g_ffn_trace == nullptr && cudaMalloc(&g_ffn_trace, 256 * sizeof(long long)) != cudaSuccess) g_ffn_trace = nullptr;
+    if (g_ffn_trace != nullptr) cudaMemset(g_ffn_trace, 0, 256 * sizeof(long long));
+    p.trace = g_ffn_trace;
+  }
+  const int max_clusters = g_num_sms / 2;
+  plan->grid = (p.n_items < max_clusters ? p.n_items : max_clusters) * 2;
+  return KIT_OK;
+}
+
+int ffn_fwd_launch(const FfnPlan* plan, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan->grid);
+  cfg.blockDim = dim3(FFN_THREADS);
+  cfg.dynamicSmemBytes = FFN_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  KIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_fwd_kernel, plan->tmX, plan->tmW1, plan->tmW2, plan->tmZ, plan->tmHh, plan->tmS,
+                                    plan->tmY, plan->p));
+  return KIT_OK;
+}
+
 }  // namespace kit
+
+// experiments only: the 128 clock64 marks of CTA 0 of the last traced fused FFN launch (KIT_FFN_TRACE=1)
+extern "C" int kit_ffn_trace_read(long long* out128) {
+  if (kit::g_ffn_trace == nullptr) return KIT_ERR_INVALID;
+  return cudaMemcpy(out128, kit::g_ffn_trace, 256 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? KIT_OK : KIT_ERR_CUDA;
+}
 
 // experiments only: the 16 clock64 marks of CTA 0 of the last traced GEMM (KIT_GEMM_TRACE=1)
 extern "C" int kit_gemm_trace_read(long long* out16) {

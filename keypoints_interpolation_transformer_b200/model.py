@@ -166,10 +166,12 @@ class KeypointCompleter(nn.Module):
         return g
 
     # ------------------------------------------------------------------ engines
-    def engine_for(self, batch, seq_len, training):
+    def engine_for(self, batch, seq_len, training, slot=0):
+        """``slot``: independent engines (own workspace) of the same shape, one per concurrent stream of
+        ``train.TrainStep(streams=...)``."""
         if not self.flat_params.is_cuda:
             raise K.KitError("KeypointCompleter.forward needs a CUDA device: this build has no CPU path")
-        key = (batch, seq_len, bool(training))
+        key = (batch, seq_len, bool(training), slot)
         eng = self._engines.get(key)
         if eng is None:
             grads = self.ensure_flat_grads() if training else None

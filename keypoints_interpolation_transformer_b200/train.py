@@ -23,10 +23,19 @@ class TrainStep:
     inputs [B,T+1,K,2] (SOS + hold-filled frames), sota [B,T,K,2], mask [B,T+1] (A1_train.py:91-135).
 
     criterion: "mse" (A1_train.py:254) or "euclid" (A4_train_with_pretrained.py:259).
-    zero_masked: A4_train_with_pretrained.py:107-108.  reducer: parallel.BucketReducer or None."""
+    zero_masked: A4_train_with_pretrained.py:107-108.  reducer: parallel.BucketReducer or None.
 
-    def __init__(self, model, optimizer=None, criterion="mse", zero_masked=False, reducer=None, lr=5e-6, use_graph=False):
+    streams > 1: the batch is cut into that many equal sub-batches, each running forward + loss + backward through its own
+    engine on its own CUDA stream, all accumulating into the one gradient arena (the weight gradients are reduce-adds);
+    Adam follows the join.  Sequences are independent, so the result is the single-stream step's (up to the order of the
+    fp32 gradient sums).  At B = 256, T = 64 most kernels are one 128-row tile per SM and latency-bound (launch, first TMA
+    tile, tear-down): two half-size chains in flight fill each other's bubbles."""
+
+    def __init__(self, model, optimizer=None, criterion="mse", zero_masked=False, reducer=None, lr=5e-6, use_graph=False,
+                 streams=1):
         self.model = model
+        self.streams = int(streams)
+        self._side = None
         # data parallel: kernel by kernel (a graph holding NCCL collectives hung process-group teardown on 2 x B200)
         self.use_graph = use_graph and reducer is None
         self.optimizer = optimizer if optimizer is not None else FlatAdam(model, lr=lr, capturable=self.use_graph)
@@ -40,6 +49,65 @@ class TrainStep:
         self.pred = None
         self.last_launches = 0
 
+    def _forward_backward_split(self, inputs, sota, mask):
+        """The ``streams > 1`` step: fork the current stream into ``streams`` side streams, one sub-batch each, join."""
+        model, S = self.model, self.streams
+        B, T1 = inputs.shape[0], inputs.shape[1]
+        T = T1 - 1
+        K2 = inputs.shape[2] * inputs.shape[3]
+        Bs = B // S
+        if Bs * S != B:
+            raise K.KitError(f"TrainStep(streams={S}): batch {B} is not divisible by the number of streams")
+        grads = model.ensure_flat_grads()
+        if self._side is None:
+            self._side = [torch.cuda.Stream(device=inputs.device) for _ in range(S)]
+        if self.pred is None or self.pred.shape != (B, T, K2 // 2, 2):
+            self.pred = torch.empty(B, T, K2 // 2, 2, device=inputs.device)
+        main = torch.cuda.current_stream()
+        grads.zero_()                                            # optimizer.zero_grad()  (A1_train.py:133)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        losses, keep = [], []
+        launches = 1
+        pending = {}       # bucket -> events of the sub-streams that have finished it (data parallel)
+
+        def bucket_ready(b):
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.setdefault(b, []).append(ev)
+            if len(pending[b]) == S:
+                for e in pending[b]:
+                    main.wait_event(e)
+                with torch.cuda.stream(main):
+                    self.reducer.bucket_ready(b)
+
+        if self.reducer is not None:
+            self.reducer.begin()
+        for s, side in enumerate(self._side):
+            lo, hi = s * Bs, (s + 1) * Bs
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                eng = model.engine_for(Bs, T, training=True, slot=s)
+                inp, msk = inputs[lo:hi], mask[lo:hi]
+                enc_mask = make_mask(msk[:, :-1], K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD)
+                dec_mask = make_mask(msk[:, 1:], K.MASK_REPEAT_INC)
+                pred = self.pred[lo:hi]
+                eng.forward(inp, T1 * K2, inp[:, 1:], T1 * K2, enc_mask, dec_mask, pred, self.zero_masked)
+                loss, dpred = fused_loss(pred, sota[lo:hi], None, self.kind, want_grad=True, grad_scale=1.0 / S)
+                eng.backward(dpred, bucket_ready if self.reducer is not None else None)
+                losses.append(loss)
+                keep.append((dpred, enc_mask, dec_mask))
+                launches += eng.fwd_launches + eng.bwd_launches + 3
+                done = torch.cuda.Event()
+                done.record(side)
+            main.wait_event(done)
+        total = torch.stack(losses).sum() / S                    # mean over the batch = mean of the equal sub-batch means
+        if self.reducer is not None:
+            self.reducer.finish()
+        self._keep = keep
+        self.last_launches = launches + 2
+        return total
+
     def forward_backward(self, inputs, sota, mask):
         model = self.model
         B, T1 = inputs.shape[0], inputs.shape[1]
@@ -47,6 +115,8 @@ class TrainStep:
         K2 = inputs.shape[2] * inputs.shape[3]
         assert inputs.is_cuda and inputs.dtype == torch.float32 and inputs.is_contiguous()
         assert mask.dtype == torch.float32 and mask.is_contiguous() and sota.is_contiguous()
+        if self.streams > 1:
+            return self._forward_backward_split(inputs, sota, mask)
         eng = model.engine_for(B, T, training=True)
         grads = model.ensure_flat_grads()
         x_dec = inputs[:, 1:]                                   # A1_train.py:94 -- a pointer offset
