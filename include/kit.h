@@ -233,6 +233,11 @@ int kit_ffn_fwd(const void* x, const void* w1, const void* w2, const float* b1, 
                 const float* beta, void* z, void* hh, void* s, void* y, float* mean, float* rstd, int32_t M, int32_t H,
                 int32_t FF, int32_t store_zh, void* stream);
 
+/* Input gradients of that block in one kernel: dz = (g w2) * gelu'(z) -> dz [M,FF] (what the weight gradients read),
+ * dx = dz w1 + g -> dx [M,H] (g = gradient w.r.t. the pre-norm sum s).  w2t = w2^T [FF,H], w1t = w1^T [H,FF], bf16 row-major. */
+int kit_ffn_bwd(const void* g, const void* w2t, const void* w1t, const void* z, void* dz, void* dx, int32_t M, int32_t H,
+                int32_t FF, void* stream);
+
 /* softmax(Q K^T / sqrt(d) + mask) V for B*NH heads.  q/k/v: bf16, element (b, t, h, c) at
  * ptr + (b*S + t)*ld + h*d + c.  out: bf16 [B*Sq, NH*d] (ld_o).  lse: fp32 [B, NH, Sq]. */
 int kit_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,

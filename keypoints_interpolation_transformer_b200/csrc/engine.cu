@@ -221,8 +221,8 @@ struct KitEngine {
   std::vector<GemmPlan> fwd_plans, bwd_plans;
   std::vector<WgradGroupPlan> group_plans;   // one per layer of the backward (grouped stream-K weight gradients)
   size_t group_cursor = 0;
-  std::vector<FfnPlan> ffn_plans;            // one per layer of the forward (fused feed-forward block)
-  size_t ffn_cursor = 0;
+  std::vector<FfnPlan> ffn_plans, ffn_bwd_plans;   // one per layer of the forward / backward (fused feed-forward block)
+  size_t ffn_cursor = 0, ffn_bwd_cursor = 0;
   bool fuse_ffn = true;
   size_t cursor = 0;
   std::vector<GemmPlan>* active = nullptr;
@@ -529,12 +529,33 @@ static int ffn_block_fwd(KitEngine* e, const bf16* x, const LinearW& l1, const L
     const FfnPlan& plan = e->ffn_plans[e->ffn_cursor++];
     e->launches++;
     prof_begin(e, KIT_PROF_GEMM_TN, 4.0 * (double)M * H * FF);
-    const int rc = ffn_fwd_launch(&plan, e->st);
+    const int rc = ffn_launch(&plan, e->st);
     prof_end(e);
     return rc;
   }
   KIT_TRY(linear_fwd(e, x, H, l1, 0, FF, hh, FF, nullptr, 0, ACT_GELU, z, FF));
   return linear_add_ln_fwd(e, hh, FF, l2, s, x, n, y, stats);
+}
+
+// Input gradients of the same block: dz = (g W2) * gelu'(z) -> gff (kept for the weight gradients), dx = dz W1 + g.
+static int ffn_block_bwd(KitEngine* e, const bf16* g, const LinearW& l1, const LinearW& l2, const bf16* z, bf16* gff, bf16* dx) {
+  const int H = e->L.cfg.hidden, FF = e->L.cfg.ff;
+  const int64_t M = e->M;
+  if (e->fuse_ffn && ffn_fwd_supported(H, FF) && l2.wbT >= 0 && l1.wbT >= 0) {
+    if (e->ffn_bwd_cursor >= e->ffn_bwd_plans.size()) {
+      FfnPlan plan;
+      KIT_TRY(ffn_bwd_plan(&plan, g, H, e->wb + l2.wbT, l2.ldT, e->wb + l1.wbT, l1.ldT, z, gff, FF, dx, H, (int)M, H, FF));
+      e->ffn_bwd_plans.push_back(plan);
+    }
+    const FfnPlan& plan = e->ffn_bwd_plans[e->ffn_bwd_cursor++];
+    e->launches++;
+    prof_begin(e, KIT_PROF_GEMM_TN, 4.0 * (double)M * H * FF);
+    const int rc = ffn_launch(&plan, e->st);
+    prof_end(e);
+    return rc;
+  }
+  KIT_TRY(linear_dgrad(e, g, H, l2, 0, H, gff, FF, nullptr, 0, ACT_GELU_BWD, const_cast<bf16*>(z), FF));
+  return linear_dgrad(e, gff, FF, l1, 0, FF, dx, H, g, H);
 }
 
 static int swiglu_fwd(KitEngine* e, const bf16* x, const SwiW& s, bf16* x12, bf16* g, bf16* out) {
@@ -635,6 +656,7 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
   e->active = &e->bwd_plans;
   e->cursor = 0;
   e->group_cursor = 0;
+  e->ffn_bwd_cursor = 0;
   e->launches = 0;
   std::vector<PendingW> pend;
   int bucket = 0;
@@ -665,9 +687,8 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
     e->launches++;
     KIT_TRY(ln_bwd(dy, a.s3, a.st3, a.st3 + M, e->params + w.n3.g, nullptr, e->g1, e->grads + w.n3.g, e->grads + w.n3.b, e->grads + w.l2.b, M, H, e->st));
     pend.push_back({e->g1, H, a.hh, FF, &w.l2, 0, H, true});
-    KIT_TRY(linear_dgrad(e, e->g1, H, w.l2, 0, H, e->gff, FF, nullptr, 0, ACT_GELU_BWD, a.z, FF));
+    KIT_TRY(ffn_block_bwd(e, e->g1, w.l1, w.l2, a.z, e->gff, e->g2));  // gff = d z, g2 = d y2
     pend.push_back({e->gff, FF, a.y2, H, &w.l1, 0, FF, false});
-    KIT_TRY(linear_dgrad(e, e->gff, FF, w.l1, 0, FF, e->g2, H, e->g1, H));  // g2 = d y2
     // cross-attention block
     e->launches++;
     KIT_TRY(ln_bwd(e->g2, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1b, e->grads + w.n2.g, e->grads + w.n2.b, e->grads + w.ca.out.b, M, H, e->st));
@@ -715,9 +736,8 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
     e->launches++;
     KIT_TRY(ln_bwd(dx, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1, e->grads + w.n2.g, e->grads + w.n2.b, e->grads + w.l2.b, M, H, e->st));
     pend.push_back({e->g1, H, a.hh, FF, &w.l2, 0, H, true});
-    KIT_TRY(linear_dgrad(e, e->g1, H, w.l2, 0, H, e->gff, FF, nullptr, 0, ACT_GELU_BWD, a.z, FF));
+    KIT_TRY(ffn_block_bwd(e, e->g1, w.l1, w.l2, a.z, e->gff, e->g2));  // gff = d z, g2 = d x1
     pend.push_back({e->gff, FF, a.x1, H, &w.l1, 0, FF, false});
-    KIT_TRY(linear_dgrad(e, e->gff, FF, w.l1, 0, FF, e->g2, H, e->g1, H));  // g2 = d x1
     e->launches++;
     KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1b, e->grads + w.n1.g, e->grads + w.n1.b, e->grads + w.sa.out.b, M, H, e->st));
     pend.push_back({e->g1b, H, a.ao, H, &w.sa.out, 0, H, true});
@@ -837,6 +857,7 @@ extern "C" int kit_engine_bind(KitEngine* e, float* params, float* grads, void* 
   e->bwd_plans.clear();
   e->group_plans.clear();
   e->ffn_plans.clear();
+  e->ffn_bwd_plans.clear();
   {
     const char* v = getenv("KIT_FUSE_FFN");   // KIT_FUSE_FFN=0: the two-GEMM path (A/B measurements)
     e->fuse_ffn = !(v != nullptr && v[0] == '0');
@@ -928,7 +949,16 @@ extern "C" int kit_ffn_fwd(const void* x, const void* w1, const void* w2, const 
   FfnPlan plan;
   KIT_TRY(ffn_fwd_plan(&plan, (const bf16*)x, H, (const bf16*)w1, H, (const bf16*)w2, FF, b1, b2, (bf16*)z, (bf16*)hh, FF, (bf16*)s,
                        H, (bf16*)y, H, gamma, beta, mean, rstd, 1e-5f, M, H, FF, store_zh));
-  return ffn_fwd_launch(&plan, (cudaStream_t)stream);
+  return ffn_launch(&plan, (cudaStream_t)stream);
+}
+
+// Its input-gradient pass: dz = (g w2) * gelu'(z) -> dz [M,FF], dx = dz w1 + g -> dx [M,H].  w2t = w2^T [FF,H], w1t = w1^T [H,FF].
+extern "C" int kit_ffn_bwd(const void* g, const void* w2t, const void* w1t, const void* z, void* dz, void* dx, int32_t M, int32_t H,
+                           int32_t FF, void* stream) {
+  FfnPlan plan;
+  KIT_TRY(ffn_bwd_plan(&plan, (const bf16*)g, H, (const bf16*)w2t, H, (const bf16*)w1t, FF, (const bf16*)z, (bf16*)dz, FF, (bf16*)dx, H,
+                       M, H, FF));
+  return ffn_launch(&plan, (cudaStream_t)stream);
 }
 
 extern "C" int kit_gemm_bf16(int32_t mode, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,

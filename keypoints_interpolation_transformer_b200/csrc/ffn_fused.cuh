@@ -17,6 +17,13 @@
 // through one ring of 16 KB slots (each CTA stages HALF of every B tile).  The final epilogue is the EPI_ADD_LN epilogue of
 // gemm_sm100.cuh (bias + residual, bf16 sum out, two-pass row statistics across the four column-group warps, LayerNorm out).
 // Persistent over 256-row items.
+//
+// BWD = true is the input-gradient pass of the same block with the same skeleton:
+//
+//     dz = (g . W2) * gelu'(z)   (GEMM1 against W2^T chunks, z chunk prefetched by TMA, dz stored for the weight gradients)
+//     dx = dz . W1 + g           (GEMM2 against W1^T chunks; the residual g is the resident A tile)
+//
+// i.e. x := g (the gradient w.r.t. the pre-norm sum), W1 := W2^T [FF, H], W2 := W1^T [H, FF], no biases, no LayerNorm.
 #pragma once
 #include "gemm_sm100.cuh"
 
@@ -24,15 +31,17 @@ namespace kit {
 
 constexpr int FFN_H = 256;
 constexpr int FFN_FC = 128;
-constexpr int FFN_HBUFS = 1;   // h chunk buffers: what bounds the kernel is the depth of the weight ring (TMA latency), not EPI1 -> GEMM2
-constexpr int FFN_RING = FFN_HBUFS == 1 ? 5 : 3;
+template <bool BWD> constexpr int ffn_ring() { return BWD ? 3 : 5; }    // 16 KB weight slots
+template <bool BWD> constexpr int ffn_zbufs() { return BWD ? 2 : 1; }   // z chunk buffers: TMA-in (double-buffered) / staging out
 constexpr int FFN_SLOT = 16384;
 constexpr int FFN_X_BYTES = 65536;   // [128 x 256] bf16: four [128 x 64] k-blocks
 constexpr int FFN_HC_BYTES = 32768;  // [128 x 128] bf16: two [128 x 64] k-blocks
 constexpr int FFN_STATS = 4096;
 constexpr int FFN_EPI_WARPS = 16;
 constexpr int FFN_THREADS = 64 + 32 * FFN_EPI_WARPS;
-constexpr int FFN_SMEM = FFN_X_BYTES + FFN_RING * FFN_SLOT + (FFN_HBUFS + 1) * FFN_HC_BYTES + FFN_STATS + 1024 + 1024;   // h[HBUFS], z
+template <bool BWD> constexpr int ffn_smem() {
+  return FFN_X_BYTES + ffn_ring<BWD>() * FFN_SLOT + (1 + ffn_zbufs<BWD>()) * FFN_HC_BYTES + FFN_STATS + 1024 + 1024;
+}
 
 struct FfnParams {
   int M, FF, n_items;
@@ -43,14 +52,14 @@ struct FfnParams {
   float* ln_mean;
   float* ln_rstd;
   float ln_eps;
-  int store_zh;   // training: the pre-activation z and the activation h leave for the backward pass
-  int dbg;            // experiments only (KIT_FFN_DBG bit mask: parts of the kernel switched off for timing)
+  int store_zh;   // forward, training: the pre-activation z and the activation h leave for the backward pass
   long long* trace;   // experiments only (KIT_FFN_TRACE): clock64 marks of CTA 0, first item; see kit_ffn_trace_read
 };
 struct FfnPlan {
   CUtensorMap tmX, tmW1, tmW2, tmZ, tmHh, tmS, tmY;
   FfnParams p;
   int grid;
+  int bwd;
 };
 
 #ifdef KIT_FFN_IMPL   // the kernel is compiled into gemm.cu only
@@ -84,20 +93,23 @@ __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint3
 }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-__global__ void __launch_bounds__(FFN_THREADS, 1) ffn_fwd_kernel(const __grid_constant__ CUtensorMap tmX,
-                                                                 const __grid_constant__ CUtensorMap tmW1,
-                                                                 const __grid_constant__ CUtensorMap tmW2,
-                                                                 const __grid_constant__ CUtensorMap tmZ,
-                                                                 const __grid_constant__ CUtensorMap tmHh,
-                                                                 const __grid_constant__ CUtensorMap tmS,
-                                                                 const __grid_constant__ CUtensorMap tmY, const FfnParams p) {
+template <bool BWD>
+__global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                             const __grid_constant__ CUtensorMap tmW1,
+                                                             const __grid_constant__ CUtensorMap tmW2,
+                                                             const __grid_constant__ CUtensorMap tmZ,
+                                                             const __grid_constant__ CUtensorMap tmHh,
+                                                             const __grid_constant__ CUtensorMap tmS,
+                                                             const __grid_constant__ CUtensorMap tmY, const FfnParams p) {
+  constexpr int FFN_RING = ffn_ring<BWD>();
+  constexpr int ZBUFS = ffn_zbufs<BWD>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* x_s = smem;
   uint8_t* ring = x_s + FFN_X_BYTES;
   uint8_t* h_s = ring + FFN_RING * FFN_SLOT;
-  uint8_t* z_s = h_s + FFN_HBUFS * FFN_HC_BYTES;   // h is double-buffered: EPI1(c + 1) does not wait for GEMM2(c)
-  float2* ln_stats = reinterpret_cast<float2*>(z_s + FFN_HC_BYTES);
+  uint8_t* z_s = h_s + FFN_HC_BYTES;
+  float2* ln_stats = reinterpret_cast<float2*>(z_s + ZBUFS * FFN_HC_BYTES);
   uint64_t* ring_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ln_stats) + FFN_STATS);
   uint64_t* ring_empty = ring_full + FFN_RING;
   uint64_t* x_full = ring_empty + FFN_RING;
@@ -108,8 +120,11 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_fwd_kernel(const __grid_co
   uint64_t* h_empty = h_full + 2;       // [2]
   uint64_t* acc2_full = h_empty + 2;
   uint64_t* acc2_empty = acc2_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
-  constexpr int N_BARS = 2 * FFN_RING + 12;
+  uint64_t* z_full = acc2_empty + 1;    // [2]  BWD: the z chunk has landed (local)
+  uint64_t* z_empty = z_full + 2;       // [2]  BWD: the epilogue warps have read it (local, 16 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_empty + 2);
+  constexpr int N_BARS = 2 * FFN_RING + 16;
+  const bool store_h = BWD || p.store_zh, store_z = !BWD && p.store_zh;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -124,13 +139,15 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_fwd_kernel(const __grid_co
     pdl_launch_dependents();
     if (lane == 0) {
       tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
-      tma_prefetch_desc(&tmS); tma_prefetch_desc(&tmY);
-      if (p.store_zh) { tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmHh); }
+      tma_prefetch_desc(&tmS);
+      if (!BWD) tma_prefetch_desc(&tmY);
+      if (store_h) tma_prefetch_desc(&tmHh);
+      if (BWD || store_z) tma_prefetch_desc(&tmZ);
     }
     for (int i = lane; i < N_BARS; i += 32) {
       uint64_t* b = &ring_full[i];
       uint32_t count = 1;
-      if (b == x_empty) count = FFN_EPI_WARPS;
+      if (b == x_empty || b == z_empty || b == z_empty + 1) count = FFN_EPI_WARPS;
       else if (b == acc1_empty || b == acc1_empty + 1 || b == h_full || b == h_full + 1 || b == acc2_empty) count = 2 * FFN_EPI_WARPS;
       mbar_init(b, count);
     }
@@ -147,7 +164,7 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_fwd_kernel(const __grid_co
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer: the x tile, then the two weight streams
     if (lane == 0) {
-      uint32_t cnt = 0, it = 0;
+      uint32_t cnt = 0, it = 0, zc = 0;
       auto slot_acquire = [&](uint32_t& s) {
         s = cnt % FFN_RING;
         mbar_wait(&ring_empty[s], ((cnt / FFN_RING) & 1) ^ 1);
@@ -179,10 +196,23 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_fwd_kernel(const __grid_co
         if (rank == 0) mbar_arrive_expect_tx(x_full, 2 * FFN_X_BYTES);
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) tma_load_2d_cg2(x_s + kb * 16384, &tmX, x_full, kb * 64, m0);
+        auto load_z = [&](int c) {   // BWD: z[m0 .. +128, c*128 .. +128] -> z_s[zc & 1], two [128 x 64] k-block tiles
+          const uint32_t zb = zc & 1;
+          mbar_wait(&z_empty[zb], ((zc >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&z_full[zb], FFN_HC_BYTES);
+          tma_load_2d(z_s + zb * FFN_HC_BYTES, &tmZ, &z_full[zb], c * FFN_FC, m0);
+          tma_load_2d(z_s + zb * FFN_HC_BYTES + 16384, &tmZ, &z_full[zb], c * FFN_FC + 64, m0);
+          ++zc;
+        };
+        if (BWD) {
+          load_z(0);
+          if (NC > 1) load_z(1);
+        }
         load_w1(0);
         for (int c = 0; c < NC; ++c) {
           if (c + 1 < NC) load_w1(c + 1);
           load_w2(c);
+          if (BWD && c + 2 < NC) load_z(c + 2);
         }
       }
     }
@@ -205,8 +235,7 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_fwd_kernel(const __grid_co
           mbar_wait(acc2_empty, (it & 1) ^ 1);   // the final epilogue of the previous item has drained acc2
           tc_fence_after();
         }
-        const uint32_t hb = FFN_HBUFS == 2 ? (hc & 1) : 0;
-        mbar_wait_cluster(&h_full[hb], (FFN_HBUFS == 2 ? (hc >> 1) : hc) & 1);   // both CTAs' epilogue warps have written (and fenced) their half of h[c]
+        mbar_wait_cluster(h_full, hc & 1);   // both CTAs' epilogue warps have written (and fenced) their half of h[c]
         tc_fence_after();
         if (it == 0) mark(17 + c);
 #pragma unroll
@@ -215,13 +244,13 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_fwd_kernel(const __grid_co
           slot_wait(s);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(h_base + hb * FFN_HC_BYTES + j * 16384 + k * 32, 0, 1024);
+            const uint64_t adesc = make_smem_desc_sw128(h_base + j * 16384 + k * 32, 0, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(ring_base + s * FFN_SLOT + k * 32, 0, 1024);
-            if (!(p.dbg & 2)) umma_bf16_cg2(tmem_base + 256, adesc, bdesc, idesc2, (c > 0 || j > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_cg2(tmem_base + 256, adesc, bdesc, idesc2, (c > 0 || j > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit_cg2(&ring_empty[s], (uint16_t)3);
         }
-        umma_commit_cg2(&h_empty[hb], (uint16_t)3);
+        umma_commit_cg2(h_empty, (uint16_t)3);
         ++hc;
       };
       for (int item = first_item; item < p.n_items; item += item_stride, ++it) {
@@ -243,7 +272,7 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_fwd_kernel(const __grid_co
               for (int k = 0; k < 4; ++k) {
                 const uint64_t adesc = make_smem_desc_sw128(x_base + kb * 16384 + k * 32, 0, 1024);
                 const uint64_t bdesc = make_smem_desc_sw128(ring_base + s * FFN_SLOT + kk * 8192 + k * 32, 0, 1024);
-                if (!(p.dbg & 4)) umma_bf16_cg2(tmem_base + b * FFN_FC, adesc, bdesc, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_bf16_cg2(tmem_base + b * FFN_FC, adesc, bdesc, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
               }
             }
             umma_commit_cg2(&ring_empty[s], (uint16_t)3);
@@ -287,48 +316,67 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_fwd_kernel(const __grid_co
         }
         const int col0 = c * FFN_FC + cg * 32;   // hidden unit of r[0]
         uint32_t zp[16], hp[16];
+        if (BWD) {   // dz = dh * gelu'(z): this lane's 64 bytes of the z chunk the producer prefetched
+          mbar_wait(&z_full[b], (gc >> 1) & 1);
+          uint4 zin[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float v[8];
+          for (int i = 0; i < 4; ++i) zin[i] = lds128(z_u32 + b * FFN_HC_BYTES + hz_off + ((uint32_t((cg & 1) * 4 + i) ^ sw) << 4));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&z_empty[b]);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[8 * i + u]);
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b1 + col0 + 8 * i));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.b1 + col0 + 8 * i + 4));
-          add_pair(v[0], v[1], b0.x, b0.y); add_pair(v[2], v[3], b0.z, b0.w);
-          add_pair(v[4], v[5], b1.x, b1.y); add_pair(v[6], v[7], b1.z, b1.w);
+          for (int i = 0; i < 4; ++i) {
+            float v[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) zp[4 * i + u] = pack_bf16(v[2 * u], v[2 * u + 1]);
-          if (!(p.dbg & 1)) { gelu_pair(v[0], v[1]); gelu_pair(v[2], v[3]); gelu_pair(v[4], v[5]); gelu_pair(v[6], v[7]); }
+            for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[8 * i + u]);
+            const float2 za = unpack_bf16(zin[i].x), zb = unpack_bf16(zin[i].y), zc = unpack_bf16(zin[i].z), zd = unpack_bf16(zin[i].w);
+            gelu_grad_mul_pair(za.x, za.y, v[0], v[1]); gelu_grad_mul_pair(zb.x, zb.y, v[2], v[3]);
+            gelu_grad_mul_pair(zc.x, zc.y, v[4], v[5]); gelu_grad_mul_pair(zd.x, zd.y, v[6], v[7]);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) hp[4 * i + u] = pack_bf16(v[2 * u], v[2 * u + 1]);
+            for (int u = 0; u < 4; ++u) hp[4 * i + u] = pack_bf16(v[2 * u], v[2 * u + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[8 * i + u]);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.b1 + col0 + 8 * i));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.b1 + col0 + 8 * i + 4));
+            add_pair(v[0], v[1], b0.x, b0.y); add_pair(v[2], v[3], b0.z, b0.w);
+            add_pair(v[4], v[5], b1.x, b1.y); add_pair(v[6], v[7], b1.z, b1.w);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) zp[4 * i + u] = pack_bf16(v[2 * u], v[2 * u + 1]);
+            gelu_pair(v[0], v[1]); gelu_pair(v[2], v[3]); gelu_pair(v[4], v[5]); gelu_pair(v[6], v[7]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) hp[4 * i + u] = pack_bf16(v[2 * u], v[2 * u + 1]);
+          }
         }
         if (it == 0 && warp == 2) mark(49 + c);
-        const uint32_t hb = FFN_HBUFS == 2 ? b : 0;
-        mbar_wait(&h_empty[hb], ((FFN_HBUFS == 2 ? (gc >> 1) : gc) & 1) ^ 1);   // the GEMM2 that last read this h buffer is done
+        mbar_wait(h_empty, (gc & 1) ^ 1);   // GEMM2 of the previous chunk has read h
         if (it == 0 && warp == 2) mark(65 + c);
-        if (p.store_zh) {   // ... and so have the TMA stores of the previous chunk's h / z tiles
+        if (store_h) {   // ... and so have the TMA stores of the previous chunk's h / z tiles
           if (issuer && lane == 0) tma_store_wait_read_n<0>();
           named_bar_sync(pair_bar, 64);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t off = hz_off + ((uint32_t((cg & 1) * 4 + i) ^ sw) << 4);
-          if (!(p.dbg & 8)) sts128(h_u32 + hb * FFN_HC_BYTES + off, hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]);
-          if (p.store_zh) sts128(z_u32 + off, zp[4 * i], zp[4 * i + 1], zp[4 * i + 2], zp[4 * i + 3]);
+          sts128(h_u32 + off, hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]);
+          if (!BWD && store_z) sts128(z_u32 + off, zp[4 * i], zp[4 * i + 1], zp[4 * i + 2], zp[4 * i + 3]);
         }
-        if (!(p.dbg & 16)) fence_proxy_async();
+        fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (rank == 0) mbar_arrive(&h_full[hb]); else mbar_arrive_cluster_relaxed(&h_full[hb], 0);
+          if (rank == 0) mbar_arrive(h_full); else mbar_arrive_cluster_relaxed(h_full, 0);
         }
         if (it == 0 && warp == 2) mark(81 + c);
         if (it == 0 && warp == 17) mark(101 + c);
-        if (p.store_zh) {
+        if (store_h) {
           named_bar_sync(pair_bar, 64);
           if (issuer && lane == 0) {
             const int gcol = c * FFN_FC + (cg >> 1) * 64;
-            tma_store_2d_a(&tmHh, h_u32 + hb * FFN_HC_BYTES + tile_off, gcol, row0);
-            tma_store_2d_a(&tmZ, z_u32 + tile_off, gcol, row0);
+            tma_store_2d_a(&tmHh, h_u32 + tile_off, gcol, row0);
+            if (!BWD && store_z) tma_store_2d_a(&tmZ, z_u32 + tile_off, gcol, row0);
             tma_store_commit();
           }
         }
@@ -337,11 +385,54 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_fwd_kernel(const __grid_co
       mbar_wait(acc2_full, it & 1);
       tc_fence_after();
       if (it == 0 && warp == 2) mark(97);
-      if (p.store_zh && issuer && lane == 0) tma_store_wait_read_n<0>();
+      if (store_h && issuer && lane == 0) tma_store_wait_read_n<0>();
       named_bar_sync(13, 32 * FFN_EPI_WARPS);   // every h / z tile has been read: the region becomes the staging tiles
-      const uint32_t t_sub[2] = {h_u32 + uint32_t(warp - 2) * 4096, h_u32 + uint32_t(warp - 2) * 4096 + 2048};
       const uint32_t tmem_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(256 + cg * 64);
       const int colg = cg * 64;
+      if (BWD) {   // dx = acc2 + g: one 2 KB staging tile per warp inside h_s (the z buffers may already be refilling)
+        const uint32_t t = h_u32 + uint32_t(warp - 2) * 2048;
+        const uint32_t row64 = t + lane * 64, sw64 = (lane >> 1) & 3;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          uint32_t r[32];
+          tmem_ld32(tmem_row + uint32_t(sub * 32), r);
+          tmem_ld_wait();
+          if (sub == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (rank == 0) mbar_arrive(acc2_empty); else mbar_arrive_cluster_relaxed(acc2_empty, 0);
+              tma_store_wait_read_n<0>();   // the first half has left the staging tile
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[8 * i + u]);
+            const uint4 in = lds128(x_u32 + cg * 16384 + row * 128 + ((uint32_t(sub * 4 + i) ^ sw) << 4));
+            const float2 a = unpack_bf16(in.x), bb = unpack_bf16(in.y), cc = unpack_bf16(in.z), d = unpack_bf16(in.w);
+            add_pair(v[0], v[1], a.x, a.y); add_pair(v[2], v[3], bb.x, bb.y);
+            add_pair(v[4], v[5], cc.x, cc.y); add_pair(v[6], v[7], d.x, d.y);
+            sts128(row64 + ((i ^ sw64) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d_a(&tmS, t, colg + sub * 32, row0);
+            tma_store_commit();
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(x_empty);
+        if (item + item_stride < p.n_items) {
+          if (lane == 0) tma_store_wait_read_n<0>();
+          named_bar_sync(13, 32 * FFN_EPI_WARPS);
+        }
+        continue;
+      }
+      const uint32_t t_sub[2] = {h_u32 + uint32_t(warp - 2) * 4096, h_u32 + uint32_t(warp - 2) * 4096 + 2048};
       uint32_t sreg[2][16];
       float rsum = 0.f;
 #pragma unroll
@@ -463,7 +554,10 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_fwd_kernel(const __grid_co
 int ffn_fwd_plan(FfnPlan* plan, const bf16* x, int64_t ldx, const bf16* w1, int64_t ldw1, const bf16* w2, int64_t ldw2,
                  const float* b1, const float* b2, bf16* z, bf16* hh, int64_t ldzh, bf16* s, int64_t lds, bf16* y, int64_t ldy,
                  const float* gamma, const float* beta, float* mean, float* rstd, float eps, int M, int H, int FF, int store_zh);
+// dz = (g . W2) * gelu'(z) -> dz_out [M, FF];  dx = dz . W1 + g -> dx [M, H].  w2t = W2^T [FF, H], w1t = W1^T [H, FF] (bf16).
+int ffn_bwd_plan(FfnPlan* plan, const bf16* g, int64_t ldg, const bf16* w2t, int64_t ldw2t, const bf16* w1t, int64_t ldw1t,
+                 const bf16* z, bf16* dz_out, int64_t ldzh, bf16* dx, int64_t lddx, int M, int H, int FF);
 bool ffn_fwd_supported(int H, int FF);
-int ffn_fwd_launch(const FfnPlan* plan, cudaStream_t stream);
+int ffn_launch(const FfnPlan* plan, cudaStream_t stream);
 
 }  // namespace kit

@@ -328,7 +328,11 @@ int ffn_fwd_plan(FfnPlan* plan, const bf16* x, int64_t ldx, const bf16* w1, int6
   if (rc) return rc;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, []() { attr_err = cudaFuncSetAttribute(ffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FFN_SMEM); });
+  std::call_once(once, []() {
+    attr_err = cudaFuncSetAttribute(ffn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ffn_smem<false>());
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(ffn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ffn_smem<true>());
+  });
   KIT_REQUIRE(attr_err == cudaSuccess, "fused FFN: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   if ((rc = make_tensor_map_2d(&plan->tmX, x, (uint64_t)H, (uint64_t)M, (uint64_t)ldx * 2, 64, 128))) return rc;
   if ((rc = make_tensor_map_2d(&plan->tmW1, w1, (uint64_t)H, (uint64_t)FF, (uint64_t)ldw1 * 2, 64, 64))) return rc;
@@ -345,8 +349,8 @@ int ffn_fwd_plan(FfnPlan* plan, const bf16* x, int64_t ldx, const bf16* w1, int6
   p.M = M; p.FF = FF; p.n_items = (M + 255) / 256;
   p.b1 = b1; p.b2 = b2; p.ln_gamma = gamma; p.ln_beta = beta; p.ln_mean = mean; p.ln_rstd = rstd; p.ln_eps = eps;
   p.store_zh = store_zh;
+  plan->bwd = 0;
   p.trace = nullptr;
-  p.dbg = getenv("KIT_FFN_DBG") != nullptr ? atoi(getenv("KIT_FFN_DBG")) : 0;
   if (getenv("KIT_FFN_TRACE") != nullptr) {
     if (g_ffn_trace == nullptr && cudaMalloc(&g_ffn_trace, 256 * sizeof(long long)) != cudaSuccess) g_ffn_trace = nullptr;
     if (g_ffn_trace != nullptr) cudaMemset(g_ffn_trace, 0, 256 * sizeof(long long));
@@ -357,11 +361,28 @@ int ffn_fwd_plan(FfnPlan* plan, const bf16* x, int64_t ldx, const bf16* w1, int6
   return KIT_OK;
 }
 
-int ffn_fwd_launch(const FfnPlan* plan, cudaStream_t stream) {
+int ffn_bwd_plan(FfnPlan* plan, const bf16* g, int64_t ldg, const bf16* w2t, int64_t ldw2t, const bf16* w1t, int64_t ldw1t,
+                 const bf16* z, bf16* dz_out, int64_t ldzh, bf16* dx, int64_t lddx, int M, int H, int FF) {
+  // the forward plan with x := g, W1 := W2^T, W2 := W1^T; the z map becomes a LOAD map ([128 x 64] boxes)
+  static const float dummy[4] = {0.f, 0.f, 0.f, 0.f};
+  KIT_REQUIRE(z != nullptr && dz_out != nullptr && dx != nullptr, "fused FFN backward: null tensor");
+  float* unused = const_cast<float*>(dummy);
+  int rc = ffn_fwd_plan(plan, g, ldg, w2t, ldw2t, w1t, ldw1t, dummy, dummy, const_cast<bf16*>(z), dz_out, ldzh, dx, lddx, dx, lddx, dummy,
+                        dummy, unused, unused, 0.f, M, H, FF, 1);
+  if (rc) return rc;
+  if ((rc = make_tensor_map_2d(&plan->tmZ, z, (uint64_t)FF, (uint64_t)M, (uint64_t)ldzh * 2, 64, 128))) return rc;
+  plan->p.b1 = plan->p.b2 = plan->p.ln_gamma = plan->p.ln_beta = nullptr;
+  plan->p.ln_mean = plan->p.ln_rstd = nullptr;
+  plan->p.store_zh = 0;
+  plan->bwd = 1;
+  return KIT_OK;
+}
+
+int ffn_launch(const FfnPlan* plan, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(plan->grid);
   cfg.blockDim = dim3(FFN_THREADS);
-  cfg.dynamicSmemBytes = FFN_SMEM;
+  cfg.dynamicSmemBytes = plan->bwd ? ffn_smem<true>() : ffn_smem<false>();
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -372,8 +393,12 @@ int ffn_fwd_launch(const FfnPlan* plan, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  KIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_fwd_kernel, plan->tmX, plan->tmW1, plan->tmW2, plan->tmZ, plan->tmHh, plan->tmS,
-                                    plan->tmY, plan->p));
+  if (plan->bwd)
+    KIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_kernel<true>, plan->tmX, plan->tmW1, plan->tmW2, plan->tmZ, plan->tmHh, plan->tmS,
+                                      plan->tmY, plan->p));
+  else
+    KIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_kernel<false>, plan->tmX, plan->tmW1, plan->tmW2, plan->tmZ, plan->tmHh, plan->tmS,
+                                      plan->tmY, plan->p));
   return KIT_OK;
 }
 

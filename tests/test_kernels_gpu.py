@@ -266,3 +266,27 @@ def test_ffn_fused_fwd(M, FF, store):
         assert (hh.float() - h_ref).abs().max().item() < 0.03 * max(1.0, h_ref.abs().max().item())
     else:
         assert torch.isnan(z.float()).all() and torch.isnan(hh.float()).all()     # inference writes neither
+
+
+@pytest.mark.parametrize("M,FF", [(256, 128), (512, 2048), (16384, 2048), (1000, 512), (40000, 1024)])
+def test_ffn_fused_bwd(M, FF):
+    """kit_ffn_bwd: dz = (g W2) * gelu'(z), dx = dz W1 + g against fp32 torch on the same bf16 operands (dz rounded to bf16
+    between the GEMMs, as the tensor core reads it and as the weight gradients read it)."""
+    H = 256
+    gen = torch.Generator(device="cpu").manual_seed(M * 3 + FF)
+    g = _bf(torch.randn(M, H, generator=gen)).to(DEV)
+    w1 = _bf(torch.randn(FF, H, generator=gen) / math.sqrt(H)).to(DEV)
+    w2 = _bf(torch.randn(H, FF, generator=gen) / math.sqrt(FF)).to(DEV)
+    z = _bf(torch.randn(M, FF, generator=gen)).to(DEV)
+    w2t, w1t = w2.t().contiguous(), w1.t().contiguous()
+    dz = torch.full((M, FF), float("nan"), dtype=torch.bfloat16, device=DEV)
+    dx = torch.full((M, H), float("nan"), dtype=torch.bfloat16, device=DEV)
+    K.check(K.lib().kit_ffn_bwd(K.ptr(g), K.ptr(w2t), K.ptr(w1t), K.ptr(z), K.ptr(dz), K.ptr(dx), M, H, FF, _sp()))
+    torch.cuda.synchronize()
+    zf = z.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).sum().backward()           # gelu'(z), erf form
+    dz_ref = (g.float() @ w2.float()) * zf.grad
+    dx_ref = _bf(dz_ref).float() @ w1.float() + g.float()
+    assert torch.isfinite(dz.float()).all() and torch.isfinite(dx.float()).all()
+    assert _rel(dz, dz_ref) < 5e-3
+    assert _rel(dx, dx_ref) < 5e-3
