@@ -200,6 +200,12 @@ typedef struct KitMissingStats {
 int kit_draw_missing(const KitMissingStats* stats, int32_t B, int32_t T, uint64_t seed, uint64_t offset,
                      int32_t* src_index, float* frame_missing, int32_t* blocks, int32_t* n_blocks, void* stream);
 
+/* The cubic-spline baseline of the evaluation (3_test_cubic_interpolation.py:32-58): frames with mask == 1 and every exact 0
+ * are missing; each (keypoint, coordinate) series is filled by the not-a-knot cubic spline through its remaining samples
+ * (pandas interpolate(method="cubicspline", limit_direction="both") = scipy CubicSpline, extrapolating at both ends),
+ * all-missing series become 0 (np.nan_to_num).  data / out [B, T1, K, 2] fp32, mask [B, T1] fp32; T1 <= 1040. */
+int kit_cubic_interpolate(const float* data, const float* mask, float* out, int32_t B, int32_t T1, int32_t K, void* stream);
+
 /* model.get_mask (model.py:172-209) on the device: frame_mask [size] -> out [size,size]. */
 int kit_get_mask(const float* frame_mask, int32_t size, int32_t matrix_type, float* out, void* stream);
 

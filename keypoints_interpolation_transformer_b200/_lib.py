@@ -78,6 +78,7 @@ _SIGNATURES = {
     "kit_prepass": (C.c_int, [C.POINTER(KitPrepassConfig), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "kit_loss_partials": (_I64, [_I64, _I32]),
     "kit_loss_fwd_bwd": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P, _P]),
+    "kit_cubic_interpolate": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P]),
     "kit_get_mask": (C.c_int, [_P, _I32, _I32, _P, _P]),
     "kit_draw_missing": (C.c_int, [C.POINTER(KitMissingStats), _I32, _I32, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P]),
     "kit_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P]),

@@ -205,6 +205,36 @@ def euclidean_distance_loss(output, target):
     return torch.norm(output.reshape(-1, 2) - target.reshape(-1, 2), dim=1).sum()
 
 
+def cubic_interpolation(data, mask):
+    """3_test_cubic_interpolation.py:32-58 -- data [T+1,K,2] (numpy or tensor), mask [T+1] or [1,T+1] 0/1.  Masked frames are
+    zeroed, every exact 0 becomes missing, and each (keypoint, coordinate) series is filled by what pandas'
+    ``interpolate(method="cubicspline", limit_direction="both")`` computes: scipy.interpolate.CubicSpline (not-a-knot,
+    extrapolating) through the remaining samples; all-missing series become 0 (np.nan_to_num).  A series with ONE sample
+    makes the reference raise (CubicSpline needs two points); here it is filled with that sample.  Returns float32
+    [T+1,K,2]."""
+    from scipy.interpolate import CubicSpline
+    d = np.array(torch.as_tensor(data).detach().cpu().numpy(), dtype=np.float32, copy=True)
+    m = np.asarray(torch.as_tensor(mask).detach().cpu().numpy()).reshape(-1)
+    T1, K, _ = d.shape
+    d[m == 1] = 0.0
+    out = np.zeros_like(d)
+    t = np.arange(T1, dtype=np.float64)
+    for k in range(K):
+        for c in range(2):
+            y = d[:, k, c].astype(np.float64)
+            ok = (y != 0) & ~np.isnan(y)
+            n = int(ok.sum())
+            if n == 0:
+                continue
+            if n == 1:
+                out[:, k, c] = y[ok][0]
+                continue
+            filled = y.copy()
+            filled[~ok] = CubicSpline(t[ok], y[ok])(t[~ok])
+            out[:, k, c] = filled.astype(np.float32)
+    return out
+
+
 def mse_loss(output, target):
     """A1_train.py:254 criterion = MSELoss() (= euclidean_loss / 2)."""
     return ((output - target) ** 2).mean()

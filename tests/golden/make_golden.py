@@ -263,6 +263,45 @@ def missing_case():
     np.savez_compressed(os.path.join(HERE, "missing_frames.npz"), **out)
 
 
+def cubic_case():
+    """3_test_cubic_interpolation.py:32-58 ``cubic_interpolation`` itself (the module runs main() at import, so the function is
+    lifted out of its source with ast), on small sequences: AUTSL-style missing blocks, a block at each end (extrapolation),
+    exact zeros in unmasked frames, a keypoint with 3 / 2 samples, an all-missing keypoint."""
+    import ast
+    import pandas as pd
+    src = open(os.path.join(REF, "3_test_cubic_interpolation.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "cubic_interpolation"][0]
+    ns = {"torch": torch, "np": np, "pd": pd}
+    exec(compile(ast.Module([fn], []), "ref_cubic", "exec"), ns)
+    ref_fn = ns["cubic_interpolation"]
+    rs = np.random.RandomState(21)
+    out = {"count": 3}
+    for n, (T1, K) in enumerate([(33, 6), (65, 5), (20, 4)]):
+        tt = np.arange(T1)[:, None, None]
+        data = (0.5 + 0.3 * np.sin(2 * np.pi * (rs.uniform(0.5, 3, (1, K, 2)) * tt / T1 + rs.uniform(0, 1, (1, K, 2))))).astype(np.float32)
+        mask = np.zeros(T1, dtype=np.float32)
+        mask[5:9] = 1
+        mask[T1 // 2:T1 // 2 + 6] = 1
+        if n == 1:
+            mask[1:4] = 1            # SOS stays, a block right behind it
+            mask[T1 - 3:] = 1        # block at the end: extrapolation
+        if n == 2:
+            mask[0:2] = 1            # block at the very start: extrapolation to the left
+        data[7, 0, 0] = 0.0          # exact zeros in unmasked frames are missing too
+        data[12, 1, :] = 0.0
+        keep = np.where(mask == 0)[0]
+        data[:, 2, 0] = 0.0
+        data[keep[[1, len(keep) // 2, -2]], 2, 0] = [0.3, 0.5, 0.2]     # three samples: parabola
+        data[:, 3, 1] = 0.0
+        data[keep[[2, -1]], 3, 1] = [0.4, 0.6]              # two samples: straight line
+        if K > 4:
+            data[:, 4, :] = 0.0                            # nothing left: zeros
+        res = ref_fn(torch.from_numpy(data.copy()), torch.from_numpy(mask).unsqueeze(0))
+        out[f"data{n}"], out[f"mask{n}"], out[f"out{n}"] = data, mask, res.numpy()
+    np.savez_compressed(os.path.join(HERE, "cubic.npz"), **out)
+    print("cubic", [out[f"out{n}"].shape for n in range(3)])
+
+
 def loss_case():
     rs = np.random.RandomState(9)
     o = torch.from_numpy(rs.normal(size=(3, 17, 71, 2)).astype(np.float32))
@@ -287,6 +326,7 @@ if __name__ == "__main__":
     missing_case()
     loss_case()
     cycle_case()
+    cubic_case()
     small_full = ["learned_input_positional_encoder", "input_embedding.bias", "fc_final.weight", "fc_final.bias",
                   "transformer.encoder.layers.0.self_attn.in_proj_bias",
                   "transformer.decoder.layers.1.multihead_attn.out_proj.weight",

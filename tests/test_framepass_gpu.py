@@ -242,3 +242,26 @@ def test_keypoint_batcher_device_policy_feeds_the_step():
     m = mask[:, 1:].bool().cpu()
     assert m.any() and (inputs[:, 0] == 1).all() and (mask[:, 0] == 0).all()
     assert torch.equal(inputs[:, 1:].cpu()[~m], raw[~m])                         # untouched frames pass through
+
+
+def test_cubic_interpolation_kernel(golden_dir):
+    """kit_cubic_interpolate (the evaluation's cubic-spline baseline, 3_test_cubic_interpolation.py:32-58) against outputs of
+    the reference's own function (extrapolation at both ends, exact zeros as missing, 3- / 2-sample and empty series), the
+    reference call signature, and a batch against the scipy oracle at BASELINE configs[3] length (T = 256)."""
+    from keypoints_interpolation_transformer_b200 import baselines
+    g = np.load(os.path.join(golden_dir, "cubic.npz"))
+    for n in range(int(g["count"])):
+        data, mask, ref = (torch.from_numpy(g[f"{k}{n}"]) for k in ("data", "mask", "out"))
+        got = baselines.cubic_interpolation(data.to(DEV), mask.unsqueeze(0).to(DEV)).cpu()     # reference call: mask [1, T+1]
+        assert got.shape == ref.shape
+        keep = (mask == 0)[:, None, None] & (data != 0)
+        assert torch.equal(got[keep], data[keep])                                               # samples bit-exact
+        scale = ref.abs().max().item()
+        assert (got - ref).abs().max().item() <= 2e-5 * max(1.0, scale), n
+    inputs, gt, mask = ko.synthetic_batch(6, 256, 71, seed=5)
+    inputs[:, :, 3] = 0.0                                        # a keypoint the detector never saw
+    got = baselines.cubic_interpolation(inputs.to(DEV), mask.to(DEV)).cpu()
+    for b in range(6):
+        ref = torch.from_numpy(ko.cubic_interpolation(inputs[b], mask[b]))
+        assert (got[b] - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item()), b
+    assert torch.count_nonzero(got[:, :, 3]) == 0

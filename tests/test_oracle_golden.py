@@ -187,3 +187,15 @@ def test_losses_match_reference(golden_dir):
         assert abs(d.item() - float(g["distance"])) <= 1e-6 * float(g["distance"])
         d.backward()
         np.testing.assert_allclose(oo.grad.numpy(), g["distance_grad"], rtol=1e-5, atol=1e-7)
+
+
+def test_cubic_interpolation_matches_reference(golden_dir):
+    """oracle cubic_interpolation against outputs of the reference's own function (3_test_cubic_interpolation.py:32-58)."""
+    g = _load(golden_dir, "cubic")
+    for n in range(int(g["count"])):
+        got = ko.cubic_interpolation(g[f"data{n}"], g[f"mask{n}"])
+        ref = g[f"out{n}"]
+        assert got.shape == ref.shape and not np.isnan(got).any()
+        np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-7)
+        keep = (g[f"mask{n}"] == 0)[:, None, None] & (g[f"data{n}"] != 0)
+        assert np.array_equal(got[keep], g[f"data{n}"][keep])          # samples are kept bit-exactly
