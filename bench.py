@@ -237,11 +237,21 @@ def gpu_run(args):
             dist.barrier()
             dist.destroy_process_group()
         return
-    gemm_ms = acc["gemm_tn"][0] + acc["gemm_wgrad"][0]
-    gemm_fl = acc["gemm_tn"][2] + acc["gemm_wgrad"][2]
-    gemm_n = acc["gemm_tn"][1] + acc["gemm_wgrad"][1]
+    # tensor-core family = plain GEMMs + grouped weight gradients + the fused feed-forward kernels
+    fam = [acc[k] for k in ("gemm_tn", "gemm_wgrad", "ffn") if k in acc]
+    gemm_ms, gemm_n, gemm_fl = (sum(a[i] for a in fam) for i in range(3))
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
-    achieved_tf = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    family_tf = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    # the dominant kernel of the step (largest share of the ncu launch list, profiles/r01c_summary.md): ffn_kernel
+    ffn = acc.get("ffn", [0.0, 0, 0.0])
+    dom_ms, dom_n, dom_fl = ffn if ffn[1] > 0 else (gemm_ms, gemm_n, gemm_fl)
+    achieved_tf = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    traffic = None
+    try:       # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tj.get("ffn_kernel_avg_bytes_per_launch") if ffn[1] > 0 else None
+    except Exception:
+        pass
     step_ms = ms / args.steps
     seqs = B_PER_GPU * world * args.steps
     value = seqs / (ms * 1e-3)
@@ -276,12 +286,21 @@ def gpu_run(args):
                 "ms_per_step": ms_e2e / args.steps, "last_loss": last},
         "gpu_launches": int(launches) * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (TN + wgrad)", "achieved": achieved_tf,
-                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
-                     "traffic": None, "launches_per_step": gemm_n // prof_steps,
-                     "ms_per_step": gemm_ms / prof_steps, "share_of_step": (gemm_ms / prof_steps) / step_ms,
+        "roofline": {"bound": "tensor",
+                     "kernel": "ffn_kernel<BWD> (fused feed-forward block, forward and input-gradient pass)" if ffn[1] > 0
+                     else "gemm_tcgen05_kernel (TN + wgrad)",
+                     "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                     "algorithmic_flops_per_launch": dom_fl / dom_n if dom_n else None,
+                     "avg_launch_us": 1e3 * dom_ms / dom_n if dom_n else None,
+                     "launches_per_step": dom_n // prof_steps,
+                     "ms_per_step": dom_ms / prof_steps, "share_of_step": (dom_ms / prof_steps) / step_ms,
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
-                     if peaks else "fallback"},
+                     if peaks else "fallback",
+                     "tensor_family": {"what": "all tcgen05 kernels of the step: plain GEMMs + grouped weight gradients + ffn_kernel",
+                                       "achieved": family_tf, "frac": family_tf / peak_tf if peak_tf else None,
+                                       "launches_per_step": gemm_n // prof_steps, "ms_per_step": gemm_ms / prof_steps,
+                                       "share_of_step": (gemm_ms / prof_steps) / step_ms}},
         "breakdown": breakdown,
         "framepass_roofline": frame,
         "cpu_baseline": None if cpu is None else {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",

@@ -139,7 +139,8 @@ int64_t kit_engine_last_launches(const KitEngine* e);
 #define KIT_PROF_GEMM_WGRAD 1
 #define KIT_PROF_ATTN_FWD 2
 #define KIT_PROF_ATTN_BWD 3
-#define KIT_PROF_CATEGORIES 4
+#define KIT_PROF_FFN 4 /* the fused feed-forward kernels (forward and input-gradient pass) */
+#define KIT_PROF_CATEGORIES 5
 int kit_engine_set_profiling(KitEngine* e, int32_t on);
 int kit_engine_profile_read(KitEngine* e, int32_t category, float* ms, int64_t* launches, double* flops);
 
@@ -243,6 +244,12 @@ int kit_ffn_fwd(const void* x, const void* w1, const void* w2, const float* b1, 
  * dx = dz w1 + g -> dx [M,H] (g = gradient w.r.t. the pre-norm sum s).  w2t = w2^T [FF,H], w1t = w1^T [H,FF], bf16 row-major. */
 int kit_ffn_bwd(const void* g, const void* w2t, const void* w1t, const void* z, void* dz, void* dx, int32_t M, int32_t H,
                 int32_t FF, void* stream);
+
+/* LayerNorm backward in the epilogue of the GEMM that produces the gradient w.r.t. the LayerNorm output (tests):
+ * dy = A B^T + addend (A [M,K], B [256,K], addend [M,256], bf16); dx = rstd (dy gamma - mean(dy gamma) - xhat mean(dy gamma xhat))
+ * with xhat = (s - mean) rstd from the saved pre-norm sum s [M,256]; dgamma += sum_rows dy xhat, dbeta += sum_rows dy. */
+int kit_gemm_lnbwd(const void* A, const void* B, const void* addend, const void* s, const float* gamma, const float* mean,
+                   const float* rstd, void* dx, float* dgamma, float* dbeta, int32_t M, int32_t K, void* stream);
 
 /* softmax(Q K^T / sqrt(d) + mask) V for B*NH heads.  q/k/v: bf16, element (b, t, h, c) at
  * ptr + (b*S + t)*ld + h*d + c.  out: bf16 [B*Sq, NH*d] (ld_o).  lse: fp32 [B, NH, Sq]. */

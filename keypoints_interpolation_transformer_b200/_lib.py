@@ -87,6 +87,7 @@ _SIGNATURES = {
                                 _I64, _I32, _P]),
     "kit_ffn_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "kit_ffn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P]),
+    "kit_gemm_lnbwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P]),
     "kit_attention_fwd": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I32, _I32, _I32, _I32, _I32,
                                     C.POINTER(KitAttnMask), _P]),
     "kit_attention_bwd": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _P, _I64,

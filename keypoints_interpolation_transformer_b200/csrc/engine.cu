@@ -224,6 +224,11 @@ struct KitEngine {
   std::vector<FfnPlan> ffn_plans, ffn_bwd_plans;   // one per layer of the forward / backward (fused feed-forward block)
   size_t ffn_cursor = 0, ffn_bwd_cursor = 0;
   bool fuse_ffn = true;
+  // LayerNorm backward in the epilogue of the kernel that produces its output gradient (EPI_ADD_LNBWD, ffn_kernel<true>).  Opt-in
+  // (KIT_FUSE_LNBWD=1): it removes 28 of the 37 ln_bwd launches of a step, but with one accumulator row per lane the dgamma / dbeta
+  // column sums need a warp transpose-reduce that costs more than the launches it saves (4.45 vs 4.34 ms per step at B = 256; 4.20
+  // without the column sums) -- see profiles/r01c_summary.md.
+  bool fuse_lnbwd = false;
   size_t cursor = 0;
   std::vector<GemmPlan>* active = nullptr;
   int64_t launches = 0;
@@ -379,23 +384,24 @@ static void prof_reset(KitEngine* e) {
 static int eg(KitEngine* e, int mode, const bf16* A, int64_t lda, const bf16* Bm, int64_t ldb, void* C, int64_t ldc, int M,
               int N, int K, const float* bias, const bf16* addend, int64_t ld_add, int out_kind, int act, bf16* aux,
               int64_t ld_aux, float* bias_grad = nullptr, bool* bias_grad_fused = nullptr, const GemmLN* ln = nullptr,
-              bool* ln_fused = nullptr) {
+              bool* ln_fused = nullptr, const LnBwdArgs* lnb = nullptr, bool* lnb_fused = nullptr) {
   std::vector<GemmPlan>& plans = *e->active;
   if (e->cursor >= plans.size()) {
     GemmPlan p;
     int rc = gemm_plan(&p, mode, A, lda, Bm, ldb, C, ldc, M, N, K, bias, addend, ld_add, out_kind, act, aux, ld_aux,
-                       mode == 1 ? 0 : 1, bias_grad, ln);
+                       mode == 1 ? 0 : 1, bias_grad, ln, lnb);
     if (rc) return rc;
     plans.push_back(p);
   }
   GemmPlan& p = plans[e->cursor++];
   if (p.p.C != C) {  // caller memory moved (pred): the output tensor map must be rebuilt
     int rc = gemm_plan(&p, mode, A, lda, Bm, ldb, C, ldc, M, N, K, bias, addend, ld_add, out_kind, act, aux, ld_aux,
-                       mode == 1 ? 0 : 1, bias_grad, ln);
+                       mode == 1 ? 0 : 1, bias_grad, ln, lnb);
     if (rc) return rc;
   }
   if (bias_grad_fused != nullptr) *bias_grad_fused = p.p.bias_grad != nullptr;
   if (ln_fused != nullptr) *ln_fused = p.epi == EPI_ADD_LN;
+  if (lnb_fused != nullptr) *lnb_fused = p.epi == EPI_ADD_LNBWD;
   e->launches++;
   prof_begin(e, mode == 0 ? KIT_PROF_GEMM_TN : KIT_PROF_GEMM_WGRAD, 2.0 * (double)M * (double)N * (double)K);
   const int rc = gemm_launch(&p, e->st);
@@ -452,9 +458,34 @@ static int linear_add_ln_fwd(KitEngine* e, const bf16* x, int64_t ldx, const Lin
 // dx = dy W[row0:row0+nrows, :] (+ addend)   (B operand = rows of W^T restricted to those columns)
 static int linear_dgrad(KitEngine* e, const bf16* dy, int64_t ld_dy, const LinearW& w, int row0, int nrows, bf16* dx,
                         int64_t ld_dx, const bf16* addend, int64_t ld_add, int act = ACT_NONE, bf16* aux = nullptr,
-                        int64_t ld_aux = 0) {
-  return eg(e, 0, dy, ld_dy, e->wb + w.wbT + row0, w.ldT, dx, ld_dx, (int)e->M, w.cols, nrows, nullptr, addend, ld_add,
-            OUT_BF16, act, aux, ld_aux);
+                        int64_t ld_aux = 0, const LnBwdArgs* lnb = nullptr) {
+  bool fused = false;
+  KIT_TRY(eg(e, 0, dy, ld_dy, e->wb + w.wbT + row0, w.ldT, dx, ld_dx, (int)e->M, w.cols, nrows, nullptr, addend, ld_add,
+             OUT_BF16, act, aux, ld_aux, nullptr, nullptr, nullptr, nullptr, lnb, &fused));
+  KIT_REQUIRE(lnb == nullptr || fused, "linear_dgrad: the planner refused the fused LayerNorm backward");
+  return KIT_OK;
+}
+// LayerNorm backward fused behind its producer is possible when a row is one 256-wide tile
+static bool lnbwd_fusable(const KitEngine* e) { return e->fuse_lnbwd && e->L.cfg.hidden == 256; }
+static LnBwdArgs lnbwd_args(KitEngine* e, const bf16* s, const float* stats, const LNW& n) {
+  return LnBwdArgs{s, e->L.cfg.hidden, e->params + n.g, stats, stats + e->M, e->grads + n.g, e->grads + n.b};
+}
+// dx_ln = LayerNormBackward(dy) with dy = din W[row0:row0+nrows, :] + addend: in the GEMM epilogue when possible (then the
+// bias gradient of the Linear that feeds the LayerNorm is left to its weight-gradient GEMM: *bias_done = false), else
+// GEMM -> tmp -> ln_bwd kernel (which also sums dx's columns into dxsum: *bias_done = true).
+static int dgrad_then_lnbwd(KitEngine* e, const bf16* din, int64_t ld_in, const LinearW& w, int row0, int nrows, const bf16* addend,
+                            bf16* tmp, bf16* dx_ln, const bf16* s, const float* stats, const LNW& n, float* dxsum, bool* bias_done) {
+  const int H = e->L.cfg.hidden;
+  const int64_t M = e->M;
+  if (lnbwd_fusable(e) && addend != nullptr && gemm_lnbwd_supported((int)M)) {
+    const LnBwdArgs lb = lnbwd_args(e, s, stats, n);
+    *bias_done = false;
+    return linear_dgrad(e, din, ld_in, w, row0, nrows, dx_ln, H, addend, H, ACT_NONE, nullptr, 0, &lb);
+  }
+  KIT_TRY(linear_dgrad(e, din, ld_in, w, row0, nrows, tmp, H, addend, H));
+  e->launches++;
+  *bias_done = true;
+  return ln_bwd(tmp, s, stats, stats + M, e->params + n.g, nullptr, dx_ln, e->grads + n.g, e->grads + n.b, dxsum, M, H, e->st);
 }
 // dW[row0:row0+nrows, :] += dy^T x ; db[row0:...] += colsum(dy)
 static int linear_wgrad(KitEngine* e, const bf16* dy, int64_t ld_dy, const bf16* x, int64_t ldx, const LinearW& w, int row0,
@@ -528,7 +559,7 @@ static int ffn_block_fwd(KitEngine* e, const bf16* x, const LinearW& l1, const L
     }
     const FfnPlan& plan = e->ffn_plans[e->ffn_cursor++];
     e->launches++;
-    prof_begin(e, KIT_PROF_GEMM_TN, 4.0 * (double)M * H * FF);
+    prof_begin(e, KIT_PROF_FFN, 4.0 * (double)M * H * FF);
     const int rc = ffn_launch(&plan, e->st);
     prof_end(e);
     return rc;
@@ -538,24 +569,37 @@ static int ffn_block_fwd(KitEngine* e, const bf16* x, const LinearW& l1, const L
 }
 
 // Input gradients of the same block: dz = (g W2) * gelu'(z) -> gff (kept for the weight gradients), dx = dz W1 + g.
-static int ffn_block_bwd(KitEngine* e, const bf16* g, const LinearW& l1, const LinearW& l2, const bf16* z, bf16* gff, bf16* dx) {
+// Then, when ln_s != null, the backward of the LayerNorm in front of the block (its output gradient is dx): dx_ln, with the same
+// fused / unfused choice and *bias_done meaning as dgrad_then_lnbwd.
+static int ffn_block_bwd(KitEngine* e, const bf16* g, const LinearW& l1, const LinearW& l2, const bf16* z, bf16* gff, bf16* dx,
+                         bf16* dx_ln, const bf16* ln_s, const float* ln_stats, const LNW& n, float* dxsum, bool* bias_done) {
   const int H = e->L.cfg.hidden, FF = e->L.cfg.ff;
   const int64_t M = e->M;
   if (e->fuse_ffn && ffn_fwd_supported(H, FF) && l2.wbT >= 0 && l1.wbT >= 0) {
+    const bool fuse_ln = lnbwd_fusable(e);
     if (e->ffn_bwd_cursor >= e->ffn_bwd_plans.size()) {
       FfnPlan plan;
-      KIT_TRY(ffn_bwd_plan(&plan, g, H, e->wb + l2.wbT, l2.ldT, e->wb + l1.wbT, l1.ldT, z, gff, FF, dx, H, (int)M, H, FF));
+      const LnBwdArgs lb = lnbwd_args(e, ln_s, ln_stats, n);
+      KIT_TRY(ffn_bwd_plan(&plan, g, H, e->wb + l2.wbT, l2.ldT, e->wb + l1.wbT, l1.ldT, z, gff, FF, fuse_ln ? dx_ln : dx, H, (int)M, H,
+                           FF, fuse_ln ? &lb : nullptr));
       e->ffn_bwd_plans.push_back(plan);
     }
     const FfnPlan& plan = e->ffn_bwd_plans[e->ffn_bwd_cursor++];
     e->launches++;
-    prof_begin(e, KIT_PROF_GEMM_TN, 4.0 * (double)M * H * FF);
+    prof_begin(e, KIT_PROF_FFN, 4.0 * (double)M * H * FF);
     const int rc = ffn_launch(&plan, e->st);
     prof_end(e);
-    return rc;
+    if (rc) return rc;
+    if (fuse_ln) {
+      *bias_done = false;
+      return KIT_OK;
+    }
+    e->launches++;
+    *bias_done = true;
+    return ln_bwd(dx, ln_s, ln_stats, ln_stats + M, e->params + n.g, nullptr, dx_ln, e->grads + n.g, e->grads + n.b, dxsum, M, H, e->st);
   }
   KIT_TRY(linear_dgrad(e, g, H, l2, 0, H, gff, FF, nullptr, 0, ACT_GELU_BWD, const_cast<bf16*>(z), FF));
-  return linear_dgrad(e, gff, FF, l1, 0, FF, dx, H, g, H);
+  return dgrad_then_lnbwd(e, gff, FF, l1, 0, FF, g, dx, dx_ln, ln_s, ln_stats, n, dxsum, bias_done);
 }
 
 static int swiglu_fwd(KitEngine* e, const bf16* x, const SwiW& s, bf16* x12, bf16* g, bf16* out) {
@@ -678,21 +722,25 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
                  e->grads + L.dec_norm.g, e->grads + L.dec_norm.b, nullptr, M, H, e->st));
   bf16* dy = e->g0;  // gradient w.r.t. the current layer's output
   bool mem_grad_started = false;
+  bool top_done = false;   // the LayerNorm backward at the top of this layer already ran in the previous layer's last GEMM (-> g1)
+  bool bd = true;
   for (int l = nl - 1; l >= 0; --l) {
     const DecW& w = L.dec[l];
     DecAct& a = e->da[l];
     const bf16* y_in = (l == 0) ? e->y0 : e->da[l - 1].y3;
     // FFN block.  Weight gradients are queued (their dy buffers g1 / gff / g1b / gqc / gkv / g1c / gqkv stay untouched
-    // until the end of the layer) and leave in one grouped launch.
-    e->launches++;
-    KIT_TRY(ln_bwd(dy, a.s3, a.st3, a.st3 + M, e->params + w.n3.g, nullptr, e->g1, e->grads + w.n3.g, e->grads + w.n3.b, e->grads + w.l2.b, M, H, e->st));
-    pend.push_back({e->g1, H, a.hh, FF, &w.l2, 0, H, true});
-    KIT_TRY(ffn_block_bwd(e, e->g1, w.l1, w.l2, a.z, e->gff, e->g2));  // gff = d z, g2 = d y2
+    // until the end of the layer) and leave in one grouped launch.  Every LayerNorm backward runs in the epilogue of the
+    // kernel that produces its output gradient (dgrad_then_lnbwd / ffn_block_bwd) when the row is one 256-wide tile.
+    if (!top_done) {
+      e->launches++;
+      KIT_TRY(ln_bwd(dy, a.s3, a.st3, a.st3 + M, e->params + w.n3.g, nullptr, e->g1, e->grads + w.n3.g, e->grads + w.n3.b, e->grads + w.l2.b, M, H, e->st));
+      bd = true;
+    }
+    pend.push_back({e->g1, H, a.hh, FF, &w.l2, 0, H, bd});
+    KIT_TRY(ffn_block_bwd(e, e->g1, w.l1, w.l2, a.z, e->gff, e->g2, e->g1b, a.s2, a.st2, w.n2, e->grads + w.ca.out.b, &bd));  // g1b = d s2
     pend.push_back({e->gff, FF, a.y2, H, &w.l1, 0, FF, false});
     // cross-attention block
-    e->launches++;
-    KIT_TRY(ln_bwd(e->g2, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1b, e->grads + w.n2.g, e->grads + w.n2.b, e->grads + w.ca.out.b, M, H, e->st));
-    pend.push_back({e->g1b, H, a.aoc, H, &w.ca.out, 0, H, true});
+    pend.push_back({e->g1b, H, a.aoc, H, &w.ca.out, 0, H, bd});
     KIT_TRY(linear_dgrad(e, e->g1b, H, w.ca.out, 0, H, e->g2, H, nullptr, 0));  // g2 = d aoc
     KIT_TRY(eattn_bwd(e, a.qc, H, a.kvc, 2 * H, a.kvc + H, 2 * H, a.aoc, H, e->g2, H, a.lsec, e->gqc, H, e->gkv, 2 * H,
                       e->gkv + H, 2 * H, nullptr));
@@ -700,17 +748,24 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
     pend.push_back({e->gkv, 2 * H, e->mem, H, &w.ca.in, H, 2 * H, false});
     KIT_TRY(linear_dgrad(e, e->gkv, 2 * H, w.ca.in, H, 2 * H, e->gmem, H, mem_grad_started ? e->gmem : nullptr, H));
     mem_grad_started = true;
-    KIT_TRY(linear_dgrad(e, e->gqc, H, w.ca.in, 0, H, e->g2, H, e->g1b, H));  // g2 = d y1
+    // d y1 = gqc Wq + g1b, then the backward of norm1 -> g1c = d s1
+    KIT_TRY(dgrad_then_lnbwd(e, e->gqc, H, w.ca.in, 0, H, e->g1b, e->g2, e->g1c, a.s1, a.st1, w.n1, e->grads + w.sa.out.b, &bd));
     // self-attention block
-    e->launches++;
-    KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1c, e->grads + w.n1.g, e->grads + w.n1.b, e->grads + w.sa.out.b, M, H, e->st));
-    pend.push_back({e->g1c, H, a.ao, H, &w.sa.out, 0, H, true});
+    pend.push_back({e->g1c, H, a.ao, H, &w.sa.out, 0, H, bd});
     KIT_TRY(linear_dgrad(e, e->g1c, H, w.sa.out, 0, H, e->g2, H, nullptr, 0));  // g2 = d ao
     KIT_TRY(eattn_bwd(e, a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, e->g2, H, a.lse, e->gqkv, 3 * H,
                       e->gqkv + H, 3 * H, e->gqkv + 2 * H, 3 * H, &e->dec_mask));
     pend.push_back({e->gqkv, 3 * H, y_in, H, &w.sa.in, 0, 3 * H, false});
-    KIT_TRY(linear_dgrad(e, e->gqkv, 3 * H, w.sa.in, 0, 3 * H, e->g0, H, e->g1c, H));  // g0 = d y_in
-    KIT_TRY(flush_wgrads(e, pend));
+    KIT_TRY(flush_wgrads(e, pend));   // before the last GEMM: fused with the next layer's norm3 backward it overwrites g1
+    if (l > 0 && lnbwd_fusable(e) && gemm_lnbwd_supported((int)M)) {   // d y_in = gqkv Win + g1c, then the backward of the layer below's norm3 -> g1
+      const DecW& wn = L.dec[l - 1];
+      DecAct& an = e->da[l - 1];
+      KIT_TRY(dgrad_then_lnbwd(e, e->gqkv, 3 * H, w.sa.in, 0, 3 * H, e->g1c, e->g0, e->g1, an.s3, an.st3, wn.n3, e->grads + wn.l2.b, &bd));
+      top_done = true;
+    } else {
+      KIT_TRY(linear_dgrad(e, e->gqkv, 3 * H, w.sa.in, 0, 3 * H, e->g0, H, e->g1c, H));  // g0 = d y_in
+      top_done = false;
+    }
     dy = e->g0;
     if (half > 0 && l == half) done();
   }
@@ -729,24 +784,34 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
   KIT_TRY(ln_bwd(e->gmem, e->ea[nl - 1].x2, e->st_encn, e->st_encn + M, e->params + L.enc_norm.g, nullptr, e->g0,
                  e->grads + L.enc_norm.g, e->grads + L.enc_norm.b, nullptr, M, H, e->st));
   bf16* dx = e->g0;
+  top_done = false;
   for (int l = nl - 1; l >= 0; --l) {
     const EncW& w = L.enc[l];
     EncAct& a = e->ea[l];
     const bf16* x_in = (l == 0) ? e->x0 : e->ea[l - 1].x2;
-    e->launches++;
-    KIT_TRY(ln_bwd(dx, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1, e->grads + w.n2.g, e->grads + w.n2.b, e->grads + w.l2.b, M, H, e->st));
-    pend.push_back({e->g1, H, a.hh, FF, &w.l2, 0, H, true});
-    KIT_TRY(ffn_block_bwd(e, e->g1, w.l1, w.l2, a.z, e->gff, e->g2));  // gff = d z, g2 = d x1
+    if (!top_done) {
+      e->launches++;
+      KIT_TRY(ln_bwd(dx, a.s2, a.st2, a.st2 + M, e->params + w.n2.g, nullptr, e->g1, e->grads + w.n2.g, e->grads + w.n2.b, e->grads + w.l2.b, M, H, e->st));
+      bd = true;
+    }
+    pend.push_back({e->g1, H, a.hh, FF, &w.l2, 0, H, bd});
+    KIT_TRY(ffn_block_bwd(e, e->g1, w.l1, w.l2, a.z, e->gff, e->g2, e->g1b, a.s1, a.st1, w.n1, e->grads + w.sa.out.b, &bd));  // g1b = d s1
     pend.push_back({e->gff, FF, a.x1, H, &w.l1, 0, FF, false});
-    e->launches++;
-    KIT_TRY(ln_bwd(e->g2, a.s1, a.st1, a.st1 + M, e->params + w.n1.g, nullptr, e->g1b, e->grads + w.n1.g, e->grads + w.n1.b, e->grads + w.sa.out.b, M, H, e->st));
-    pend.push_back({e->g1b, H, a.ao, H, &w.sa.out, 0, H, true});
+    pend.push_back({e->g1b, H, a.ao, H, &w.sa.out, 0, H, bd});
     KIT_TRY(linear_dgrad(e, e->g1b, H, w.sa.out, 0, H, e->g2, H, nullptr, 0));
     KIT_TRY(eattn_bwd(e, a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, e->g2, H, a.lse, e->gqkv, 3 * H,
                       e->gqkv + H, 3 * H, e->gqkv + 2 * H, 3 * H, &e->enc_mask));
     pend.push_back({e->gqkv, 3 * H, x_in, H, &w.sa.in, 0, 3 * H, false});
-    KIT_TRY(linear_dgrad(e, e->gqkv, 3 * H, w.sa.in, 0, 3 * H, e->g0, H, e->g1b, H));
     KIT_TRY(flush_wgrads(e, pend));
+    if (l > 0 && lnbwd_fusable(e) && gemm_lnbwd_supported((int)M)) {   // d x_in = gqkv Win + g1b, then the backward of the layer below's norm2 -> g1
+      const EncW& wn = L.enc[l - 1];
+      EncAct& an = e->ea[l - 1];
+      KIT_TRY(dgrad_then_lnbwd(e, e->gqkv, 3 * H, w.sa.in, 0, 3 * H, e->g1b, e->g0, e->g1, an.s2, an.st2, wn.n2, e->grads + wn.l2.b, &bd));
+      top_done = true;
+    } else {
+      KIT_TRY(linear_dgrad(e, e->gqkv, 3 * H, w.sa.in, 0, 3 * H, e->g0, H, e->g1b, H));
+      top_done = false;
+    }
     dx = e->g0;
     if (half > 0 && l == half) done();
   }
@@ -861,6 +926,8 @@ extern "C" int kit_engine_bind(KitEngine* e, float* params, float* grads, void* 
   {
     const char* v = getenv("KIT_FUSE_FFN");   // KIT_FUSE_FFN=0: the two-GEMM path (A/B measurements)
     e->fuse_ffn = !(v != nullptr && v[0] == '0');
+    v = getenv("KIT_FUSE_LNBWD");
+    e->fuse_lnbwd = v != nullptr && v[0] == '1';
   }
   // upload the weight-refresh tables (synchronous, bind time only)
   std::vector<int> prefix(e->L.wdescs.size() + 1, 0);
@@ -959,6 +1026,17 @@ extern "C" int kit_ffn_bwd(const void* g, const void* w2t, const void* w1t, cons
   KIT_TRY(ffn_bwd_plan(&plan, (const bf16*)g, H, (const bf16*)w2t, H, (const bf16*)w1t, FF, (const bf16*)z, (bf16*)dz, FF, (bf16*)dx, H,
                        M, H, FF));
   return ffn_launch(&plan, (cudaStream_t)stream);
+}
+
+// Tests: dx = LayerNormBackward(dy = A B^T + addend; saved sum s, mean, rstd, gamma) in the GEMM epilogue (N must be 256).
+extern "C" int kit_gemm_lnbwd(const void* A, const void* B, const void* addend, const void* s, const float* gamma, const float* mean,
+                              const float* rstd, void* dx, float* dgamma, float* dbeta, int32_t M, int32_t K, void* stream) {
+  GemmPlan p;
+  LnBwdArgs lnb{(const bf16*)s, 256, gamma, mean, rstd, dgamma, dbeta};
+  KIT_TRY(gemm_plan(&p, 0, (const bf16*)A, K, (const bf16*)B, K, dx, 256, M, 256, K, nullptr, (const bf16*)addend, 256, OUT_BF16,
+                    ACT_NONE, nullptr, 0, 1, nullptr, nullptr, &lnb));
+  KIT_REQUIRE(p.epi == EPI_ADD_LNBWD, "kit_gemm_lnbwd: the planner did not select the fused epilogue");
+  return gemm_launch(&p, (cudaStream_t)stream);
 }
 
 extern "C" int kit_gemm_bf16(int32_t mode, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,

@@ -53,6 +53,7 @@ struct FfnParams {
   float* ln_rstd;
   float ln_eps;
   int store_zh;   // forward, training: the pre-activation z and the activation h leave for the backward pass
+  LnBwdArgs lnb;  // BWD: the LayerNorm whose backward follows dx (s == null: none)
   long long* trace;   // experiments only (KIT_FFN_TRACE): clock64 marks of CTA 0, first item; see kit_ffn_trace_read
 };
 struct FfnPlan {
@@ -122,8 +123,9 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
   uint64_t* acc2_empty = acc2_full + 1;
   uint64_t* z_full = acc2_empty + 1;    // [2]  BWD: the z chunk has landed (local)
   uint64_t* z_empty = z_full + 2;       // [2]  BWD: the epilogue warps have read it (local, 16 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(z_empty + 2);
-  constexpr int N_BARS = 2 * FFN_RING + 16;
+  uint64_t* s_bars = z_empty + 2;       // [16][2] BWD + LayerNorm backward: the saved-sum tiles (local)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_bars + 2 * FFN_EPI_WARPS);
+  constexpr int N_BARS = 2 * FFN_RING + 16 + 2 * FFN_EPI_WARPS;
   const bool store_h = BWD || p.store_zh, store_z = !BWD && p.store_zh;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
     if (lane == 0) {
       tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
       tma_prefetch_desc(&tmS);
-      if (!BWD) tma_prefetch_desc(&tmY);
+      if (!BWD || p.lnb.s != nullptr) tma_prefetch_desc(&tmY);
       if (store_h) tma_prefetch_desc(&tmHh);
       if (BWD || store_z) tma_prefetch_desc(&tmZ);
     }
@@ -389,9 +391,30 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
       named_bar_sync(13, 32 * FFN_EPI_WARPS);   // every h / z tile has been read: the region becomes the staging tiles
       const uint32_t tmem_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(256 + cg * 64);
       const int colg = cg * 64;
-      if (BWD) {   // dx = acc2 + g: one 2 KB staging tile per warp inside h_s (the z buffers may already be refilling)
-        const uint32_t t = h_u32 + uint32_t(warp - 2) * 2048;
-        const uint32_t row64 = t + lane * 64, sw64 = (lane >> 1) & 3;
+      if (BWD) {   // dx = acc2 + g, optionally followed by the backward of the LayerNorm that fed this block (lnbwd_rows)
+        const uint32_t t_sub[2] = {h_u32 + uint32_t(warp - 2) * 4096, h_u32 + uint32_t(warp - 2) * 4096 + 2048};
+        const bool fuse_ln = p.lnb.s != nullptr;
+        // saved-sum tiles: every z chunk and weight slot of this item has been consumed (acc2_full), and the producer does not
+        // start the next item before x_empty: warps 0..7 stage in the second z buffer, warps 8..15 in the weight ring
+        const int ew = warp - 2;
+        const uint32_t s_base = ew < 8 ? z_u32 + FFN_HC_BYTES + uint32_t(ew) * 4096 : smem_u32(ring) + uint32_t(ew - 8) * 4096;
+        const uint32_t s_sub[2] = {s_base, s_base + 2048};
+        uint64_t* s_bar = &s_bars[ew * 2];
+        float ln_mean = 0.f, ln_rstd = 0.f;
+        if (fuse_ln) {
+          if (lane == 0) {
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              mbar_arrive_expect_tx(&s_bar[sub], 2048);
+              tma_load_2d_a(s_sub[sub], &tmY, &s_bar[sub], colg + sub * 32, row0);
+            }
+          }
+          __syncwarp();
+          if (row0 + lane < p.M) {
+            ln_mean = __ldg(p.lnb.mean + row0 + lane);
+            ln_rstd = __ldg(p.lnb.rstd + row0 + lane);
+          }
+        }
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
           uint32_t r[32];
@@ -402,10 +425,9 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
             __syncwarp();
             if (lane == 0) {
               if (rank == 0) mbar_arrive(acc2_empty); else mbar_arrive_cluster_relaxed(acc2_empty, 0);
-              tma_store_wait_read_n<0>();   // the first half has left the staging tile
             }
-            __syncwarp();
           }
+          const uint32_t row64 = t_sub[sub] + lane * 64, sw64 = (lane >> 1) & 3;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float v[8];
@@ -417,19 +439,28 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
             add_pair(v[4], v[5], cc.x, cc.y); add_pair(v[6], v[7], d.x, d.y);
             sts128(row64 + ((i ^ sw64) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
           }
+        }
+        auto store = [&](int sub) {
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d_a(&tmS, t, colg + sub * 32, row0);
+            tma_store_2d_a(&tmS, t_sub[sub], colg + sub * 32, row0);
             tma_store_commit();
           }
+        };
+        if (fuse_ln) {
+          mbar_wait(&s_bar[0], it & 1);
+          mbar_wait(&s_bar[1], it & 1);
+          lnbwd_rows(p.lnb, t_sub, s_sub, ln_mean, ln_rstd, colg, q, cg, lane, ln_stats, 9 + q, 14, 32 * FFN_EPI_WARPS, store);
+        } else {
+          store(0);
+          store(1);
         }
+        // the staging tiles cover h_s and the first z buffer: the producer (next item's x, then z) starts only now
+        if (lane == 0) tma_store_wait_read_n<0>();
         __syncwarp();
         if (lane == 0) mbar_arrive(x_empty);
-        if (item + item_stride < p.n_items) {
-          if (lane == 0) tma_store_wait_read_n<0>();
-          named_bar_sync(13, 32 * FFN_EPI_WARPS);
-        }
+        if (item + item_stride < p.n_items) named_bar_sync(13, 32 * FFN_EPI_WARPS);
         continue;
       }
       const uint32_t t_sub[2] = {h_u32 + uint32_t(warp - 2) * 4096, h_u32 + uint32_t(warp - 2) * 4096 + 2048};
@@ -556,7 +587,8 @@ int ffn_fwd_plan(FfnPlan* plan, const bf16* x, int64_t ldx, const bf16* w1, int6
                  const float* gamma, const float* beta, float* mean, float* rstd, float eps, int M, int H, int FF, int store_zh);
 // dz = (g . W2) * gelu'(z) -> dz_out [M, FF];  dx = dz . W1 + g -> dx [M, H].  w2t = W2^T [FF, H], w1t = W1^T [H, FF] (bf16).
 int ffn_bwd_plan(FfnPlan* plan, const bf16* g, int64_t ldg, const bf16* w2t, int64_t ldw2t, const bf16* w1t, int64_t ldw1t,
-                 const bf16* z, bf16* dz_out, int64_t ldzh, bf16* dx, int64_t lddx, int M, int H, int FF);
+                 const bf16* z, bf16* dz_out, int64_t ldzh, bf16* dx, int64_t lddx, int M, int H, int FF,
+                 const LnBwdArgs* lnb = nullptr);
 bool ffn_fwd_supported(int H, int FF);
 int ffn_launch(const FfnPlan* plan, cudaStream_t stream);
 

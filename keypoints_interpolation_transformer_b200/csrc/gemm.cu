@@ -70,7 +70,7 @@ static long long* g_trace_buf = nullptr;
 #define KIT_GEMM_FOR_ALL(X)                                                                                     \
   X(128, 0, EPI_STORE) X(128, 0, EPI_ADD) X(128, 0, EPI_GELU) X(128, 0, EPI_GELU_BWD) X(128, 0, EPI_F32) X(128, 0, EPI_GENERIC) \
   X(256, 0, EPI_STORE) X(256, 0, EPI_ADD) X(256, 0, EPI_GELU) X(256, 0, EPI_GELU_BWD) X(256, 0, EPI_F32) X(256, 0, EPI_GENERIC) \
-  X(256, 0, EPI_ADD_LN)                                                                                          \
+  X(256, 0, EPI_ADD_LN) X(256, 0, EPI_ADD_LNBWD)                                                                 \
   X(128, 1, EPI_F32) X(128, 1, EPI_GENERIC) X(256, 1, EPI_F32) X(256, 1, EPI_GENERIC)
 #define KIT_GEMM_KERNEL_BG(BN) gemm_tcgen05_kernel<BN, 1, ((BN) == 256 ? 2 : 1), EPI_F32, true>
 
@@ -103,13 +103,19 @@ int gemm_init_attributes() {
   return status == 0 ? KIT_OK : KIT_ERR_CUDA;
 }
 
+// EPI_ADD_LNBWD stages the saved-sum tiles through the operand ring once the accumulator is complete: one 256-row item per CTA pair
+bool gemm_lnbwd_supported(int M) {
+  if (gemm_init_attributes()) return false;
+  return (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM) <= g_num_sms / 2;
+}
+
 static bool aligned16(const void* ptr, int64_t ld_elems, size_t esize) {
   return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ((size_t)ld_elems * esize) % 16 == 0;
 }
 
 int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, void* C, int64_t ldc,
               int M, int N, int K, const float* bias, const bf16* addend, int64_t ld_addend, int out_kind, int act,
-              bf16* aux, int64_t ld_aux, int split_k, float* bias_grad, const GemmLN* ln) {
+              bf16* aux, int64_t ld_aux, int split_k, float* bias_grad, const GemmLN* ln, const LnBwdArgs* lnb) {
   KIT_REQUIRE(mode == 0 || mode == 1, "gemm mode must be 0 (TN) or 1 (wgrad)");
   KIT_REQUIRE(M > 0 && N > 0 && K > 0, "gemm dims must be positive (M=%d N=%d K=%d)", M, N, K);
   KIT_REQUIRE(act == ACT_NONE || aux != nullptr, "gelu epilogues need the aux tensor");
@@ -165,13 +171,19 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
         if (ln != nullptr && N == 256 && bn == 256 && aligned16(ln->y, ln->ldy, 2) && aligned16(ln->gamma, 0, 4) &&
             aligned16(ln->beta, 0, 4) && (bias == nullptr || aligned16(bias, 0, 4)))
           epi = EPI_ADD_LN;
+        else if (lnb != nullptr && lnb->s != nullptr && N == 256 && bn == 256 && aligned16(lnb->s, lnb->ld_s, 2) &&
+                 aligned16(lnb->gamma, 0, 4) && (bias == nullptr || aligned16(bias, 0, 4)))
+          epi = EPI_ADD_LNBWD;
       }
       else if (act == ACT_GELU && addend == nullptr && aligned16(aux, ld_aux, 2)) epi = EPI_GELU;
       else if (act == ACT_GELU_BWD && addend == nullptr && aligned16(aux, ld_aux, 2)) epi = EPI_GELU_BWD;
     }
   }
+  if (epi == EPI_ADD_LNBWD && groups > g_num_sms / cl) epi = EPI_ADD;   // the fused kind stages through the operand ring: one item per CTA
   plan->epi = epi;
   p.bias_grad = (mode == 1 && epi == EPI_F32) ? bias_grad : nullptr;   // else the caller sums the columns of dy itself
+  p.lnb = LnBwdArgs{nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (epi == EPI_ADD_LNBWD) p.lnb = *lnb;
   p.ln_gamma = p.ln_beta = nullptr;
   p.ln_mean = p.ln_rstd = nullptr;
   p.ln_eps = 0.f;
@@ -185,9 +197,12 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
     if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   } else if (epi != EPI_GENERIC) {
     if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-    const bool add_kind = epi == EPI_ADD || epi == EPI_ADD_LN;
+    const bool add_kind = epi == EPI_ADD || epi == EPI_ADD_LN || epi == EPI_ADD_LNBWD;
     const bf16* side = add_kind ? addend : aux;
     const int64_t side_ld = add_kind ? ld_addend : ld_aux;
+    if (epi == EPI_ADD_LNBWD) {
+      if ((rc = make_tensor_map_2d_typed(&plan->tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, lnb->s, (uint64_t)N, (uint64_t)M, (uint64_t)lnb->ld_s * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    }
     if (epi == EPI_ADD_LN) {
       if ((rc = make_tensor_map_2d_typed(&plan->tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, ln->y, (uint64_t)N, (uint64_t)M, (uint64_t)ln->ldy * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     }
@@ -349,6 +364,7 @@ int ffn_fwd_plan(FfnPlan* plan, const bf16* x, int64_t ldx, const bf16* w1, int6
   p.M = M; p.FF = FF; p.n_items = (M + 255) / 256;
   p.b1 = b1; p.b2 = b2; p.ln_gamma = gamma; p.ln_beta = beta; p.ln_mean = mean; p.ln_rstd = rstd; p.ln_eps = eps;
   p.store_zh = store_zh;
+  p.lnb = LnBwdArgs{nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
   plan->bwd = 0;
   p.trace = nullptr;
   if (getenv("KIT_FFN_TRACE") != nullptr) {
@@ -362,7 +378,7 @@ int ffn_fwd_plan(FfnPlan* plan, const bf16* x, int64_t ldx, const bf16* w1, int6
 }
 
 int ffn_bwd_plan(FfnPlan* plan, const bf16* g, int64_t ldg, const bf16* w2t, int64_t ldw2t, const bf16* w1t, int64_t ldw1t,
-                 const bf16* z, bf16* dz_out, int64_t ldzh, bf16* dx, int64_t lddx, int M, int H, int FF) {
+                 const bf16* z, bf16* dz_out, int64_t ldzh, bf16* dx, int64_t lddx, int M, int H, int FF, const LnBwdArgs* lnb) {
   // the forward plan with x := g, W1 := W2^T, W2 := W1^T; the z map becomes a LOAD map ([128 x 64] boxes)
   static const float dummy[4] = {0.f, 0.f, 0.f, 0.f};
   KIT_REQUIRE(z != nullptr && dz_out != nullptr && dx != nullptr, "fused FFN backward: null tensor");
@@ -375,6 +391,12 @@ int ffn_bwd_plan(FfnPlan* plan, const bf16* g, int64_t ldg, const bf16* w2t, int
   plan->p.ln_mean = plan->p.ln_rstd = nullptr;
   plan->p.store_zh = 0;
   plan->bwd = 1;
+  if (lnb != nullptr && lnb->s != nullptr) {
+    KIT_REQUIRE(aligned16(lnb->s, lnb->ld_s, 2) && aligned16(lnb->gamma, 0, 4), "fused FFN backward: LayerNorm tensors must be 16-byte aligned");
+    plan->p.lnb = *lnb;   // tmY (unused by the backward otherwise) becomes the load map of the saved sum: [32 x 32] boxes
+    if ((rc = make_tensor_map_2d_typed(&plan->tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, lnb->s, (uint64_t)H, (uint64_t)M,
+                                       (uint64_t)lnb->ld_s * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  }
   return KIT_OK;
 }
 

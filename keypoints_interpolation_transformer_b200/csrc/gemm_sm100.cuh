@@ -37,7 +37,20 @@ enum {
   EPI_GENERIC = 5,   // any combination through direct global accesses (pitches / extents a tensor map cannot describe)
   EPI_ADD_LN = 6,    // EPI_ADD + LayerNorm of the sum over the full row (N = BN = 256): s = acc + bias + addend -> C (bf16),
                      // y = LN(s) * gamma + beta -> D (bf16), mean / rstd of the bf16-rounded s (what the backward reads)
-  EPI_KINDS = 7
+  EPI_ADD_LNBWD = 7, // EPI_ADD followed by the BACKWARD of the LayerNorm whose output gradient the sum is (N = BN = 256):
+                     // dy = acc + addend ; dx = rstd (dy g - mean(dy g) - xhat mean(dy g xhat)) -> C (bf16); dgamma / dbeta partials
+  EPI_KINDS = 8
+};
+
+// LayerNorm backward fused behind the GEMM (or the fused FFN kernel) that produces the gradient w.r.t. the LayerNorm output.
+struct LnBwdArgs {
+  const bf16* s;        // the saved pre-norm sum [M, 256] (what the forward normalised), null = not fused
+  int64_t ld_s;
+  const float* gamma;   // LayerNorm weight [256]
+  const float* mean;    // per-row statistics of s [M]
+  const float* rstd;
+  float* dgamma;        // [256] += sum_rows dy * xhat
+  float* dbeta;         // [256] += sum_rows dy
 };
 
 struct GemmParams {
@@ -57,6 +70,7 @@ struct GemmParams {
   float* ln_mean;
   float* ln_rstd;
   float ln_eps;
+  LnBwdArgs lnb;      // EPI_ADD_LNBWD
   float* bias_grad;   // MODE 1, BG kernels: bias_grad[m] += sum_k A[k, m] (column sums of dy), else null
   long long* trace;   // experiments only (KIT_GEMM_TRACE): clock64 marks of CTA 0, see kit_gemm_trace_read
 };
@@ -83,7 +97,7 @@ constexpr int gemm_threads() { return 64 + 32 * gemm_epi_warps<BN>(); }
 template <int EPI>
 constexpr int gemm_epi_tiles() { return EPI == EPI_GENERIC ? 0 : (EPI == EPI_GELU || EPI == EPI_GELU_BWD) ? 3 : 2; }
 template <int EPI>
-constexpr int gemm_tail_bytes() { return GEMM_SMEM_TAIL + (EPI == EPI_ADD_LN ? GEMM_LN_STATS : 0); }
+constexpr int gemm_tail_bytes() { return GEMM_SMEM_TAIL + ((EPI == EPI_ADD_LN || EPI == EPI_ADD_LNBWD) ? GEMM_LN_STATS : 0); }
 template <int BN, int CL>
 constexpr int gemm_stage_bytes() { return GEMM_BM * GEMM_BK * 2 + (BN / CL) * GEMM_BK * 2; }
 template <int BN, int CL, int EPI>
@@ -255,6 +269,136 @@ __device__ __forceinline__ void gemm_epilogue_sub(const GemmParams& p, int col0,
   }
 }
 
+// ---------------------------------------------------------------- LayerNorm backward on accumulator rows
+// A row's 256 columns sit in the four epilogue warps of one TMEM lane quadrant: warp column group cg holds columns
+// [64 cg, 64 cg + 64) of row (32 q + lane) as 2 x 16 packed bf16 pairs.
+// sum over the 32 lanes of a[c] for every c: on return lane l holds column l's sum (31 shuffles: halve the array each step)
+__device__ __forceinline__ float warp_col_reduce32(float (&a)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float keep = up ? a[i + h] : a[i];
+      const float send = up ? a[i] : a[i + h];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return a[0];
+}
+// The gradient w.r.t. the LayerNorm output (dy, bf16) sits in the warp's two [32 rows x 32 columns] staging tiles (SWIZZLE_64B:
+// 16-byte chunk i of row r at chunk i ^ ((r >> 1) & 3)); s_sub: the saved pre-norm sum in two more tiles of the same layout.  On return the tiles hold dx and
+// store(sub) has been called for each (fence + TMA store are the caller's).  ln_stats: [4][128] float2 scratch shared by the
+// quadrant's four warps; bar_id: their named barrier (128 threads).  Register budget (96 per thread next to 16 epilogue
+// warps): dy is re-read from the tiles in every pass, only one 32-column array is alive at a time.
+template <typename StoreFn>
+__device__ __forceinline__ void lnbwd_rows(const LnBwdArgs& a, const uint32_t (&t_sub)[2], const uint32_t (&s_sub)[2], float mean,
+                                           float rstd, int colg, int q, int cg, int lane, float2* ln_stats, int bar_id,
+                                           int bar_all, int n_epi_threads, StoreFn&& store) {
+  const uint32_t sw64 = (lane >> 1) & 3;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 in = lds128(t_sub[sub] + lane * 64 + ((i ^ sw64) << 4));
+      const uint32_t vw[4] = {in.x, in.y, in.z, in.w};
+      const uint4 sc = lds128(s_sub[sub] + lane * 64 + ((i ^ sw64) << 4));
+      const uint32_t sw_[4] = {sc.x, sc.y, sc.z, sc.w};
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(a.gamma + colg + sub * 32 + 8 * i));
+      const float4 gb = __ldg(reinterpret_cast<const float4*>(a.gamma + colg + sub * 32 + 8 * i + 4));
+      const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 v = unpack_bf16(vw[u]), x = unpack_bf16(sw_[u]);
+        const float g0 = v.x * gm[2 * u], g1 = v.y * gm[2 * u + 1];
+        s1 += g0 + g1;
+        s2 = fmaf(g0, (x.x - mean) * rstd, s2);
+        s2 = fmaf(g1, (x.y - mean) * rstd, s2);
+      }
+    }
+  const int rl = q * 32 + lane;
+  ln_stats[cg * 128 + rl] = make_float2(s1, s2);
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+  const float2 p0 = ln_stats[rl], p1 = ln_stats[128 + rl], p2 = ln_stats[256 + rl], p3 = ln_stats[384 + rl];
+  const float c1 = ((p0.x + p1.x) + (p2.x + p3.x)) * (1.f / 256.f);
+  const float c2 = ((p0.y + p1.y) + (p2.y + p3.y)) * (1.f / 256.f);
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // everyone has read the partials: the slots may be reused
+  float sb[2], sg[2];   // this warp's 32-row partial of dbeta / dgamma for column colg + 32 sub + lane
+#pragma unroll
+  for (int sub = 0; sub < 2; ++sub) {
+    const uint32_t row64 = t_sub[sub] + lane * 64;
+    float col[32];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 in = lds128(row64 + ((i ^ sw64) << 4));
+      const float2 v0 = unpack_bf16(in.x), v1 = unpack_bf16(in.y), v2 = unpack_bf16(in.z), v3 = unpack_bf16(in.w);
+      col[8 * i] = v0.x; col[8 * i + 1] = v0.y; col[8 * i + 2] = v1.x; col[8 * i + 3] = v1.y;
+      col[8 * i + 4] = v2.x; col[8 * i + 5] = v2.y; col[8 * i + 6] = v3.x; col[8 * i + 7] = v3.y;
+    }
+    sb[sub] = warp_col_reduce32(col, lane);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 in = lds128(row64 + ((i ^ sw64) << 4));
+      const uint32_t vw[4] = {in.x, in.y, in.z, in.w};
+      const uint4 sc = lds128(s_sub[sub] + lane * 64 + ((i ^ sw64) << 4));
+      const uint32_t sw_[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 v = unpack_bf16(vw[u]), x = unpack_bf16(sw_[u]);
+        col[8 * i + 2 * u] = v.x * ((x.x - mean) * rstd);
+        col[8 * i + 2 * u + 1] = v.y * ((x.y - mean) * rstd);
+      }
+    }
+    sg[sub] = warp_col_reduce32(col, lane);
+  }
+#pragma unroll
+  for (int sub = 0; sub < 2; ++sub) {   // dx = rstd (dy gamma - c1 - xhat c2), in place, and out
+    const uint32_t row64 = t_sub[sub] + lane * 64;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t addr = row64 + ((i ^ sw64) << 4);
+      const uint4 in = lds128(addr);
+      const uint32_t vw[4] = {in.x, in.y, in.z, in.w};
+      const uint4 sc = lds128(s_sub[sub] + lane * 64 + ((i ^ sw64) << 4));
+      const uint32_t sw_[4] = {sc.x, sc.y, sc.z, sc.w};
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(a.gamma + colg + sub * 32 + 8 * i));
+      const float4 gb = __ldg(reinterpret_cast<const float4*>(a.gamma + colg + sub * 32 + 8 * i + 4));
+      const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 v = unpack_bf16(vw[u]), x = unpack_bf16(sw_[u]);
+        const float d0 = rstd * (v.x * gm[2 * u] - c1 - (x.x - mean) * rstd * c2);
+        const float d1 = rstd * (v.y * gm[2 * u + 1] - c1 - (x.y - mean) * rstd * c2);
+        o[u] = pack_bf16(d0, d1);
+      }
+      sts128(addr, o[0], o[1], o[2], o[3]);
+    }
+    store(sub);
+  }
+  // dbeta / dgamma: the four quadrants' partials meet in shared memory (the statistics scratch, now [4][256] floats), so each
+  // column costs ONE atomic per CTA -- 512-way contention per address (one per warp) was slower than the kernel it replaces
+  float* scratch = reinterpret_cast<float*>(ln_stats);
+  const int c0 = colg + lane;
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_all), "r"(n_epi_threads) : "memory");   // the scratch is free (statistics / previous round read)
+    scratch[q * 256 + c0] = which == 0 ? sb[0] : sg[0];
+    scratch[q * 256 + c0 + 32] = which == 0 ? sb[1] : sg[1];
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_all), "r"(n_epi_threads) : "memory");
+    if (q == 0) {
+      float* dst = which == 0 ? a.dbeta : a.dgamma;
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const int c = c0 + 32 * sub;
+        atomicAdd(dst + c, (scratch[c] + scratch[256 + c]) + (scratch[512 + c] + scratch[768 + c]));
+      }
+    }
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_all), "r"(n_epi_threads) : "memory");   // before the scratch holds statistics again
+}
+
 // BG (MODE 1 only): the bias gradient of the same Linear -- the column sums of dy, i.e. the row sums of the A^T operand --
 // comes out of the tensor pipe too: every k-step issues one more MMA of the A tile against an all-ones [16 x 16] B tile
 // into 16 spare accumulator columns (one accumulator stage instead of two: weight-gradient work items are one per CTA
@@ -283,7 +427,8 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
   uint64_t* tmem_full = empty + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;   // [2]
   uint64_t* in_bars = tmem_empty + 2;     // [EPI_WARPS][2] epilogue input tiles (addend / GELU' pre-activation)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_bars + 2 * GEMM_MAX_EPI_WARPS);
+  uint64_t* s_bars = in_bars + 2 * GEMM_MAX_EPI_WARPS;   // [EPI_WARPS][2] EPI_ADD_LNBWD: the saved-sum tiles
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_bars + 2 * GEMM_MAX_EPI_WARPS);
   uint8_t* ones_tile = reinterpret_cast<uint8_t*>(full) + 1024;   // BG: 1 KB of bf16 1.0 (any layout of all-ones is all-ones)
   float2* ln_stats = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(full) + 2048);   // EPI_ADD_LN: [4][128]
 
@@ -306,8 +451,8 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
       if (EPI != EPI_GENERIC) tma_prefetch_desc(&tmC);
-      if (EPI == EPI_ADD || EPI == EPI_GELU || EPI == EPI_GELU_BWD || EPI == EPI_ADD_LN) tma_prefetch_desc(&tmAux);
-      if (EPI == EPI_ADD_LN) tma_prefetch_desc(&tmD);
+      if (EPI == EPI_ADD || EPI == EPI_GELU || EPI == EPI_GELU_BWD || EPI == EPI_ADD_LN || EPI == EPI_ADD_LNBWD) tma_prefetch_desc(&tmAux);
+      if (EPI == EPI_ADD_LN || EPI == EPI_ADD_LNBWD) tma_prefetch_desc(&tmD);
     }
     // full[s]: the producer's arrive.expect_tx (CL = 2: only the leader's is used; it collects the bytes of both CTAs);
     // empty[s], tmem_full[s]: one tcgen05.commit arrival (multicast to both CTAs when CL = 2);
@@ -317,6 +462,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
       const bool is_tmem_empty = i >= 2 * STAGES + 2 && i < 2 * STAGES + 4;
       mbar_init(&full[i], is_tmem_empty ? EPI_WARPS * CL : 1);
     }
+    if (EPI == EPI_ADD_LNBWD) mbar_init(&s_bars[lane], 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -463,28 +609,86 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
         t_sub[0] = tiles + (rr % 3) * 2048;
         t_sub[1] = tiles + ((rr + 1) % 3) * 2048;
         rr += 2;
-      } else if (EPI == EPI_STORE || EPI == EPI_ADD || EPI == EPI_ADD_LN) {
+      } else if (EPI == EPI_STORE || EPI == EPI_ADD || EPI == EPI_ADD_LN || EPI == EPI_ADD_LNBWD) {
         t_sub[1] = tiles + 2048;
       }
       if (EPI != EPI_GENERIC && have0 && p.bias != nullptr && lane < 2 && colg + 32 * lane < p.N) prefetch_l1(p.bias + colg + 32 * lane);
-      if (EPI == EPI_ADD || EPI == EPI_GELU_BWD || EPI == EPI_ADD_LN) {   // input tiles land while the MMAs of this tile are still running
+      if (EPI == EPI_ADD || EPI == EPI_GELU_BWD || EPI == EPI_ADD_LN || EPI == EPI_ADD_LNBWD) {   // input tiles land while the MMAs of this tile are still running
         if (lane == 0 && have0) {
           tma_store_wait_read_n<1>();   // the tile(s) below were last read by stores that are at least 2 groups old
           mbar_arrive_expect_tx(&in_bar[0], 2048);
           tma_load_2d_a(t_sub[0], &tmAux, &in_bar[0], colg, row0);
           if (have1) {
-            if (EPI == EPI_ADD || EPI == EPI_ADD_LN) tma_store_wait_read_n<0>();   // two tiles only: tile 1 carried the most recent store
+            if (EPI == EPI_ADD || EPI == EPI_ADD_LN || EPI == EPI_ADD_LNBWD) tma_store_wait_read_n<0>();   // two tiles only: tile 1 carried the most recent store
             mbar_arrive_expect_tx(&in_bar[1], 2048);
             tma_load_2d_a(t_sub[1], &tmAux, &in_bar[1], colg + 32, row0);
           }
         }
         __syncwarp();
       }
+      float lnb_mean = 0.f, lnb_rstd = 0.f;
+      if (EPI == EPI_ADD_LNBWD && have0 && row0 + lane < p.M) {
+        lnb_mean = __ldg(p.lnb.mean + row0 + lane);
+        lnb_rstd = __ldg(p.lnb.rstd + row0 + lane);
+      }
       mbar_wait(&tmem_full[as], aph);
       if (it == 0 && warp == 2) mark(6);
       tc_fence_after();
       if (!have0) {   // nothing to write: only keep the TMEM protocol alive
         release_tmem();
+        continue;
+      }
+      if (EPI == EPI_ADD_LNBWD) {   // dy = acc (+ bias) + addend (written over the addend tile), then the LayerNorm backward
+        // The saved-sum tiles land in the operand ring: this kind runs one work item per CTA (planner), so once the
+        // accumulator is complete nothing else touches the ring.
+        const uint32_t s_sub[2] = {smem_u32(smem) + uint32_t(warp - 2) * 4096, smem_u32(smem) + uint32_t(warp - 2) * 4096 + 2048};
+        uint64_t* s_bar = &s_bars[(warp - 2) * 2];
+        if (lane == 0) {
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            mbar_arrive_expect_tx(&s_bar[sub], 2048);
+            tma_load_2d_a(s_sub[sub], &tmD, &s_bar[sub], colg + sub * 32, row0);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          uint32_t r[32];
+          tmem_ld32(tmem_row + uint32_t(sub * 32), r);
+          mbar_wait(&in_bar[sub], in_ph[sub]);
+          in_ph[sub] ^= 1;
+          tmem_ld_wait();
+          if (sub == 1) release_tmem();
+          const int col0 = colg + sub * 32;
+          const uint32_t row64 = t_sub[sub] + lane * 64, sw64 = (lane >> 1) & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[8 * i + u]);
+            if (p.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * i));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * i + 4));
+              add_pair(v[0], v[1], b0.x, b0.y); add_pair(v[2], v[3], b0.z, b0.w);
+              add_pair(v[4], v[5], b1.x, b1.y); add_pair(v[6], v[7], b1.z, b1.w);
+            }
+            const uint4 in = lds128(row64 + ((i ^ sw64) << 4));
+            const float2 a = unpack_bf16(in.x), b = unpack_bf16(in.y), c = unpack_bf16(in.z), d = unpack_bf16(in.w);
+            add_pair(v[0], v[1], a.x, a.y); add_pair(v[2], v[3], b.x, b.y);
+            add_pair(v[4], v[5], c.x, c.y); add_pair(v[6], v[7], d.x, d.y);
+            sts128(row64 + ((i ^ sw64) << 4), pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          }
+        }
+        mbar_wait(&s_bar[0], 0);
+        mbar_wait(&s_bar[1], 0);
+        lnbwd_rows(p.lnb, t_sub, s_sub, lnb_mean, lnb_rstd, colg, q, cg, lane, ln_stats, 1 + q, 5, 32 * EPI_WARPS, [&](int sub) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d_a(&tmC, t_sub[sub], colg + sub * 32, row0);
+            tma_store_commit();
+          }
+        });
         continue;
       }
       if (EPI == EPI_ADD_LN) {   // N = BN = 256: the four warps with this warp's TMEM quadrant hold complete rows between them
@@ -671,8 +875,10 @@ struct GemmLN {
 };
 int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* B, int64_t ldb, void* C, int64_t ldc,
               int M, int N, int K, const float* bias, const bf16* addend, int64_t ld_addend, int out_kind, int act,
-              bf16* aux, int64_t ld_aux, int split_k, float* bias_grad = nullptr, const GemmLN* ln = nullptr);
+              bf16* aux, int64_t ld_aux, int split_k, float* bias_grad = nullptr, const GemmLN* ln = nullptr,
+              const LnBwdArgs* lnb = nullptr);
 int gemm_launch(const GemmPlan* plan, cudaStream_t stream);
+bool gemm_lnbwd_supported(int M);
 int gemm_init_attributes();
 
 }  // namespace kit

@@ -109,7 +109,7 @@ class StepEngine:
         K.check(K.lib().kit_engine_backward(self._h, K.ptr(dpred), cb, None, K.stream_ptr()))
         self.bwd_launches = K.lib().kit_engine_last_launches(self._h)
 
-    PROF_CATEGORIES = ("gemm_tn", "gemm_wgrad", "attn_fwd", "attn_bwd")
+    PROF_CATEGORIES = ("gemm_tn", "gemm_wgrad", "attn_fwd", "attn_bwd", "ffn")
 
     def set_profiling(self, on):
         K.check(K.lib().kit_engine_set_profiling(self._h, 1 if on else 0))

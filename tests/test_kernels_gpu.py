@@ -290,3 +290,33 @@ def test_ffn_fused_bwd(M, FF):
     assert torch.isfinite(dz.float()).all() and torch.isfinite(dx.float()).all()
     assert _rel(dz, dz_ref) < 5e-3
     assert _rel(dx, dx_ref) < 5e-3
+
+
+@pytest.mark.parametrize("M,Kd", [(128, 256), (16384, 768), (1000, 2048), (18944, 256)])
+def test_gemm_layernorm_backward_epilogue(M, Kd):
+    """EPI_ADD_LNBWD: dy = A B^T + addend stays on chip and the LayerNorm backward (row statistics across the four column-group
+    warps, dgamma / dbeta partials by warp transpose-reduce) runs in the epilogue -- against fp32 torch autograd."""
+    H = 256
+    g = torch.Generator(device="cpu").manual_seed(M + Kd)
+    a = _bf(torch.randn(M, Kd, generator=g)).to(DEV)
+    b = _bf(torch.randn(H, Kd, generator=g) / math.sqrt(Kd)).to(DEV)
+    add = _bf(torch.randn(M, H, generator=g)).to(DEV)
+    s = _bf(torch.randn(M, H, generator=g) * 2 + 0.3).to(DEV)
+    gamma = (1 + 0.2 * torch.randn(H, generator=g)).to(DEV)
+    sf = s.float()
+    mean, var = sf.mean(1), sf.var(1, unbiased=False)
+    rstd = (var + 1e-5).rsqrt()
+    dx = torch.full((M, H), float("nan"), dtype=torch.bfloat16, device=DEV)
+    dgamma, dbeta = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    K.check(K.lib().kit_gemm_lnbwd(K.ptr(a), K.ptr(b), K.ptr(add), K.ptr(s), K.ptr(gamma), K.ptr(mean.contiguous()),
+                                   K.ptr(rstd.contiguous()), K.ptr(dx), K.ptr(dgamma), K.ptr(dbeta), M, Kd, _sp()))
+    torch.cuda.synchronize()
+    dy = _bf(a.float() @ b.float().t() + add.float()).float()           # the kernel rounds dy to bf16 like the unfused path
+    sr = sf.clone().requires_grad_(True)
+    gp = gamma.clone().requires_grad_(True)
+    bp = torch.zeros(H, device=DEV, requires_grad=True)
+    torch.nn.functional.layer_norm(sr, (H,), gp, bp, 1e-5).backward(dy)
+    assert torch.isfinite(dx.float()).all()
+    assert _rel(dx, sr.grad) < 5e-3
+    assert _rel(dgamma, gp.grad) < 2e-3
+    assert _rel(dbeta, bp.grad) < 2e-3

@@ -293,3 +293,28 @@ def test_euclidean_distance_loss_kernel(golden_dir):
     assert abs(d.item() - float(g["distance"])) <= 1e-5 * float(g["distance"])
     np.testing.assert_allclose(o.grad.cpu().numpy(), g["distance_grad"], rtol=1e-5, atol=1e-6)
     assert o.grad[3, 5].abs().max().item() == 0.0
+
+
+def test_fused_layernorm_backward_path_matches_default(monkeypatch):
+    """KIT_FUSE_LNBWD=1 (LayerNorm backward inside the dgrad GEMM epilogues and the fused feed-forward backward) and
+    KIT_FUSE_FFN=0 (the two-GEMM feed-forward path) produce the default path's loss and gradients."""
+    Kp, H, L, NH, B, T = 54, 256, 2, 8, 8, 64
+    inputs, gt, mask = (t.to(DEV) for t in ko.synthetic_batch(B, T, Kp, seed=31))
+    results = {}
+    for name, env in (("default", {}), ("lnbwd", {"KIT_FUSE_LNBWD": "1"}), ("no_ffn", {"KIT_FUSE_FFN": "0"}),
+                      ("no_ffn_lnbwd", {"KIT_FUSE_FFN": "0", "KIT_FUSE_LNBWD": "1"})):
+        for k in ("KIT_FUSE_LNBWD", "KIT_FUSE_FFN"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        m = _build(2 * Kp, H, L, NH)          # the switches are read when an engine is bound
+        m.train()
+        step = train.TrainStep(m, optim.FlatAdam(m, lr=0.0), criterion="mse")
+        loss = step.forward_backward(inputs, gt, mask)
+        torch.cuda.synchronize()
+        results[name] = (loss.item(), m.flat_grads.clone(), step.last_launches)
+    l0, g0, n0 = results["default"]
+    for name, (l, g, n) in results.items():
+        assert abs(l - l0) <= 2e-3 * abs(l0), name
+        assert _rel(g, g0) < 1e-2, name                      # same math, bf16 rounding points differ slightly
+    assert results["lnbwd"][2] < n0 < results["no_ffn"][2]   # fewer launches with every fusion
