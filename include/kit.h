@@ -256,7 +256,8 @@ int kit_gemm_lnbwd(const void* A, const void* B, const void* addend, const void*
 int kit_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                       int64_t ldo, float* lse, int32_t B, int32_t NH, int32_t Sq, int32_t Sk, int32_t d,
                       const KitAttnMask* mask, void* stream);
-/* dq_accum: fp32 workspace [B*Sq, NH*d], required only when Sk > 64 (dQ summed over key tiles). */
+/* dq_accum: fp32 workspace of B*Sq*NH*d + B*NH*Sq floats, required only when Sk > 64 (dQ summed over key tiles, followed by
+ * the per-row sums of dO * O). */
 int kit_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                       const void* out, int64_t ldo, const void* dout, int64_t ld_do, const float* lse, void* dq,
                       int64_t ld_dq, void* dk, int64_t ld_dk, void* dv, int64_t ld_dv, float* dq_accum, int32_t B,

@@ -384,6 +384,240 @@ __global__ void dq_convert_kernel(const float* __restrict__ acc, bf16* __restric
   store8(dq + r * ld_dq + c, f);
 }
 
+
+// ------------------------------------------------------------------------ long-sequence backward (more than one key tile)
+constexpr float LOG2E_F = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_approx_f(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// delta[b, h, i] = sum_c dO[i, c] O[i, c], once per call (the one-CTA-per-key-tile kernel above recomputes it in every key tile)
+template <int D>
+__global__ void attn_delta_kernel(const bf16* __restrict__ o, int64_t ldo, const bf16* __restrict__ dout, int64_t ld_do,
+                                  float* __restrict__ delta, int NH, int Sq, int64_t n_rows) {
+  pdl_grid_sync();
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (b * Sq + i) * NH + h
+  if (idx >= n_rows * NH) return;
+  const int64_t row = idx / NH;
+  const int h = (int)(idx - row * NH);
+  const bf16* op = o + row * ldo + h * D;
+  const bf16* gp = dout + row * ld_do + h * D;
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < D; c += 8) {
+    float a[8], g[8];
+    load8(op + c, a);
+    load8(gp + c, g);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc = fmaf(a[u], g[u], acc);
+  }
+  const int64_t b = row / Sq, i = row - b * Sq;
+  delta[(b * NH + h) * Sq + i] = acc;
+}
+
+template <int D>
+struct BwdStreamSmem {
+  bf16 K[AT][D + 8];
+  bf16 V[AT][D + 8];
+  bf16 Q[2][AT][D + 8];
+  bf16 dO[2][AT][D + 8];
+  bf16 dS[AT][AT + 8];  // [key][query]
+  float fm[AT];
+  float kbias[AT];   // per key: additive bias * log2(e)            (key padding mask)
+  float kcut[AT];    // per key: 1 = masked for every query before it (repeat-inc / triangle), else 0
+  float lse[2][AT];
+  float delta[2][AT];
+};
+
+// Same mathematics and warp layout as attn_bwd_kernel (one CTA per (key tile, batch * head), warp w owns keys 16w .. 16w + 15,
+// the transposed score tile), but the query tiles STREAM: while tile i is being processed, cp.async is filling the other
+// buffer with Q / dO / lse / delta of tile i + 1; delta comes from attn_delta_kernel; dQ partials leave as 8-byte vector
+// reductions.  configs[4] (T = 512, d = 64): 1.2 ms -> see profiles/r01c_summary.md.
+template <int D>
+__global__ void __launch_bounds__(AT_THREADS) attn_bwd_stream_kernel(
+    const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ k, int64_t ldk, const bf16* __restrict__ v,
+    int64_t ldv, const bf16* __restrict__ dout, int64_t ld_do, const float* __restrict__ lse,
+    const float* __restrict__ delta, bf16* __restrict__ dk, int64_t ld_dk, bf16* __restrict__ dv, int64_t ld_dv,
+    float* __restrict__ dq_acc, int NH, int Sq, int Sk, float scale, MaskDev mask) {
+  pdl_grid_sync();
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  BwdStreamSmem<D>& s = *reinterpret_cast<BwdStreamSmem<D>*>(smem_raw);
+  constexpr int KS = D / 16, NT = D / 8, VPR = D / 8;
+  const int b = blockIdx.y / NH, h = blockIdx.y % NH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int k0 = blockIdx.x * AT;
+  const bf16* qb = q + (int64_t)b * Sq * ldq + h * D;
+  const bf16* kb = k + (int64_t)b * Sk * ldk + h * D;
+  const bf16* vb = v + (int64_t)b * Sk * ldv + h * D;
+  const bf16* dob = dout + (int64_t)b * Sq * ld_do + h * D;
+  const float* lse_g = lse + ((int64_t)b * NH + h) * Sq;
+  const float* delta_g = delta + ((int64_t)b * NH + h) * Sq;
+
+  auto prefetch = [&](int q0, int buf) {   // Q / dO rows [q0, q0 + 64) and their lse / delta -> buffer buf (zero beyond Sq)
+    for (int idx = threadIdx.x; idx < AT * VPR; idx += AT_THREADS) {
+      const int r = idx / VPR, c = (idx % VPR) * 8;
+      const bool ok = q0 + r < Sq;
+      const int64_t row = ok ? q0 + r : 0;
+      cp_async16(&s.Q[buf][r][c], qb + row * ldq + c, ok);
+      cp_async16(&s.dO[buf][r][c], dob + row * ld_do + c, ok);
+    }
+    if (threadIdx.x < AT) {
+      const bool ok = q0 + (int)threadIdx.x < Sq;
+      cp_async4(&s.lse[buf][threadIdx.x], lse_g + (ok ? q0 + threadIdx.x : 0), ok);
+    } else {
+      const int r = threadIdx.x - AT;
+      const bool ok = q0 + r < Sq;
+      cp_async4(&s.delta[buf][r], delta_g + (ok ? q0 + r : 0), ok);
+    }
+    cp_async_commit();
+  };
+  prefetch(0, 0);
+  load_tile<D>(s.K, kb, ldk, k0, Sk);
+  load_tile<D>(s.V, vb, ldv, k0, Sk);
+  if (threadIdx.x < AT) {
+    const int j = k0 + threadIdx.x;
+    const float fmj = (mask.frame_mask != nullptr && j < Sk) ? mask.frame_mask[(int64_t)b * mask.frame_mask_stride + j] : 0.f;
+    s.fm[threadIdx.x] = fmj;
+    s.kbias[threadIdx.x] = (mask.flags & KIT_MASK_KEYPAD_ADD) ? fmj * LOG2E_F : 0.f;
+    s.kcut[threadIdx.x] = (((mask.flags & KIT_MASK_REPEAT_INC) && fmj == 1.f) || (mask.flags & KIT_MASK_TRIANGLE)) ? 1.f : 0.f;
+  }
+  __syncthreads();
+  uint32_t ak[KS][4], av[KS][4];
+  const int kr = warp * 16 + g;
+#pragma unroll
+  for (int kk = 0; kk < KS; ++kk) {
+    const int c = kk * 16 + 2 * t;
+    ak[kk][0] = lds_pair<D>(s.K, kr, c);     ak[kk][1] = lds_pair<D>(s.K, kr + 8, c);
+    ak[kk][2] = lds_pair<D>(s.K, kr, c + 8); ak[kk][3] = lds_pair<D>(s.K, kr + 8, c + 8);
+    av[kk][0] = lds_pair<D>(s.V, kr, c);     av[kk][1] = lds_pair<D>(s.V, kr + 8, c);
+    av[kk][2] = lds_pair<D>(s.V, kr, c + 8); av[kk][3] = lds_pair<D>(s.V, kr + 8, c + 8);
+  }
+  float dk_acc[NT][4], dv_acc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    dk_acc[j][0] = dk_acc[j][1] = dk_acc[j][2] = dk_acc[j][3] = 0.f;
+    dv_acc[j][0] = dv_acc[j][1] = dv_acc[j][2] = dv_acc[j][3] = 0.f;
+  }
+  // this thread's two keys (rows g and g + 8 of the warp's 16): folded mask terms, base-2 softmax scale
+  const bool folded = mask.bias == nullptr;
+  const float scale2 = scale * LOG2E_F;
+  float kb2[2], kc2[2];
+  int kjj[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int kl = warp * 16 + g + 8 * r;
+    kb2[r] = s.kbias[kl];
+    kc2[r] = s.kcut[kl];
+    kjj[r] = k0 + kl;
+  }
+  const int nq = (Sq + AT - 1) / AT;
+  for (int it = 0; it < nq; ++it) {
+    const int q0 = it * AT, buf = it & 1;
+    if (it + 1 < nq) {
+      prefetch(q0 + AT, buf ^ 1);   // its previous readers finished before the barrier that ended iteration it - 1
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();   // tile `it` has landed for every thread
+    const bf16 (*sQ)[D + 8] = s.Q[buf];
+    const bf16 (*sdO)[D + 8] = s.dO[buf];
+    float st[8][4], dp[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f;
+      dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = kk * 16 + 2 * t;
+        mma16816(st[j], ak[kk], lds_pair<D>(sQ, j * 8 + g, c), lds_pair<D>(sQ, j * 8 + g, c + 8));
+        mma16816(dp[j], av[kk], lds_pair<D>(sdO, j * 8 + g, c), lds_pair<D>(sdO, j * 8 + g, c + 8));
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kl = warp * 16 + g + 8 * (e >> 1), kj = k0 + kl;   // key
+        const int ql = j * 8 + 2 * t + (e & 1), qi = q0 + ql;        // query
+        float p = 0.f;
+        if (kj < Sk && qi < Sq) {
+          if (folded) {   // exp(x - lse) = 2^(s * scale * log2e + bias * log2e - lse * log2e); a cut key is masked for earlier queries
+            const int r = e >> 1;
+            const bool cut = kc2[r] != 0.f && kjj[r] > qi;
+            p = cut ? 0.f : ex2_approx_f(fmaf(st[j][e], scale2, kb2[r]) - s.lse[buf][ql] * LOG2E_F);
+          } else {
+            const float x = st[j][e] * scale + mask_bias(mask, b, h, qi, kj, Sk, s.fm[kl]);
+            p = __expf(x - s.lse[buf][ql]);
+          }
+        }
+        st[j][e] = p;
+        dp[j][e] = p * (dp[j][e] - s.delta[buf][ql]) * scale;
+      }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t ap[4], ad[4];
+      ap[0] = pack_bf16(st[2 * kk][0], st[2 * kk][1]);         ap[1] = pack_bf16(st[2 * kk][2], st[2 * kk][3]);
+      ap[2] = pack_bf16(st[2 * kk + 1][0], st[2 * kk + 1][1]); ap[3] = pack_bf16(st[2 * kk + 1][2], st[2 * kk + 1][3]);
+      ad[0] = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]);         ad[1] = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
+      ad[2] = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]); ad[3] = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, &sdO[kk * 16 + (lane & 15)][j * 8]);
+        mma16816(dv_acc[j], ap, b0, b1);
+        ldsm_x2_trans(b0, b1, &sQ[kk * 16 + (lane & 15)][j * 8]);
+        mma16816(dk_acc[j], ad, b0, b1);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      *reinterpret_cast<uint32_t*>(&s.dS[warp * 16 + g][j * 8 + 2 * t]) = pack_bf16(dp[j][0], dp[j][1]);
+      *reinterpret_cast<uint32_t*>(&s.dS[warp * 16 + g + 8][j * 8 + 2 * t]) = pack_bf16(dp[j][2], dp[j][3]);
+    }
+    __syncthreads();
+    float dq_r[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) dq_r[j][0] = dq_r[j][1] = dq_r[j][2] = dq_r[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t a[4];
+      ldsm_x4_trans(a, &s.dS[kk * 16 + (lane & 7) + ((lane >> 4) << 3)][warp * 16 + (((lane >> 3) & 1) << 3)]);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, &s.K[kk * 16 + (lane & 15)][j * 8]);
+        mma16816(dq_r[j], a, b0, b1);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int qi = q0 + warp * 16 + g + 8 * r;
+      if (qi >= Sq) continue;
+      float* ap = dq_acc + ((int64_t)b * Sq + qi) * (int64_t)(NH * D) + h * D;
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(ap + j * 8 + 2 * t), "f"(dq_r[j][2 * r]), "f"(dq_r[j][2 * r + 1]) : "memory");
+    }
+    __syncthreads();   // every warp is done with this tile's Q / dO / dS before they are overwritten
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int kj = k0 + warp * 16 + g + 8 * r;
+    if (kj >= Sk) continue;
+    bf16* dkp = dk + ((int64_t)b * Sk + kj) * ld_dk + h * D;
+    bf16* dvp = dv + ((int64_t)b * Sk + kj) * ld_dv + h * D;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      *reinterpret_cast<uint32_t*>(dkp + j * 8 + 2 * t) = pack_bf16(dk_acc[j][2 * r], dk_acc[j][2 * r + 1]);
+      *reinterpret_cast<uint32_t*>(dvp + j * 8 + 2 * t) = pack_bf16(dv_acc[j][2 * r], dv_acc[j][2 * r + 1]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------ single-tile kernels (Sq, Sk <= 64)
 // The benchmark shape (T = 64, d = 32) is one 64 x 64 score tile per (batch, head): 4 KB per operand, far too little work
 // to hide a load -> compute -> store chain per CTA.  These kernels are PERSISTENT over the (batch, head) units: while a CTA
@@ -967,6 +1201,24 @@ static int bwd_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, co
   if (ktiles > 1) {
     KIT_REQUIRE(dq_acc != nullptr, "attention backward with more than 64 keys needs the fp32 dq accumulator workspace");
     KIT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)B * Sq * NH * D * sizeof(float), st));
+    if (md.bias == nullptr || true) {   // streaming kernel: delta once per call, query tiles prefetched with cp.async
+      static bool stream_attr_done = false;
+      if (!stream_attr_done) {
+        KIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_stream_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdStreamSmem<D>)));
+        stream_attr_done = true;
+      }
+      float* delta = dq_acc + (int64_t)B * Sq * NH * D;   // workspace tail: [B, NH, Sq]
+      const int64_t n_rows = (int64_t)B * Sq;
+      launch_kernel(attn_delta_kernel<D>, dim3((unsigned)ceil_div(n_rows * NH, 256)), dim3(256), 0, st, o, ldo, dout, ld_do, delta, NH, Sq, n_rows);
+      KIT_LAUNCH_CHECK();
+      launch_kernel(attn_bwd_stream_kernel<D>, dim3(ktiles, B * NH), dim3(AT_THREADS), sizeof(BwdStreamSmem<D>), st, q, ldq, k, ldk, v, ldv,
+                    dout, ld_do, lse, (const float*)delta, dk, ld_dk, dv, ld_dv, dq_acc, NH, Sq, Sk, rsqrtf((float)D), md);
+      KIT_LAUNCH_CHECK();
+      const int64_t n = (int64_t)B * Sq * NH * D;
+      launch_kernel(dq_convert_kernel, dim3((unsigned)ceil_div(n / 8, 256)), dim3(256), 0, st, dq_acc, dq, ld_dq, (int64_t)B * Sq, NH * D);
+      KIT_LAUNCH_CHECK();
+      return KIT_OK;
+    }
   }
   dim3 grid(ktiles, B * NH);
   launch_kernel(attn_bwd_kernel<D>, dim3(grid), dim3(AT_THREADS), sizeof(BwdSmem<D>), st, q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq,

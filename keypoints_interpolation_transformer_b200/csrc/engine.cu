@@ -316,7 +316,7 @@ static void plan_workspace(KitEngine* e) {
   e->alloc("gqkv", gm * 3 * H, 2, 3 * H);
   e->alloc("gkv", gm * 2 * H, 2, 2 * H);
   e->alloc("g2h", gm * 2 * H, 2, 2 * H);
-  e->alloc("dq_acc", (e->training && e->T > 64) ? M * H : 8, 4, H);
+  e->alloc("dq_acc", (e->training && e->T > 64) ? M * H + M * NH : 8, 4, H);
 }
 
 static void resolve_pointers(KitEngine* e) {

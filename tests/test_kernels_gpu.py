@@ -173,7 +173,7 @@ def test_attention_fwd_bwd(B, NH, S, d, flags, explicit):
     K.check(lib.kit_attention_fwd(K.ptr(q), 3 * H, K.ptr(k), 3 * H, K.ptr(v), 3 * H, K.ptr(out), H, K.ptr(lse), B, NH, S,
                                   S, d, C.byref(mask), _sp()))
     dq = torch.empty(B * S, 3 * H, dtype=torch.bfloat16, device=DEV)
-    dq_acc = torch.empty(B * S, H, device=DEV) if S > 64 else None
+    dq_acc = torch.empty(B * S * H + B * NH * S, device=DEV) if S > 64 else None      # dQ partial sums + rowsum(dO * O)
     K.check(lib.kit_attention_bwd(K.ptr(q), 3 * H, K.ptr(k), 3 * H, K.ptr(v), 3 * H, K.ptr(out), H, K.ptr(dout), H,
                                   K.ptr(lse), K.ptr(dq[:, :H]), 3 * H, K.ptr(dq[:, H:2 * H]), 3 * H, K.ptr(dq[:, 2 * H:]),
                                   3 * H, K.ptr(dq_acc), B, NH, S, S, d, C.byref(mask), _sp()))
