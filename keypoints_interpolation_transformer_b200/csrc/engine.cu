@@ -288,12 +288,14 @@ static void plan_workspace(KitEngine* e) {
   e->alloc("st_encn", 2 * M, 4, 0);
   e->alloc("st_decn", 2 * M, 4, 0);
   const int n_saved = e->training ? L.cfg.layers : 1;
+  // the [M, FF] hidden activation of the feed-forward block exists in HBM only for the backward pass (or the two-GEMM path)
+  const int64_t zh_elems = (!e->training && e->fuse_ffn && ffn_fwd_supported(H, FF)) ? 8 : M * FF;
   for (int l = 0; l < n_saved; ++l) {
     const std::string p = "enc" + std::to_string(l) + ".";
     e->alloc(p + "qkv", M * 3 * H, 2, 3 * H);
     for (const char* n : {"ao", "s1", "x1", "s2", "x2"}) e->alloc(p + n, M * H, 2, H);
-    e->alloc(p + "z", M * FF, 2, FF);
-    e->alloc(p + "hh", M * FF, 2, FF);
+    e->alloc(p + "z", zh_elems, 2, FF);
+    e->alloc(p + "hh", zh_elems, 2, FF);
     e->alloc(p + "lse", lse_n, 4, 0);
     e->alloc(p + "st1", 2 * M, 4, 0);
     e->alloc(p + "st2", 2 * M, 4, 0);
@@ -303,8 +305,8 @@ static void plan_workspace(KitEngine* e) {
     e->alloc(p + "qkv", M * 3 * H, 2, 3 * H);
     e->alloc(p + "kvc", M * 2 * H, 2, 2 * H);
     for (const char* n : {"ao", "s1", "y1", "qc", "aoc", "s2", "y2", "s3", "y3"}) e->alloc(p + n, M * H, 2, H);
-    e->alloc(p + "z", M * FF, 2, FF);
-    e->alloc(p + "hh", M * FF, 2, FF);
+    e->alloc(p + "z", zh_elems, 2, FF);
+    e->alloc(p + "hh", zh_elems, 2, FF);
     e->alloc(p + "lse", lse_n, 4, 0);
     e->alloc(p + "lsec", lse_n, 4, 0);
     for (const char* n : {"st1", "st2", "st3"}) e->alloc(p + n, 2 * M, 4, 0);
@@ -899,6 +901,12 @@ extern "C" int kit_engine_create(const KitModelConfig* cfg, int32_t batch, int32
   e->training = training ? 1 : 0;
   e->M = (int64_t)batch * seq_len;
   e->K2p = (int)up8(cfg->input_size);
+  {
+    const char* v = getenv("KIT_FUSE_FFN");   // KIT_FUSE_FFN=0: the two-GEMM path (A/B measurements)
+    e->fuse_ffn = !(v != nullptr && v[0] == '0');
+    v = getenv("KIT_FUSE_LNBWD");
+    e->fuse_lnbwd = v != nullptr && v[0] == '1';
+  }
   plan_workspace(e);
   *out = e;
   return KIT_OK;
@@ -923,12 +931,7 @@ extern "C" int kit_engine_bind(KitEngine* e, float* params, float* grads, void* 
   e->group_plans.clear();
   e->ffn_plans.clear();
   e->ffn_bwd_plans.clear();
-  {
-    const char* v = getenv("KIT_FUSE_FFN");   // KIT_FUSE_FFN=0: the two-GEMM path (A/B measurements)
-    e->fuse_ffn = !(v != nullptr && v[0] == '0');
-    v = getenv("KIT_FUSE_LNBWD");
-    e->fuse_lnbwd = v != nullptr && v[0] == '1';
-  }
+
   // upload the weight-refresh tables (synchronous, bind time only)
   std::vector<int> prefix(e->L.wdescs.size() + 1, 0);
   for (size_t i = 0; i < e->L.wdescs.size(); ++i) {
