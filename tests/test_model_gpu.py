@@ -318,3 +318,25 @@ def test_fused_layernorm_backward_path_matches_default(monkeypatch):
         assert abs(l - l0) <= 2e-3 * abs(l0), name
         assert _rel(g, g0) < 1e-2, name                      # same math, bf16 rounding points differ slightly
     assert results["lnbwd"][2] < n0 < results["no_ffn"][2]   # fewer launches with every fusion
+
+
+def test_multi_stream_step_matches_single_stream():
+    """train.TrainStep(streams=2): two half-batches through their own engines on their own streams, one gradient arena --
+    same loss, gradients and parameter update as the single-stream step (also under CUDA-graph replay)."""
+    Kp, H, L, NH, B, T = 54, 64, 2, 4, 8, 16
+    inputs, gt, mask = (t.to(DEV) for t in ko.synthetic_batch(B, T, Kp, seed=41))
+    out = {}
+    for streams, use_graph in ((1, False), (2, False), (2, True)):
+        m = _build(2 * Kp, H, L, NH)
+        m.train()
+        opt = optim.FlatAdam(m, lr=1e-3, capturable=use_graph)
+        step = train.TrainStep(m, opt, criterion="mse", streams=streams, use_graph=use_graph)
+        losses = [step(inputs, gt, mask).item() for _ in range(5)]
+        torch.cuda.synchronize()
+        out[(streams, use_graph)] = (losses, m.flat_params[:m.layout.trainable].clone())
+    l0, p0 = out[(1, False)]
+    for key, (l, p) in out.items():
+        assert np.allclose(l, l0, rtol=2e-3, atol=1e-6), (key, l, l0)
+        assert _rel(p, p0) < 1e-4, key
+    with pytest.raises(K.KitError):
+        train.TrainStep(_build(2 * Kp, H, L, NH).train(), criterion="mse", streams=3)(inputs, gt, mask)      # 8 % 3 != 0
