@@ -1198,37 +1198,31 @@ static int bwd_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, co
     attr_done = true;
   }
   const int ktiles = (Sk + AT - 1) / AT;
-  if (ktiles > 1) {
+  if (ktiles > 1) {   // long sequences: the streaming kernel (delta once per call, query tiles prefetched with cp.async)
     KIT_REQUIRE(dq_acc != nullptr, "attention backward with more than 64 keys needs the fp32 dq accumulator workspace");
     KIT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)B * Sq * NH * D * sizeof(float), st));
-    if (md.bias == nullptr || true) {   // streaming kernel: delta once per call, query tiles prefetched with cp.async
-      static bool stream_attr_done = false;
-      if (!stream_attr_done) {
-        KIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_stream_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdStreamSmem<D>)));
-        stream_attr_done = true;
-      }
-      float* delta = dq_acc + (int64_t)B * Sq * NH * D;   // workspace tail: [B, NH, Sq]
-      const int64_t n_rows = (int64_t)B * Sq;
-      launch_kernel(attn_delta_kernel<D>, dim3((unsigned)ceil_div(n_rows * NH, 256)), dim3(256), 0, st, o, ldo, dout, ld_do, delta, NH, Sq, n_rows);
-      KIT_LAUNCH_CHECK();
-      launch_kernel(attn_bwd_stream_kernel<D>, dim3(ktiles, B * NH), dim3(AT_THREADS), sizeof(BwdStreamSmem<D>), st, q, ldq, k, ldk, v, ldv,
-                    dout, ld_do, lse, (const float*)delta, dk, ld_dk, dv, ld_dv, dq_acc, NH, Sq, Sk, rsqrtf((float)D), md);
-      KIT_LAUNCH_CHECK();
-      const int64_t n = (int64_t)B * Sq * NH * D;
-      launch_kernel(dq_convert_kernel, dim3((unsigned)ceil_div(n / 8, 256)), dim3(256), 0, st, dq_acc, dq, ld_dq, (int64_t)B * Sq, NH * D);
-      KIT_LAUNCH_CHECK();
-      return KIT_OK;
+    static bool stream_attr_done = false;
+    if (!stream_attr_done) {
+      KIT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_stream_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdStreamSmem<D>)));
+      stream_attr_done = true;
     }
+    float* delta = dq_acc + (int64_t)B * Sq * NH * D;   // workspace tail: [B, NH, Sq]
+    const int64_t n_rows = (int64_t)B * Sq;
+    launch_kernel(attn_delta_kernel<D>, dim3((unsigned)ceil_div(n_rows * NH, 256)), dim3(256), 0, st, o, ldo, dout, ld_do, delta, NH, Sq, n_rows);
+    KIT_LAUNCH_CHECK();
+    launch_kernel(attn_bwd_stream_kernel<D>, dim3(ktiles, B * NH), dim3(AT_THREADS), sizeof(BwdStreamSmem<D>), st, q, ldq, k, ldk, v, ldv,
+                  dout, ld_do, lse, (const float*)delta, dk, ld_dk, dv, ld_dv, dq_acc, NH, Sq, Sk, rsqrtf((float)D), md);
+    KIT_LAUNCH_CHECK();
+    const int64_t n = (int64_t)B * Sq * NH * D;
+    launch_kernel(dq_convert_kernel, dim3((unsigned)ceil_div(n / 8, 256)), dim3(256), 0, st, dq_acc, dq, ld_dq, (int64_t)B * Sq, NH * D);
+    KIT_LAUNCH_CHECK();
+    return KIT_OK;
   }
+  // one key tile with an explicit additive mask: the plain kernel (dQ written directly)
   dim3 grid(ktiles, B * NH);
   launch_kernel(attn_bwd_kernel<D>, dim3(grid), dim3(AT_THREADS), sizeof(BwdSmem<D>), st, q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq,
                                                                     dk, ld_dk, dv, ld_dv, dq_acc, NH, Sq, Sk, rsqrtf((float)D), md);
   KIT_LAUNCH_CHECK();
-  if (ktiles > 1) {
-    const int64_t n = (int64_t)B * Sq * NH * D;
-    launch_kernel(dq_convert_kernel, dim3((unsigned)ceil_div(n / 8, 256)), dim3(256), 0, st, dq_acc, dq, ld_dq, (int64_t)B * Sq, NH * D);
-    KIT_LAUNCH_CHECK();
-  }
   return KIT_OK;
 }
 

@@ -225,7 +225,7 @@ struct KitEngine {
   size_t ffn_cursor = 0, ffn_bwd_cursor = 0;
   bool fuse_ffn = true;
   // LayerNorm backward in the epilogue of the kernel that produces its output gradient (EPI_ADD_LNBWD, ffn_kernel<true>).  Opt-in
-  // (KIT_FUSE_LNBWD=1): it removes 28 of the 37 ln_bwd launches of a step, but with one accumulator row per lane the dgamma / dbeta
+  // (KIT_FUSE_LNBWD=1): it removes 28 of the 32 ln_bwd launches of a step, but with one accumulator row per lane the dgamma / dbeta
   // column sums need a warp transpose-reduce that costs more than the launches it saves (4.45 vs 4.34 ms per step at B = 256; 4.20
   // without the column sums) -- see profiles/r01c_summary.md.
   bool fuse_lnbwd = false;
@@ -424,7 +424,7 @@ static int eattn_bwd(KitEngine* e, const bf16* q, int64_t ldq, const bf16* k, in
                      const bf16* o, int64_t ldo, const bf16* dout, int64_t ld_do, const float* lse, bf16* dq, int64_t ld_dq,
                      bf16* dk, int64_t ld_dk, bf16* dv, int64_t ld_dv, const KitAttnMask* mask) {
   const int H = e->L.cfg.hidden, NH = e->L.cfg.heads, d = H / NH;
-  e->launches += 2;
+  e->launches += e->T > 64 ? 3 : 1;   // one persistent tile kernel, or rowsum(dO * O) + streaming kernel + fp32 -> bf16 dQ
   prof_begin(e, KIT_PROF_ATTN_BWD, 10.0 * e->B * NH * (double)e->T * e->T * d);
   const int rc = attention_bwd(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq, dk, ld_dk, dv, ld_dv,
                                e->T > 64 ? e->dq_acc : nullptr, e->B, NH, e->T, e->T, d, mask, e->st);
