@@ -1237,6 +1237,8 @@ int attention_fwd(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const 
                   cudaStream_t st) {
   int rc = check_attn(d, ldq, ldk, ldv, ldo);
   if (rc) return rc;
+  if (attention_fwd_tc_supported(ldq, ldk, ldv, NH, Sq, Sk, d, mask, q, k, v))
+    return attention_fwd_tc(q, ldq, k, ldk, v, ldv, out, ldo, lse, B, NH, Sq, Sk, d, mask, st);
   const MaskDev md = to_dev(mask);
   switch (d) {
     case 16: return fwd_launch<16>(q, ldq, k, ldk, v, ldv, out, ldo, lse, B, NH, Sq, Sk, md, st);
