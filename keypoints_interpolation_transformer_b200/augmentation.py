@@ -7,7 +7,6 @@ import math
 import random
 
 import numpy as np
-import torch
 
 from . import preprocess as PP
 

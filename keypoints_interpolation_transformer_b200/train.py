@@ -14,7 +14,7 @@ import torch
 
 from . import _lib as K
 from .engine import make_mask
-from .euclidean_loss import EuclideanLoss, MSELoss, fused_loss
+from .euclidean_loss import EuclideanLoss, fused_loss
 from .optim import FlatAdam
 
 

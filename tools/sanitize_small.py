@@ -1,6 +1,5 @@
 """Small invocations of the kernels added late in round 1, for `compute-sanitizer --tool memcheck python tools/sanitize_small.py`
 (one tool per gpurun call, B200_PROFILING.md)."""
-import ctypes as C
 import math
 import os
 import sys
