@@ -240,18 +240,23 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains (no fp reassociation by nvcc)
       const uint32_t kb_s = smem_u32(kb), kc_s = smem_u32(kc);
       const float qif = (float)qi;
+      const uint64_t sc2 = pk2(p.scale2, p.scale2);
       if (need_cut) {
 #pragma unroll
         for (int c4 = 0; c4 < 32; ++c4) {
           const uint4 kbw = lds128(kb_s + 16 * c4), kcw = lds128(kc_s + 16 * c4);
           const uint32_t kbv[4] = {kbw.x, kbw.y, kbw.z, kbw.w}, kcv[4] = {kcw.x, kcw.y, kcw.z, kcw.w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 4; u += 2) {   // packed fp32 pairs for the scale + bias
             const int c = 4 * c4 + u;
-            float v = fmaf(x[c], p.scale2, __uint_as_float(kbv[u]));
-            v = (__uint_as_float(kcv[u]) > qif) ? -INFINITY : v;
-            x[c] = v;
-            mx4[u] = fmaxf(mx4[u], v);
+            float v0, v1;
+            up2(fma2(pk2(x[c], x[c + 1]), sc2, pk2(__uint_as_float(kbv[u]), __uint_as_float(kbv[u + 1]))), v0, v1);
+            v0 = (__uint_as_float(kcv[u]) > qif) ? -INFINITY : v0;
+            v1 = (__uint_as_float(kcv[u + 1]) > qif) ? -INFINITY : v1;
+            x[c] = v0;
+            x[c + 1] = v1;
+            mx4[u] = fmaxf(mx4[u], v0);
+            mx4[u + 1] = fmaxf(mx4[u + 1], v1);
           }
         }
       } else {
@@ -260,11 +265,14 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
           const uint4 kbw = lds128(kb_s + 16 * c4);
           const uint32_t kbv[4] = {kbw.x, kbw.y, kbw.z, kbw.w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 4; u += 2) {
             const int c = 4 * c4 + u;
-            const float v = fmaf(x[c], p.scale2, __uint_as_float(kbv[u]));
-            x[c] = v;
-            mx4[u] = fmaxf(mx4[u], v);
+            float v0, v1;
+            up2(fma2(pk2(x[c], x[c + 1]), sc2, pk2(__uint_as_float(kbv[u]), __uint_as_float(kbv[u + 1]))), v0, v1);
+            x[c] = v0;
+            x[c + 1] = v1;
+            mx4[u] = fmaxf(mx4[u], v0);
+            mx4[u + 1] = fmaxf(mx4[u + 1], v1);
           }
         }
       }
@@ -272,15 +280,20 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
       const float m_new = fmaxf(m_run, mx);
       const float m_ref = (m_new == -INFINITY) ? 0.f : m_new;
       const float corr = ex2f(m_run - m_ref);
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint64_t rs2[4] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
+      const uint64_t nm2 = pk2(-m_ref, -m_ref);
       uint32_t* pk = reinterpret_cast<uint32_t*>(x);   // the packed probabilities overwrite the scores they came from
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
-        const float p0 = ex2f(x[2 * c] - m_ref), p1 = ex2f(x[2 * c + 1] - m_ref);
-        rs4[c & 3] += p0 + p1;
+        float a0, a1;
+        up2(add2(pk2(x[2 * c], x[2 * c + 1]), nm2), a0, a1);
+        const float p0 = ex2f(a0), p1 = ex2f(a1);
+        rs2[c & 3] = add2(rs2[c & 3], pk2(p0, p1));
         pk[c] = pack_bf16(p0, p1);
       }
-      const float rs = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+      float r0, r1, r2, r3, r4, r5, r6, r7;
+      up2(rs2[0], r0, r1); up2(rs2[1], r2, r3); up2(rs2[2], r4, r5); up2(rs2[3], r6, r7);
+      const float rs = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
       l_run = l_run * corr + rs;
       m_run = m_new;
       // the previous step of this slot has been accumulated (P buffer free); the previous tile of this head too (O stable)
