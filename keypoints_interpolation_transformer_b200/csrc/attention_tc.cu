@@ -230,52 +230,61 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
       mbar_wait(&s_full[sl], (n >> 1) & 1);
       tc_fence_after();
       float x[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(tmem_base + lane_base + uint32_t(sl * 128 + c * 32), reinterpret_cast<uint32_t*>(x) + c * 32);
+      uint32_t* xr = reinterpret_cast<uint32_t*>(x);
+      const uint32_t s_addr = tmem_base + lane_base + uint32_t(sl * 128);
+      tmem_ld32(s_addr, xr);
+      tmem_ld32(s_addr + 32, xr + 32);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[sl]);
+      tmem_ld32(s_addr + 64, xr + 64);    // the second half of the row travels while the first is scaled and masked
+      tmem_ld32(s_addr + 96, xr + 96);
       // scale + mask (base 2), row maximum
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains (no fp reassociation by nvcc)
       const uint32_t kb_s = smem_u32(kb), kc_s = smem_u32(kc);
       const float qif = (float)qi;
       const uint64_t sc2 = pk2(p.scale2, p.scale2);
-      if (need_cut) {
+      auto half = [&](int h0) {
+        if (need_cut) {
 #pragma unroll
-        for (int c4 = 0; c4 < 32; ++c4) {
-          const uint4 kbw = lds128(kb_s + 16 * c4), kcw = lds128(kc_s + 16 * c4);
-          const uint32_t kbv[4] = {kbw.x, kbw.y, kbw.z, kbw.w}, kcv[4] = {kcw.x, kcw.y, kcw.z, kcw.w};
+          for (int c4 = h0; c4 < h0 + 16; ++c4) {
+            const uint4 kbw = lds128(kb_s + 16 * c4), kcw = lds128(kc_s + 16 * c4);
+            const uint32_t kbv[4] = {kbw.x, kbw.y, kbw.z, kbw.w}, kcv[4] = {kcw.x, kcw.y, kcw.z, kcw.w};
 #pragma unroll
-          for (int u = 0; u < 4; u += 2) {   // packed fp32 pairs for the scale + bias
-            const int c = 4 * c4 + u;
-            float v0, v1;
-            up2(fma2(pk2(x[c], x[c + 1]), sc2, pk2(__uint_as_float(kbv[u]), __uint_as_float(kbv[u + 1]))), v0, v1);
-            v0 = (__uint_as_float(kcv[u]) > qif) ? -INFINITY : v0;
-            v1 = (__uint_as_float(kcv[u + 1]) > qif) ? -INFINITY : v1;
-            x[c] = v0;
-            x[c + 1] = v1;
-            mx4[u] = fmaxf(mx4[u], v0);
-            mx4[u + 1] = fmaxf(mx4[u + 1], v1);
+            for (int u = 0; u < 4; u += 2) {   // packed fp32 pairs for the scale + bias
+              const int c = 4 * c4 + u;
+              float v0, v1;
+              up2(fma2(pk2(x[c], x[c + 1]), sc2, pk2(__uint_as_float(kbv[u]), __uint_as_float(kbv[u + 1]))), v0, v1);
+              v0 = (__uint_as_float(kcv[u]) > qif) ? -INFINITY : v0;
+              v1 = (__uint_as_float(kcv[u + 1]) > qif) ? -INFINITY : v1;
+              x[c] = v0;
+              x[c + 1] = v1;
+              mx4[u] = fmaxf(mx4[u], v0);
+              mx4[u + 1] = fmaxf(mx4[u + 1], v1);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c4 = h0; c4 < h0 + 16; ++c4) {
+            const uint4 kbw = lds128(kb_s + 16 * c4);
+            const uint32_t kbv[4] = {kbw.x, kbw.y, kbw.z, kbw.w};
+#pragma unroll
+            for (int u = 0; u < 4; u += 2) {
+              const int c = 4 * c4 + u;
+              float v0, v1;
+              up2(fma2(pk2(x[c], x[c + 1]), sc2, pk2(__uint_as_float(kbv[u]), __uint_as_float(kbv[u + 1]))), v0, v1);
+              x[c] = v0;
+              x[c + 1] = v1;
+              mx4[u] = fmaxf(mx4[u], v0);
+              mx4[u + 1] = fmaxf(mx4[u + 1], v1);
+            }
           }
         }
-      } else {
-#pragma unroll
-        for (int c4 = 0; c4 < 32; ++c4) {
-          const uint4 kbw = lds128(kb_s + 16 * c4);
-          const uint32_t kbv[4] = {kbw.x, kbw.y, kbw.z, kbw.w};
-#pragma unroll
-          for (int u = 0; u < 4; u += 2) {
-            const int c = 4 * c4 + u;
-            float v0, v1;
-            up2(fma2(pk2(x[c], x[c + 1]), sc2, pk2(__uint_as_float(kbv[u]), __uint_as_float(kbv[u + 1]))), v0, v1);
-            x[c] = v0;
-            x[c + 1] = v1;
-            mx4[u] = fmaxf(mx4[u], v0);
-            mx4[u + 1] = fmaxf(mx4[u + 1], v1);
-          }
-        }
-      }
+      };
+      half(0);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[sl]);
+      half(16);
       const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m_run, mx);
       const float m_ref = (m_new == -INFINITY) ? 0.f : m_new;
@@ -354,12 +363,8 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
 
 bool attention_fwd_tc_supported(int64_t ldq, int64_t ldk, int64_t ldv, int NH, int Sq, int Sk, int d, const KitAttnMask* mask,
                                 const void* q, const void* k, const void* v) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("KIT_ATTN_TC");
-    enabled = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  if (!enabled) return false;
+  const char* e = getenv("KIT_ATTN_TC");   // KIT_ATTN_TC=0: the mma.sync streaming kernel (A/B measurements, tests)
+  if (e != nullptr && e[0] == '0') return false;
   if (d != 32 && d != 64) return false;
   if (NH % (64 / d) != 0) return false;
   (void)Sq;
