@@ -146,12 +146,8 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, false, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);   // B = V tile [keys][64 columns]: MN-major
-      int iu = 0, jt0 = 0, n = 0;   // jt0: key tiles before this unit
-      // step bookkeeping of the PV that trails the QK by one step
-      int pv_j = 0, pv_jt = 0;       // key tile (within its unit / global) of the pending PV step
       auto issue_pv = [&](int m, int j, int jt, int g) {   // O_g += P[m & 1] V_j   (m = global step)
         const int sl = m & 1;
-        mbar_wait(&p_full[sl], (m >> 1) & 1);
         tc_fence_after();
         const uint32_t p_base = smem_u32(s.p[sl]), v_base = smem_u32(s.v[jt & 1]);
 #pragma unroll
@@ -163,34 +159,46 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
         umma_commit(&pv_done[sl]);
         if (g == G - 1) umma_commit(&kv_empty[jt & 1]);   // every MMA that reads this K / V stage has been issued
       };
-      bool pending = false;
-      int pend_m = 0, pend_g = 0;
-      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
-        mbar_wait(&q_full[iu & 1], (iu >> 1) & 1);
-        const uint32_t q_buf = smem_u32(s.q[iu & 1][0]);
-        for (int ns = 0; ns < NS; ++ns, ++n) {
-          const int j = ns / G, g = ns % G, sl = n & 1, jt = jt0 + j;
-          if (g == 0) mbar_wait(&kv_full[jt & 1], (jt >> 1) & 1);
-          mbar_wait(&s_free[sl], ((n >> 1) & 1) ^ 1);   // the softmax group has read the score tile two steps back
-          tc_fence_after();
-          const uint32_t k_base = smem_u32(s.k[jt & 1]);
+      // Two in-order queues, issued as their inputs become ready: Q K^T of step n needs its score slot drained (s_free, early in
+      // step n - 2 of the same group) and the K / V stage; P V of step m needs P (p_full, the end of softmax step m).  Issuing
+      // strictly QK(n), PV(n - 1), QK(n + 1), ... made every group wait ~1.3 k cycles for a score tile that could have been ready.
+      const int n_units = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int total = n_units * NS;
+      int qk = 0, pv = 0;
+      while (pv < total) {
+        bool progressed = false;
+        if (qk < total && qk < pv + 2) {
+          const int iuq = qk / NS, ns = qk % NS, j = ns / G, g = ns % G, sl = qk & 1, jt = iuq * p.n_ktiles + j;
+          bool ready = mbar_try_wait(&s_free[sl], ((qk >> 1) & 1) ^ 1);
+          if (ready && ns == 0) ready = mbar_try_wait(&q_full[iuq & 1], (iuq >> 1) & 1);
+          if (ready && g == 0) ready = mbar_try_wait(&kv_full[jt & 1], (jt >> 1) & 1);
+          if (ready) {
+            tc_fence_after();
+            const uint32_t q_buf = smem_u32(s.q[iuq & 1][0]), k_base = smem_u32(s.k[jt & 1]);
 #pragma unroll
-          for (int kk = 0; kk < KS; ++kk) {
-            // d = 32: group = head half of the shared tiles; d = 64: group = query tile, the whole K tile
-            const uint32_t a_off = (D == 64) ? g * ATC_TILE : g * D * 2, b_off = (D == 64) ? 0 : g * D * 2;
-            const uint64_t adesc = make_smem_desc_sw128(q_buf + a_off + kk * 32, 0, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(k_base + b_off + kk * 32, 0, 1024);
-            umma_bf16(tmem_base + sl * 128, adesc, bdesc, idesc_qk, kk > 0 ? 1u : 0u);
+            for (int kk = 0; kk < KS; ++kk) {
+              // d = 32: group = head half of the shared tiles; d = 64: group = query tile, the whole K tile
+              const uint32_t a_off = (D == 64) ? g * ATC_TILE : g * D * 2, b_off = (D == 64) ? 0 : g * D * 2;
+              const uint64_t adesc = make_smem_desc_sw128(q_buf + a_off + kk * 32, 0, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(k_base + b_off + kk * 32, 0, 1024);
+              umma_bf16(tmem_base + sl * 128, adesc, bdesc, idesc_qk, kk > 0 ? 1u : 0u);
+            }
+            umma_commit(&s_full[sl]);
+            if (ns == NS - 1) umma_commit(&q_empty[iuq & 1]);   // the producer may refill this Q buffer
+            ++qk;
+            progressed = true;
           }
-          umma_commit(&s_full[sl]);
-          if (ns == NS - 1) umma_commit(&q_empty[iu & 1]);   // the producer may refill this Q buffer
-          if (pending) issue_pv(pend_m, pv_j, pv_jt, pend_g);
-          pending = true;
-          pend_m = n; pend_g = g; pv_j = j; pv_jt = jt;
         }
-        jt0 += p.n_ktiles;
+        if (pv < qk) {
+          const int iup = pv / NS, ns = pv % NS, j = ns / G, g = ns % G, jt = iup * p.n_ktiles + j;
+          if (mbar_try_wait(&p_full[pv & 1], (pv >> 1) & 1)) {
+            issue_pv(pv, j, jt, g);
+            ++pv;
+            progressed = true;
+          }
+        }
+        (void)progressed;
       }
-      if (pending) issue_pv(pend_m, pv_j, pv_jt, pend_g);
     }
     __syncwarp();
   } else {
@@ -208,24 +216,36 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
     const int qi = q0 + (D == 64 ? grp * ATC_Q : 0) + row;
     const int o_col = 256 + grp * 64 + (D == 64 ? 0 : grp * D);   // this group's D accumulator columns
     float m_run = -INFINITY, l_run = 0.f;
+    float fm_next[4];
+    auto load_fm = [&](int jn) {
+#pragma unroll
+      for (int uu = 0; uu < 4; ++uu) {
+        const int kj = jn * ATC_K + lane * 4 + uu;
+        fm_next[uu] = (p.frame_mask != nullptr && kj < p.Sk) ? __ldg(p.frame_mask + (int64_t)b * p.frame_mask_stride + kj) : 0.f;
+      }
+    };
+    load_fm(0);
     for (int j = 0; j < p.n_ktiles; ++j) {
       const int n = n0 + j * G + grp, sl = n & 1;
       // folded mask terms of the 128 keys of this tile, warp-private (4 keys per lane)
       __syncwarp();
       // kb: additive term in base 2 (-inf for keys beyond the sequence); kc: the key's own index when it is cut for every earlier
       // query (repeat-inc / triangle), else -1 -- a score is masked iff kc > query index
+      // A tile entirely behind this warp's last query has its cut keys masked for every row: folded into kb (-inf), no compare;
+      // a tile entirely at or before the warp's first query cuts nothing.  Only tiles that cross the diagonal compare per score.
+      const bool tile_after = j * ATC_K > qi - lane + 31, tile_before = j * ATC_K + ATC_K - 1 <= qi - lane;
       bool any_cut = false;
 #pragma unroll
       for (int uu = 0; uu < 4; ++uu) {
         const int kl = lane * 4 + uu, kj = j * ATC_K + kl;
-        const float fm = (p.frame_mask != nullptr && kj < p.Sk) ? p.frame_mask[(int64_t)b * p.frame_mask_stride + kj] : 0.f;
+        const float fm = fm_next[uu];
         const bool cut = ((p.flags & KIT_MASK_REPEAT_INC) && fm == 1.f) || (p.flags & KIT_MASK_TRIANGLE);
-        kb[kl] = (kj >= p.Sk) ? -INFINITY : ((p.flags & KIT_MASK_KEYPAD_ADD) ? fm * 1.4426950408889634f : 0.f);
+        kb[kl] = (kj >= p.Sk || (cut && tile_after)) ? -INFINITY : ((p.flags & KIT_MASK_KEYPAD_ADD) ? fm * 1.4426950408889634f : 0.f);
         kc[kl] = cut ? (float)kj : -1.f;
         any_cut |= cut;
       }
-      // no key of this tile can be cut for this warp's rows when the whole tile lies at or before the warp's first query
-      const bool need_cut = __any_sync(0xffffffffu, any_cut) && (j * ATC_K + ATC_K - 1 > qi - lane);
+      const bool need_cut = __any_sync(0xffffffffu, any_cut) && !tile_after && !tile_before;
+      if (j + 1 < p.n_ktiles) load_fm(j + 1);   // the next tile's frame mask travels during this step
       __syncwarp();
       mbar_wait(&s_full[sl], (n >> 1) & 1);
       tc_fence_after();
@@ -238,7 +258,7 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
       tmem_ld32(s_addr + 64, xr + 64);    // the second half of the row travels while the first is scaled and masked
       tmem_ld32(s_addr + 96, xr + 96);
       // scale + mask (base 2), row maximum
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains (no fp reassociation by nvcc)
+      float mx4[8] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains
       const uint32_t kb_s = smem_u32(kb), kc_s = smem_u32(kc);
       const float qif = (float)qi;
       const uint64_t sc2 = pk2(p.scale2, p.scale2);
@@ -257,8 +277,8 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
               v1 = (__uint_as_float(kcv[u + 1]) > qif) ? -INFINITY : v1;
               x[c] = v0;
               x[c + 1] = v1;
-              mx4[u] = fmaxf(mx4[u], v0);
-              mx4[u + 1] = fmaxf(mx4[u + 1], v1);
+              mx4[u + 4 * (c4 & 1)] = fmaxf(mx4[u + 4 * (c4 & 1)], v0);
+              mx4[u + 1 + 4 * (c4 & 1)] = fmaxf(mx4[u + 1 + 4 * (c4 & 1)], v1);
             }
           }
         } else {
@@ -273,8 +293,8 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
               up2(fma2(pk2(x[c], x[c + 1]), sc2, pk2(__uint_as_float(kbv[u]), __uint_as_float(kbv[u + 1]))), v0, v1);
               x[c] = v0;
               x[c + 1] = v1;
-              mx4[u] = fmaxf(mx4[u], v0);
-              mx4[u + 1] = fmaxf(mx4[u + 1], v1);
+              mx4[u + 4 * (c4 & 1)] = fmaxf(mx4[u + 4 * (c4 & 1)], v0);
+              mx4[u + 1 + 4 * (c4 & 1)] = fmaxf(mx4[u + 1 + 4 * (c4 & 1)], v1);
             }
           }
         }
@@ -285,7 +305,7 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[sl]);
       half(16);
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float mx = fmaxf(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), fmaxf(fmaxf(mx4[4], mx4[5]), fmaxf(mx4[6], mx4[7])));
       const float m_new = fmaxf(m_run, mx);
       const float m_ref = (m_new == -INFINITY) ? 0.f : m_new;
       const float corr = ex2f(m_run - m_ref);
