@@ -315,6 +315,103 @@ __global__ void __launch_bounds__(WARPS * 32) ln_bwd_kernel(const bf16* __restri
   if (dxsum != nullptr) ln_bwd_cols<NV, WARPS>(accx, dxsum, H, s_buf);
 }
 
+// H == 256 (one 16-byte vector per lane and row), no addend: the same arithmetic with ALL of a warp's rows in flight before
+// the first one is consumed.  At M = 16384 a warp owns 7 rows: the kernel above walks them in four dependent
+// load -> reduce -> store round trips with 32 KB per SM in flight; here the 2 x 7 packed vectors (56 registers) are requested
+// up front -- 112 KB per SM in flight, one round trip -- and the three column partials meet in shared memory in one pass.
+template <int WARPS, int R>
+__global__ void __launch_bounds__(WARPS * 32) ln_bwd_rows_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ s_saved,
+                                                                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                                 const float* __restrict__ gamma, bf16* __restrict__ dx,
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                 float* __restrict__ dxsum, int64_t M) {
+  constexpr int H = 256;
+  extern __shared__ __align__(16) float s_part[];   // [3][WARPS][256]
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float gm[8], accg[8], accb[8], accx[8];
+  load8(gamma + lane * 8, gm);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) accg[u] = accb[u] = accx[u] = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * WARPS;
+  for (int64_t row0 = (int64_t)blockIdx.x * WARPS + warp; row0 < M; row0 += R * stride) {
+    uint4 xr[R], gr[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int64_t row = row0 + k * stride;
+      if (row < M) {
+        xr[k] = __ldg(reinterpret_cast<const uint4*>(s_saved + row * H) + lane);
+        gr[k] = __ldg(reinterpret_cast<const uint4*>(dy + row * H) + lane);
+      } else {
+        xr[k] = make_uint4(0u, 0u, 0u, 0u);
+        gr[k] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    float my_mean = 0.f, my_rstd = 0.f;   // lane k holds the statistics of row k
+    {
+      const int64_t rl = row0 + lane * stride;
+      if (lane < R && rl < M) {
+        my_mean = mean_in[rl];
+        my_rstd = rstd_in[rl];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int64_t row = row0 + k * stride;
+      const float mean = __shfl_sync(0xffffffffu, my_mean, k), rstd = __shfl_sync(0xffffffffu, my_rstd, k);
+      if (row < M) {   // warp-uniform
+        float xh[8], gg[8];
+        const uint32_t xw[4] = {xr[k].x, xr[k].y, xr[k].z, xr[k].w}, gw[4] = {gr[k].x, gr[k].y, gr[k].z, gr[k].w};
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 xv = unpack_bf16(xw[j]), dv = unpack_bf16(gw[j]);
+          const float xs[2] = {xv.x, xv.y}, ds[2] = {dv.x, dv.y};
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int u = 2 * j + e;
+            const float h = (xs[e] - mean) * rstd, d = ds[e];
+            accg[u] += d * h;
+            accb[u] += d;
+            const float w = d * gm[u];
+            s1 += w;
+            s2 += w * h;
+            xh[u] = h;
+            gg[u] = w;
+          }
+        }
+        s1 = warp_sum(s1) * (1.f / H);
+        s2 = warp_sum(s2) * (1.f / H);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float r = rstd * (gg[u] - s1 - xh[u] * s2);
+          accx[u] += r;
+          gg[u] = r;
+        }
+        store8(dx + row * H + lane * 8, gg);
+      }
+    }
+  }
+  float* mine = s_part + warp * H + lane * 8;
+  *reinterpret_cast<float4*>(mine) = make_float4(accg[0], accg[1], accg[2], accg[3]);
+  *reinterpret_cast<float4*>(mine + 4) = make_float4(accg[4], accg[5], accg[6], accg[7]);
+  *reinterpret_cast<float4*>(mine + WARPS * H) = make_float4(accb[0], accb[1], accb[2], accb[3]);
+  *reinterpret_cast<float4*>(mine + WARPS * H + 4) = make_float4(accb[4], accb[5], accb[6], accb[7]);
+  *reinterpret_cast<float4*>(mine + 2 * WARPS * H) = make_float4(accx[0], accx[1], accx[2], accx[3]);
+  *reinterpret_cast<float4*>(mine + 2 * WARPS * H + 4) = make_float4(accx[4], accx[5], accx[6], accx[7]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < 3 * H; c += WARPS * 32) {
+    const int which = c >> 8, col = c & (H - 1);
+    float* out = which == 0 ? dgamma : (which == 1 ? dbeta : dxsum);
+    if (out == nullptr) continue;
+    const float* p = s_part + which * WARPS * H + col;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) t += p[w * H];
+    atomicAdd(out + col, t);
+  }
+}
+
 // ---------------------------------------------------------------- SwiGLU gate (model.py:18-22)
 // x12 [M,2H] = fc1(x) | fc2(x);  g = x1 * sigmoid(x2)
 __global__ void swiglu_gate_fwd_kernel(const bf16* __restrict__ x12, bf16* __restrict__ g, int64_t M, int H) {
@@ -576,7 +673,18 @@ int ln_bwd(const bf16* dy, const bf16* s_saved, const float* mean, const float* 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  if (H <= 256) {   // 16 warps x 16 KB of column partials; one block per SM (103 registers x 512 threads)
+  static int rows_variant = -1;   // KIT_LNBWD_ROWS=0: the two-rows-in-flight kernel (A/B measurements)
+  if (rows_variant < 0) {
+    const char* e = getenv("KIT_LNBWD_ROWS");
+    rows_variant = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (H == 256 && addend == nullptr && rows_variant == 1) {   // every row of a warp in flight at once
+    constexpr int R = 7, W = 16;
+    const int64_t want = ceil_div(M, W * R);
+    const unsigned grid = (unsigned)(want < sms ? (want < 1 ? 1 : want) : sms);
+    launch_kernel(ln_bwd_rows_kernel<W, R>, dim3(grid), dim3(W * 32), 3 * W * 256 * sizeof(float), st, dy, s_saved, mean, rstd, gamma, dx,
+                  dgamma, dbeta, dxsum, M);
+  } else if (H <= 256) {   // 16 warps x 16 KB of column partials; one block per SM (103 registers x 512 threads)
     const int64_t want = ceil_div(M, 16 * 2);
     const unsigned grid = (unsigned)(want < sms ? (want < 1 ? 1 : want) : sms);
     launch_kernel(ln_bwd_kernel<1, 16>, dim3(grid), dim3(512), 0, st, dy, s_saved, mean, rstd, gamma, addend, dx, dgamma, dbeta, dxsum, M, H);
