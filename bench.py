@@ -148,7 +148,7 @@ def gpu_run(args):
     torch.manual_seed(42)
     m = model.KeypointCompleter(2 * KP, H, L, NH).to(dev)
     m.train()
-    use_graph = world == 1 and not args.no_graph
+    use_graph = not args.no_graph     # world > 1: a chain of graphs cut at the all-reduce buckets (train.TrainStep)
     opt = optim.FlatAdam(m, lr=5e-6, capturable=use_graph)
     reducer = None
     if world > 1:
@@ -156,7 +156,7 @@ def gpu_run(args):
         reducer = parallel.BucketReducer(m.flat_grads, m.layout.buckets)
         opt.grad_scale = 1.0 / world
         dist.broadcast(m.flat_params, src=0)
-    # single GPU: the step is captured once per input slot as a CUDA graph and replayed (train.TrainStep use_graph)
+    # the step is captured once per input slot as a CUDA graph (a chain of graphs under data parallelism) and replayed
     step = train.TrainStep(m, opt, criterion="mse", reducer=reducer, use_graph=use_graph, streams=args.streams)
 
     # a ring of distinct synthetic batches (pinned host copies + device-resident copies)

@@ -36,8 +36,9 @@ class TrainStep:
         self.model = model
         self.streams = int(streams)
         self._side = None
-        # data parallel: kernel by kernel (a graph holding NCCL collectives hung process-group teardown on 2 x B200)
-        self.use_graph = use_graph and reducer is None
+        # data parallel: a graph holding NCCL collectives hung process-group teardown on 2 x B200, so the step is captured
+        # as a CHAIN of graphs cut at the bucket boundaries of backward and the collectives are launched between them
+        self.use_graph = use_graph and (reducer is None or self.streams == 1)
         self.optimizer = optimizer if optimizer is not None else FlatAdam(model, lr=lr, capturable=self.use_graph)
         if self.use_graph and not getattr(self.optimizer, "capturable", False):
             raise ValueError("use_graph=True needs FlatAdam(capturable=True): the step count must live on the device")
@@ -108,7 +109,7 @@ class TrainStep:
         self.last_launches = launches + 2
         return total
 
-    def forward_backward(self, inputs, sota, mask):
+    def forward_backward(self, inputs, sota, mask, _bucket_cb=None):
         model = self.model
         B, T1 = inputs.shape[0], inputs.shape[1]
         T = T1 - 1
@@ -127,7 +128,9 @@ class TrainStep:
         eng.forward(inputs, T1 * K2, x_dec, T1 * K2, enc_mask, dec_mask, self.pred, self.zero_masked)
         loss, dpred = fused_loss(self.pred, sota, None, self.kind, want_grad=True)
         grads.zero_()                                            # optimizer.zero_grad()  (A1_train.py:133)
-        if self.reducer is not None:
+        if _bucket_cb is not None:                               # segmented capture: the caller owns the collectives
+            eng.backward(dpred, _bucket_cb)
+        elif self.reducer is not None:
             self.reducer.begin()
             eng.backward(dpred, self.reducer.bucket_ready)
             self.reducer.finish()
@@ -135,6 +138,59 @@ class TrainStep:
             eng.backward(dpred)
         self.last_launches = eng.fwd_launches + eng.bwd_launches + 3
         return loss
+
+    def _capture_chain(self, inputs, sota, mask):
+        """Data-parallel capture: [graph | bucket 0 ready | graph | bucket 1 ready | ... | last bucket ready | wait for the
+        collectives | graph (Adam)].  The cuts are made from inside ``kit_engine_backward``'s bucket callback -- the capture of the running
+        graph ends, a new one begins on the same stream and shares the memory pool -- so each all-reduce is enqueued on
+        the reducer's side stream exactly where the kernel-by-kernel step enqueues it and still overlaps the rest of
+        backward, while the ~240 kernels of the step are replayed instead of launched."""
+        pool = torch.cuda.graph_pool_handle()
+        chain, cur = [], [None]
+
+        def begin():
+            cur[0] = torch.cuda.CUDAGraph()
+            cur[0].capture_begin(pool=pool, capture_error_mode="thread_local")
+
+        def end():
+            cur[0].capture_end()
+            chain.append(("graph", cur[0]))
+            cur[0] = None
+
+        def cut(b):
+            end()
+            chain.append(("bucket", b))
+            begin()
+
+        side = torch.cuda.Stream(device=inputs.device)
+        side.wait_stream(torch.cuda.current_stream())
+        try:
+            with torch.cuda.stream(side):
+                begin()
+                loss = self.forward_backward(inputs, sota, mask, _bucket_cb=cut)
+                self.optimizer.step()      # backward ends with its last bucket: the graph opened by that cut holds Adam
+                self.last_launches += 2
+                end()
+                chain.insert(len(chain) - 1, ("finish", None))
+        except Exception:
+            if cur[0] is not None:
+                try:
+                    cur[0].capture_end()
+                except Exception:   # noqa: BLE001 -- the capture is already invalid
+                    pass
+            raise
+        torch.cuda.current_stream().wait_stream(side)
+        return chain, loss
+
+    def _replay_chain(self, chain):
+        self.reducer.begin()
+        for kind, x in chain:
+            if kind == "graph":
+                x.replay()
+            elif kind == "bucket":
+                self.reducer.bucket_ready(x)
+            else:
+                self.reducer.finish()
 
     def _eager(self, inputs, sota, mask):
         loss = self.forward_backward(inputs, sota, mask)
@@ -158,8 +214,11 @@ class TrainStep:
             graph = torch.cuda.CUDAGraph()
             steps_before = self.optimizer.step_count
             try:
-                with torch.cuda.graph(graph):
-                    loss = self._eager(inputs, sota, mask)
+                if self.reducer is not None:
+                    graph, loss = self._capture_chain(inputs, sota, mask)
+                else:
+                    with torch.cuda.graph(graph):
+                        loss = self._eager(inputs, sota, mask)
             except Exception as exc:   # noqa: BLE001 -- a failed capture must not cost the step: fall back to launches
                 import warnings
                 warnings.warn(f"CUDA-graph capture of the train step failed ({exc!r}); continuing kernel by kernel")
@@ -171,7 +230,10 @@ class TrainStep:
             entry = (graph, loss, (inputs, sota, mask))           # keep the buffers alive
             self._graphs[key] = entry
         self.optimizer.sync_host_values()
-        entry[0].replay()
+        if self.reducer is not None:
+            self._replay_chain(entry[0])
+        else:
+            entry[0].replay()
         self.optimizer.step_count += 1
         return entry[1]
 

@@ -221,6 +221,37 @@ def test_graph_replayed_step_matches_eager_step():
     assert _rel(p1, p0) < 1e-4        # same kernels, same order; atomics in the weight gradients reorder fp32 sums
 
 
+def test_chained_graph_step_with_reducer_matches_eager_step():
+    """The data-parallel form of the captured step: a chain of graphs cut at backward's bucket boundaries, the bucket
+    callbacks (the all-reduces; no-ops in a one-process world) issued between them, Adam in the last graph."""
+    from keypoints_interpolation_transformer_b200 import parallel
+    Kp, H, L, NH, B, T = 54, 64, 2, 4, 4, 16
+    batches = [tuple(t.to(DEV) for t in ko.synthetic_batch(B, T, Kp, seed=40 + i)) for i in range(2)]
+    results = []
+    for use_graph in (False, True):
+        m = _build(2 * Kp, H, L, NH)
+        m.train()
+        m.ensure_flat_grads()
+        reducer = parallel.BucketReducer(m.flat_grads, m.layout.buckets)
+        seen = []
+        ready = reducer.bucket_ready
+        reducer.bucket_ready = lambda b, ready=ready, seen=seen: (seen.append(b), ready(b))[1]
+        opt = optim.FlatAdam(m, lr=1e-3, capturable=use_graph)
+        step = train.TrainStep(m, opt, criterion="mse", reducer=reducer, use_graph=use_graph)
+        losses = [step(*batches[i % 2]).item() for i in range(8)]
+        torch.cuda.synchronize()
+        nb = len(m.layout.buckets)
+        assert seen == list(range(nb)) * 8                       # every step, replayed or not, announces every bucket in order
+        if use_graph:
+            assert step.use_graph and len(step._graphs) == 2 and opt.step_count == 8
+            chain = next(iter(step._graphs.values()))[0]
+            assert [k for k, _ in chain].count("graph") == nb + 1 and [k for k, _ in chain][-2] == "finish"
+        results.append((losses, m.flat_params[:m.layout.trainable].clone()))
+    (l0, p0), (l1, p1) = results
+    assert np.allclose(l0, l1, rtol=2e-3, atol=1e-6), (l0, l1)
+    assert _rel(p1, p0) < 1e-4
+
+
 def test_cycle_model_matches_reference_golden(golden_dir):
     """model.KeypointCompleterCycle (model.py:212-321) through the A2_train_cycle.py call surface, one sequence per call:
     the second-model call (:111-115, "all" masks + all-ones pad masks) and a first-model style call (repeat-inc masks, frame
