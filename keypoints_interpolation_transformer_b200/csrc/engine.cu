@@ -936,7 +936,7 @@ extern "C" int kit_engine_bind(KitEngine* e, float* params, float* grads, void* 
   std::vector<int> prefix(e->L.wdescs.size() + 1, 0);
   for (size_t i = 0; i < e->L.wdescs.size(); ++i) {
     const WeightDesc& d = e->L.wdescs[i];
-    prefix[i + 1] = prefix[i] + ((d.rows + 31) / 32) * ((d.cols_pad + 31) / 32);
+    prefix[i + 1] = prefix[i] + ((d.rows + WR_TILE - 1) / WR_TILE) * ((d.cols_pad + WR_TILE - 1) / WR_TILE);
   }
   e->total_tiles = prefix.back();
   KIT_CHECK_CUDA(cudaMemcpy(e->wdesc_dev, e->L.wdescs.data(), e->L.wdescs.size() * sizeof(WeightDesc), cudaMemcpyHostToDevice));

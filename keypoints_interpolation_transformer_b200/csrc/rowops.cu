@@ -584,12 +584,14 @@ __global__ void pack_frames_kernel(const float* __restrict__ src, int64_t batch_
 }
 
 // ---------------------------------------------------------------- weight refresh (fp32 -> bf16 (+T))
-// One 32x32 tile per block; the tile table maps a flat tile index to (matrix, tile_r, tile_c).
-__global__ void weight_refresh_kernel(const float* __restrict__ params, bf16* __restrict__ wb,
-                                      const WeightDesc* __restrict__ descs, const int* __restrict__ tile_prefix,
-                                      int n_desc) {
+// One WR_TILE x WR_TILE tile per block; the tile table maps a flat tile index to (matrix, tile_r, tile_c).  16-byte loads of
+// the fp32 masters (arena offsets are multiples of 8 floats), 8-byte stores of both bf16 copies (the transposed one through
+// shared memory); matrices whose width is not a multiple of four (the K = 142 embeddings) take the scalar loads.
+__global__ void __launch_bounds__(256) weight_refresh_kernel(const float* __restrict__ params, bf16* __restrict__ wb,
+                                                             const WeightDesc* __restrict__ descs,
+                                                             const int* __restrict__ tile_prefix, int n_desc) {
   pdl_grid_sync();
-  __shared__ float tile[32][33];
+  __shared__ float tile[WR_TILE][WR_TILE + 1];
   int lo = 0, hi = n_desc - 1;
   const int tid = blockIdx.x;
   while (lo < hi) {  // last desc with prefix <= tid
@@ -598,23 +600,41 @@ __global__ void weight_refresh_kernel(const float* __restrict__ params, bf16* __
   }
   const WeightDesc d = descs[lo];
   const int local = tid - tile_prefix[lo];
-  const int tiles_c = (d.cols_pad + 31) / 32;
+  const int tiles_c = (d.cols_pad + WR_TILE - 1) / WR_TILE;
   const int tr = local / tiles_c, tc = local % tiles_c;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, four columns each, rows ty + 16 i
+  const bool vec = (d.cols & 3) == 0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = tr * 32 + ty + 8 * i, c = tc * 32 + tx;
-    float v = 0.f;
-    if (r < d.rows && c < d.cols) v = params[d.src_off + (int64_t)r * d.cols + c];
-    tile[ty + 8 * i][tx] = v;
-    if (r < d.rows_pad && c < d.dst_ld && d.dst_off >= 0) wb[d.dst_off + (int64_t)r * d.dst_ld + c] = __float2bfloat16(v);
+  for (int i = 0; i < WR_TILE / 16; ++i) {
+    const int r = tr * WR_TILE + ty + 16 * i, c = tc * WR_TILE + 4 * tx;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < d.rows) {
+      const float* src = params + d.src_off + (int64_t)r * d.cols + c;
+      if (vec) {
+        if (c < d.cols) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(src));
+          v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c + u < d.cols) v[u] = __ldg(src + u);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) tile[ty + 16 * i][4 * tx + u] = v[u];
+    if (d.dst_off >= 0 && r < d.rows_pad && c < d.dst_ld)   // dst_ld is a multiple of 8: the four columns are inside
+      *reinterpret_cast<uint2*>(wb + d.dst_off + (int64_t)r * d.dst_ld + c) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
   }
   if (d.dstT_off < 0) return;
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = tc * 32 + ty + 8 * i, r = tr * 32 + tx;  // transposed element (c, r)
-    if (c < d.cols && r < d.dstT_ld) wb[d.dstT_off + (int64_t)c * d.dstT_ld + r] = __float2bfloat16(tile[tx][ty + 8 * i]);
+  for (int i = 0; i < WR_TILE / 16; ++i) {
+    const int c = tc * WR_TILE + ty + 16 * i, r = tr * WR_TILE + 4 * tx;  // transposed elements (c, r .. r + 3)
+    if (c < d.cols && r < d.dstT_ld)
+      *reinterpret_cast<uint2*>(wb + d.dstT_off + (int64_t)c * d.dstT_ld + r) =
+          make_uint2(pack_bf16(tile[4 * tx][ty + 16 * i], tile[4 * tx + 1][ty + 16 * i]),
+                     pack_bf16(tile[4 * tx + 2][ty + 16 * i], tile[4 * tx + 3][ty + 16 * i]));
   }
 }
 

@@ -6,6 +6,7 @@ namespace kit {
 
 // One 2-D weight of the fp32 arena and where its bf16 copy (dst) and transposed bf16 copy (dstT)
 // live in the bf16 weight arena (-1 = not needed).  cols_pad/rows_pad: zero-filled extents.
+constexpr int WR_TILE = 64;   // weight_refresh_kernel: tile edge (the tile table built at bind time uses it too)
 struct WeightDesc {
   int64_t src_off;
   int rows, cols;
