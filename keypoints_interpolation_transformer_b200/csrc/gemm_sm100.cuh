@@ -546,6 +546,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
           const uint32_t ph = (cnt / STAGES) & 1;
           mbar_wait(&full[s], ph);
           if (cnt == 0) mark(4);
+          else if (cnt < 4) mark(11 + cnt);   // slots 12..14: k-blocks 1..3 of the first item
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t b_base = a_base + A_BYTES;

@@ -30,6 +30,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default=None)
+    ap.add_argument("--warm", action="store_true", help="no L2 flush between iterations (operands L2-resident, as inside the step)")
     args = ap.parse_args()
     dev = "cuda"
     lib = K.lib()
@@ -62,7 +63,8 @@ def main():
         torch.cuda.synchronize()
         times = []
         for _ in range(args.iters):
-            flush.zero_()                       # evict L2 between iterations
+            if not args.warm:
+                flush.zero_()                   # evict L2 between iterations
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             run()
@@ -79,8 +81,9 @@ def main():
             if lib.kit_gemm_trace_read(buf) == 0:
                 t0 = buf[0]
                 names = ["entry", "setup_done", "pdl_done", "tma_first", "full_first", "mma_item0_done", "epi_tmem_full",
-                         "epi_ld_done", "epi_store_issued", "epi_loop_end", "epi_store_drained", "exit"]
-                print("   trace(cycles): " + " ".join(f"{n}={buf[i] - t0}" for i, n in enumerate(names)))
+                         "epi_ld_done", "epi_store_issued", "epi_loop_end", "epi_store_drained", "exit", "full_kb1", "full_kb2",
+                         "full_kb3"]
+                print("   trace(cycles): " + " ".join(f"{n}={buf[i] - t0}" for i, n in enumerate(names) if buf[i] > 0))
         print(f"{name:20s} M={m:6d} N={n:5d} K={k:6d}  {med * 1e3:8.1f} us  {fl / (med * 1e-3) / 1e12:7.1f} TFLOP/s", flush=True)
 
 
