@@ -195,6 +195,41 @@ def test_long_sequence_inference_matches_oracle_and_is_batch_independent():
     assert _rel(pred_big[:4], pred_small) < 5e-3      # same sequences, different tile / pair assignment
 
 
+def test_full_size_train_step_is_linear_in_the_batch():
+    """BASELINE configs[1] at its full size (B = 256 x T = 64 x K = 71, default dims), where the CPU oracle takes minutes:
+    size-independent properties instead.  Sequences are independent, so (i) a sequence's prediction does not depend on
+    what else is in the batch, (ii) the batch loss is the mean of the losses of its equal parts, (iii) the gradient of the
+    batch is the mean of the gradients of its parts; and the first 8 sequences are checked against the oracle itself."""
+    from keypoints_interpolation_transformer_b200 import synthetic
+    Kp, H, L, NH, B, T, P = 71, 256, 6, 8, 256, 64, 4
+    m = _build(2 * Kp, H, L, NH)
+    m.train()
+    inputs, gt, mask = synthetic.synthetic_batch(B, T, Kp, seed=42, smooth=True)
+    d_in, d_gt, d_mask = inputs.to(DEV), gt.to(DEV), mask.to(DEV)
+    step = train.TrainStep(m, optim.FlatAdam(m, lr=0.0), criterion="mse")
+    loss_full = step.forward_backward(d_in, d_gt, d_mask).item()
+    torch.cuda.synchronize()
+    pred_full, grad_full = step.pred.clone(), m.flat_grads[:m.layout.trainable].clone()
+    assert torch.isfinite(pred_full).all() and torch.isfinite(grad_full).all()
+    part = B // P
+    losses, grad_sum = [], torch.zeros_like(grad_full)
+    for p in range(P):
+        sl = slice(p * part, (p + 1) * part)
+        lp = step.forward_backward(d_in[sl].contiguous(), d_gt[sl].contiguous(), d_mask[sl].contiguous()).item()
+        torch.cuda.synchronize()
+        losses.append(lp)
+        grad_sum += m.flat_grads[:m.layout.trainable]
+        assert _rel(step.pred, pred_full[sl]) < 5e-3          # (i): same kernels, different tile / pair assignment
+    assert abs(sum(losses) / P - loss_full) < 1e-5 * abs(loss_full)                # (ii)
+    assert _rel(grad_sum / P, grad_full) < 5e-3                                    # (iii): fp32 sums in a different order
+    # the oracle on the first sequences of the same batch
+    sd = ko.deterministic_state_dict(2 * Kp, H, L)
+    with torch.no_grad():
+        params = {k: v.clone() for k, v in sd.items()}
+        _, ref_pred = ko.train_forward_loss(params, inputs[:8], gt[:8], mask[:8], NH, criterion="mse")
+    assert _rel(pred_full[:8], ref_pred) < TOL
+
+
 def test_graph_replayed_step_matches_eager_step():
     """train.TrainStep(use_graph=True): the captured step (device-side Adam step count / lr) updates the parameters
     exactly like the eager step, honours a learning-rate change between replays, and works across two input slots."""
