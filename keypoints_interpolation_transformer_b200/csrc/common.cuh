@@ -252,6 +252,13 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// The barrier before a CTA of a pair exits (its peer may still read its shared memory / signal its barriers): pure execution
+// ordering, no data is handed over, so the arrive is relaxed -- the release form is MEMBAR.ALL.GPU + ERRBAR per thread, which at
+// the end of a kernel waits for every outstanding global store of the epilogue (7-10 % of the samples of a K = 256 GEMM).
+__device__ __forceinline__ void cluster_sync_exit() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // smem (generic-proxy writes made visible with fence.proxy.async) -> global tile, clipped at the tensor edge
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -351,6 +358,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// relaxed remote arrive: the data the barrier guards is ordered by tcgen05 fences (TMEM) or by fence.proxy.async (this CTA's
+// shared memory, read by the tensor core) -- a release fence at cluster scope per arrival costs ~1000 cycles per warp per arrival (MEMBAR.ALL.CTA + ERRBAR in the SASS)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets TMEM lane (base_lane + i).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {

@@ -85,13 +85,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
   }
 }
-// relaxed remote arrive: the data the barrier guards is ordered by tcgen05 fences (TMEM) or by fence.proxy.async (this CTA's
-// shared memory, read by the tensor core) -- a release fence at cluster scope per arrival costs ~1000 cycles per warp per chunk
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t rank) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 template <bool BWD>
@@ -570,12 +563,12 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
         named_bar_sync(13, 32 * FFN_EPI_WARPS);
       }
     }
-    if (lane == 0) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_read();   // the staging tiles have been read; the writes complete with the kernel
     if (warp == 2) mark(98);
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();
+  cluster_sync_exit();
   if (warp == 1) tmem_dealloc_cg2<512>(tmem_base);
   if (warp == 0) mark(99);
 }

@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (CL == 1 || rank == 0) mbar_arrive(&tmem_empty[as]); else mbar_arrive_cluster(&tmem_empty[as], 0);
+          if (CL == 1 || rank == 0) mbar_arrive(&tmem_empty[as]); else mbar_arrive_cluster_relaxed(&tmem_empty[as], 0);   // the accumulator reads are complete (tcgen05.wait::ld): nothing for a release fence to order
         }
       };
       const bool have0 = colg < p.N, have1 = colg + 32 < p.N;   // warp-uniform
@@ -848,12 +848,12 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
       }
     }
     if (warp == 2) mark(9);
-    if (EPI != EPI_GENERIC && lane == 0) tma_store_wait_all();   // global writes complete before the CTA exits
+    if (EPI != EPI_GENERIC && lane == 0) tma_store_wait_read();   // the staging tiles have been read: shared memory may go; the writes complete with the kernel
     if (warp == 2) mark(10);
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // no CTA exits while its peer may still read its shared memory / signal its barriers
+  if (CL > 1) cluster_sync_exit();   // no CTA exits while its peer may still read its shared memory / signal its barriers
   if (warp == 0) mark(11);
   if (warp == 1) {
     if (CL == 1) tmem_dealloc<TMEM_COLS>(tmem_base); else tmem_dealloc_cg2<TMEM_COLS>(tmem_base);

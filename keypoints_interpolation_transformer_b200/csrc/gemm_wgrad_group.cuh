@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(gemm_threads<WG_BN>(), 1) gemm_wgrad_group_ker
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (rank == 0) mbar_arrive(&tmem_empty[0]); else mbar_arrive_cluster(&tmem_empty[0], 0);
+          if (rank == 0) mbar_arrive(&tmem_empty[0]); else mbar_arrive_cluster_relaxed(&tmem_empty[0], 0);
         }
       };
       if (!waited) {
@@ -230,11 +230,11 @@ __global__ void __launch_bounds__(gemm_threads<WG_BN>(), 1) gemm_wgrad_group_ker
         }
       }
     }
-    if (lane == 0) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_read();   // the staging tiles have been read; the reduce-adds complete with the kernel
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();
+  cluster_sync_exit();
   if (warp == 1) tmem_dealloc_cg2<TMEM_COLS>(tmem_base);
 }
 
