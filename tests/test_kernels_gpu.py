@@ -200,7 +200,7 @@ def _attention_case(B, NH, S, d, flags, explicit):
 
 
 # ------------------------------------------------------------------------------- LayerNorm
-@pytest.mark.parametrize("M,H", [(1000, 256), (333, 64), (512, 512), (64, 1024)])
+@pytest.mark.parametrize("M,H", [(1000, 256), (333, 64), (512, 512), (64, 1024), (16384, 256), (40000, 256)])
 def test_add_layernorm_fwd_bwd(M, H):
     g = torch.Generator(device="cpu").manual_seed(M + H)
     a = _bf(torch.randn(M, H, generator=g)).to(DEV)
@@ -235,6 +235,17 @@ def test_add_layernorm_fwd_bwd(M, H):
     assert _rel(dx, sx.grad + add.float()) < 5e-3
     assert _rel(dgamma, gr.grad) < 1e-4
     assert _rel(dbeta, br.grad) < 1e-4
+    # without an addend (the form the engine uses; H = 256 takes ln_bwd_rows_kernel: every row of a warp in flight at once,
+    # M = 40000 walks more than one chunk of rows per warp), accumulating into non-zero dgamma / dbeta
+    dx2 = torch.empty(M, H, dtype=torch.bfloat16, device=DEV)
+    dgamma2 = torch.ones(H, device=DEV)
+    dbeta2 = torch.full((H,), -2.0, device=DEV)
+    K.check(lib.kit_layernorm_bwd(K.ptr(dy), K.ptr(s), K.ptr(mean), K.ptr(rstd), K.ptr(gamma), None, K.ptr(dx2),
+                                  K.ptr(dgamma2), K.ptr(dbeta2), M, H, _sp()))
+    torch.cuda.synchronize()
+    assert _rel(dx2, sx.grad) < 5e-3
+    assert _rel(dgamma2 - 1.0, gr.grad) < 1e-4
+    assert _rel(dbeta2 + 2.0, br.grad) < 1e-4
 
 
 # ------------------------------------------------------------------------------- fused feed-forward block
