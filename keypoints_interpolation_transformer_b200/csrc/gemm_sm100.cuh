@@ -546,7 +546,6 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
           const uint32_t ph = (cnt / STAGES) & 1;
           mbar_wait(&full[s], ph);
           if (cnt == 0) mark(4);
-          else if (cnt < 4) mark(11 + cnt);   // slots 12..14: k-blocks 1..3 of the first item
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t b_base = a_base + A_BYTES;
@@ -832,9 +831,12 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
           }
           __syncwarp();
         }
+        if (it == 0 && warp == 2 && sub == 0) mark(12);
         gemm_epilogue_sub<EPI>(p, col0, lane, r, t_sub[sub], t_aux[sub]);
+        if (it == 0 && warp == 2 && sub == 0) mark(13);
         fence_proxy_async();
         __syncwarp();
+        if (it == 0 && warp == 2 && sub == 0) mark(14);
         if (lane == 0) {
           if (EPI == EPI_GELU) {   // one bulk group per store: the rotation waits on "all but the latest"
             tma_store_2d_a(&tmAux, t_aux[sub], col0, row0);
