@@ -255,6 +255,14 @@ __device__ __forceinline__ void cluster_sync_all() {
 // The barrier before a CTA of a pair exits (its peer may still read its shared memory / signal its barriers): pure execution
 // ordering, no data is handed over, so the arrive is relaxed -- the release form is MEMBAR.ALL.GPU + ERRBAR per thread, which at
 // the end of a kernel waits for every outstanding global store of the epilogue (7-10 % of the samples of a K = 256 GEMM).
+// The barrier after set-up: what the peer must see is (a) the mbarrier initialisation, published by
+// fence.mbarrier_init.release.cluster, and (b) the all-ones operand tile, made visible to the tensor core by this thread's
+// fence.proxy.async -- both issued before the arrive, so the arrive itself is relaxed (the release form starts every kernel
+// with MEMBAR.ALL.GPU + ERRBAR: ~1.1 k of the 1.7 k set-up cycles of a GEMM launch).
+__device__ __forceinline__ void cluster_sync_setup() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_sync_exit() {
   asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
   if (warp == 1) tmem_alloc_cg2<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();
+  cluster_sync_setup();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 

@@ -465,9 +465,11 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
     if (EPI == EPI_ADD_LNBWD) mbar_init(&s_bars[lane], 1);
     fence_barrier_init();
     fence_proxy_async();
+    mark(12);
   }
   if (warp == 1) {
     if (CL == 1) tmem_alloc<TMEM_COLS>(tmem_slot); else tmem_alloc_cg2<TMEM_COLS>(tmem_slot);
+    mark(13);
   }
   if (BG && warp >= 2 && threadIdx.x < 64 + 64) {   // 64 threads x 16 bytes
     *reinterpret_cast<uint4*>(ones_tile + (threadIdx.x - 64) * 16) = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -475,7 +477,8 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // peer barriers are initialised before anyone signals them
+  if (warp == 0) mark(14);
+  if (CL > 1) cluster_sync_setup();   // peer barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) mark(1);
@@ -831,12 +834,9 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
           }
           __syncwarp();
         }
-        if (it == 0 && warp == 2 && sub == 0) mark(12);
         gemm_epilogue_sub<EPI>(p, col0, lane, r, t_sub[sub], t_aux[sub]);
-        if (it == 0 && warp == 2 && sub == 0) mark(13);
         fence_proxy_async();
         __syncwarp();
-        if (it == 0 && warp == 2 && sub == 0) mark(14);
         if (lane == 0) {
           if (EPI == EPI_GELU) {   // one bulk group per store: the rotation waits on "all but the latest"
             tma_store_2d_a(&tmAux, t_aux[sub], col0, row0);

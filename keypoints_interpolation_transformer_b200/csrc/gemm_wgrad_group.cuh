@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(gemm_threads<WG_BN>(), 1) gemm_wgrad_group_ker
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();
+  cluster_sync_setup();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 

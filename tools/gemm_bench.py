@@ -81,8 +81,8 @@ def main():
             if lib.kit_gemm_trace_read(buf) == 0:
                 t0 = buf[0]
                 names = ["entry", "setup_done", "pdl_done", "tma_first", "full_first", "mma_item0_done", "epi_tmem_full",
-                         "epi_ld_done", "epi_store_issued", "epi_loop_end", "epi_store_drained", "exit", "epi_tile_free", "epi_sts_done",
-                         "epi_fence_done"]
+                         "epi_ld_done", "epi_store_issued", "epi_loop_end", "epi_store_drained", "exit", "bar_init_done", "tmem_alloc_done",
+                         "cta_synced"]
                 print("   trace(cycles): " + " ".join(f"{n}={buf[i] - t0}" for i, n in enumerate(names) if buf[i] > 0))
         print(f"{name:20s} M={m:6d} N={n:5d} K={k:6d}  {med * 1e3:8.1f} us  {fl / (med * 1e-3) / 1e12:7.1f} TFLOP/s", flush=True)
 
