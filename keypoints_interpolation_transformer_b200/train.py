@@ -201,7 +201,9 @@ class TrainStep:
     def __call__(self, inputs, sota, mask):
         """use_graph: the whole step (weight refresh, forward, loss, zero grads, backward, Adam -- ~280 kernel launches
         with their programmatic-dependency edges) is captured once per distinct set of input buffers (e.g. the two slots of
-        ``dataloader.DevicePrefetcher``) and replayed; the returned loss is the graph's static 0-dim tensor."""
+        ``dataloader.DevicePrefetcher``) and replayed; the returned loss is the graph's static 0-dim tensor.  With a
+        reducer (data parallelism) the capture is a chain of graphs cut at backward's bucket boundaries and the
+        all-reduces are launched between the replays (``_capture_chain``)."""
         if not self.use_graph:
             return self._eager(inputs, sota, mask)
         key = (inputs.data_ptr(), sota.data_ptr(), mask.data_ptr(), tuple(inputs.shape))
