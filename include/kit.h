@@ -263,6 +263,14 @@ int kit_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, co
                       int64_t ld_dq, void* dk, int64_t ld_dk, void* dv, int64_t ld_dv, float* dq_accum, int32_t B,
                       int32_t NH, int32_t Sq, int32_t Sk, int32_t d, const KitAttnMask* mask, void* stream);
 
+/* Test-only probe of the tensor-core operand layouts: ONE sequence of `steps` tcgen05.mma (M x N x 16, kind::f16, bf16 in,
+ * fp32 accumulate) from two operand tiles the caller lays out byte by byte (a_bytes / b_bytes are copied verbatim to 1024-byte
+ * aligned shared memory; descriptors are built from args), accumulator read back as out[128 lanes][n_cols] fp32 (lanes the
+ * instruction does not write hold -12345).  args_host: 17 int32 on the HOST = {idesc, steps, a_off, a_step, a_lbo, a_sbo,
+ * a_layout, b_off, b_step, b_lbo, b_sbo, b_layout, a_from_tmem, a_tmem_cols, a_tmem_step, d_lane, n_cols}. */
+int kit_umma_probe(const void* a_bytes, int32_t a_len, const void* b_bytes, int32_t b_len, const int32_t* args_host,
+                   float* out, void* stream);
+
 /* Row kernels over [M,H] bf16 (H multiple of 8, <= 1024).  See csrc/rowops.cu. */
 int kit_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* sum_out,
                           void* y, float* mean, float* rstd, int64_t M, int32_t H, void* stream);

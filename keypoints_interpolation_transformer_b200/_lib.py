@@ -92,6 +92,7 @@ _SIGNATURES = {
                                     C.POINTER(KitAttnMask), _P]),
     "kit_attention_bwd": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _I64, _P, _I64, _P, _I64,
                                     _P, _I32, _I32, _I32, _I32, _I32, C.POINTER(KitAttnMask), _P]),
+    "kit_umma_probe": (C.c_int, [_P, _I32, _P, _I32, C.POINTER(_I32), _P, _P]),
     "kit_add_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "kit_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "kit_cast_fp32_to_bf16_padded": (C.c_int, [_P, _I64, _I64, _I64, _P, _I64, _P]),

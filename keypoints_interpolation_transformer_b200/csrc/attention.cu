@@ -1237,6 +1237,12 @@ int attention_fwd(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const 
                   cudaStream_t st) {
   int rc = check_attn(d, ldq, ldk, ldv, ldo);
   if (rc) return rc;
+  {
+    const void* ptrs[4] = {q, k, v, out};
+    const int64_t lds[4] = {ldq, ldk, ldv, ldo};
+    if (attention_t64_supported(NH, Sq, Sk, d, mask, ptrs, lds, 4))
+      return attention_t64_fwd(q, ldq, k, ldk, v, ldv, out, ldo, lse, B, NH, Sq, Sk, mask, st);
+  }
   if (attention_fwd_tc_supported(ldq, ldk, ldv, NH, Sq, Sk, d, mask, q, k, v))
     return attention_fwd_tc(q, ldq, k, ldk, v, ldv, out, ldo, lse, B, NH, Sq, Sk, d, mask, st);
   const MaskDev md = to_dev(mask);
@@ -1254,6 +1260,12 @@ int attention_bwd(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const 
   if (rc) return rc;
   rc = check_attn(d, ld_do, ld_dq, ld_dk, ld_dv);
   if (rc) return rc;
+  {
+    const void* ptrs[7] = {q, k, v, dout, dq, dk, dv};
+    const int64_t lds[7] = {ldq, ldk, ldv, ld_do, ld_dq, ld_dk, ld_dv};
+    if (attention_t64_supported(NH, Sq, Sk, d, mask, ptrs, lds, 7))
+      return attention_t64_bwd(q, ldq, k, ldk, v, ldv, dout, ld_do, lse, dq, ld_dq, dk, ld_dk, dv, ld_dv, B, NH, Sq, Sk, mask, st);
+  }
   const MaskDev md = to_dev(mask);
   switch (d) {
     case 16: return bwd_launch<16>(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq, dk, ld_dk, dv, ld_dv, dq_acc, B, NH, Sq, Sk, md, st);

@@ -61,6 +61,25 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint6
   return KIT_OK;
 }
 
+// [d2][d1][d0] bf16 tensor (d0 contiguous; strides of d1 / d2 in bytes), box (box0, box1, box2), 128B swizzle, out-of-range
+// elements read as zeros: the T <= 64 attention kernels load [2 sequences][64 frames][64 columns] tiles of [B, T, ld] tensors.
+int make_tensor_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                       uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
+  EncodeTiledFn fn = get_encode_fn();
+  KIT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  KIT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (stride1_bytes & 15) == 0 && (stride2_bytes & 15) == 0,
+              "TMA base address and strides must be multiples of 16 bytes");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KIT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+  return KIT_OK;
+}
+
 static int g_num_sms = 0;
 static long long* g_trace_buf = nullptr;
 

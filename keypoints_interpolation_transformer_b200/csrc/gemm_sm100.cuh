@@ -881,6 +881,8 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
 // ---------------------------------------------------------------- host side
 int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_pitch_bytes,
                        uint32_t box_inner, uint32_t box_outer);
+int make_tensor_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                       uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
 // Builds a plan: tensor maps + grid.  split_k <= 0 lets the planner choose (wgrad only).
 // Optional LayerNorm behind a +residual GEMM (EPI_ADD_LN): y = LN(C) * gamma + beta, statistics of the bf16-rounded C.
 struct GemmLN {

@@ -144,9 +144,16 @@ def _mask_bias(fm, flags, Sq, Sk):
     (2, 8, 64, 32, K.MASK_REPEAT_INC, False), (2, 4, 12, 16, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD, False),
     (2, 2, 100, 64, K.MASK_TRIANGLE, False), (1, 4, 256, 32, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD, False),
     (3, 8, 200, 32, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD, False), (2, 8, 512, 64, K.MASK_REPEAT_INC, False),
-    (2, 4, 130, 32, 0, False), (2, 4, 40, 32, 0, True), (2, 4, 150, 32, 0, True)])
+    (2, 4, 130, 32, 0, False), (2, 4, 40, 32, 0, True), (2, 4, 150, 32, 0, True),
+    # attention_t64.cu (tcgen05, S <= 64, d = 32): odd batch, short sequences, every mask kind, the bench shape
+    (5, 8, 40, 32, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD, False), (1, 2, 7, 32, K.MASK_REPEAT_INC, False),
+    (3, 4, 64, 32, K.MASK_TRIANGLE, False), (256, 8, 64, 32, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD, False),
+    (301, 8, 64, 32, 0, False)])
 def test_attention_fwd_bwd(B, NH, S, d, flags, explicit, monkeypatch):
     _attention_case(B, NH, S, d, flags, explicit)
+    if S <= 64 and d == 32 and not explicit:   # short sequences take attention_t64.cu by default: the mma.sync tile kernels too
+        monkeypatch.setenv("KIT_ATTN_T64", "0")
+        _attention_case(B, NH, S, d, flags, explicit)
     if S > 64 and not explicit:          # long sequences take the tcgen05 forward by default: the mma.sync streaming kernel too
         monkeypatch.setenv("KIT_ATTN_TC", "0")
         _attention_case(B, NH, S, d, flags, explicit)
