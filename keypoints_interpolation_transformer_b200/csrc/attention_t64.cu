@@ -56,18 +56,29 @@ __device__ __forceinline__ float a64_ex2(float x) {
   return r;
 }
 // Folded mask terms of the 2 x 64 keys of a sequence pair, warp-private: kb = additive term in base 2 (-inf beyond Sk),
-// kc = the key's index when it is cut for every earlier query (repeat-inc with m[j] = 1, or triangle), else -1.
-__device__ __forceinline__ bool a64_key_terms(const A64Params& p, int pair, float* kb, float* kc, int lane) {
-  bool any_cut = false;
+// kc = the key's index when it is cut for every earlier query (repeat-inc with m[j] = 1, or triangle), else -1.  The frame-mask
+// values of the NEXT unit are requested (a64_load_fm) while the current one is processed and folded at its start.
+__device__ __forceinline__ void a64_load_fm(const A64Params& p, int pair, int lane, float (&fmv)[4]) {
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int idx = lane * 4 + u, s = idx >> 6, j = idx & 63, b = pair * 2 + s;
-    const float fm = (p.frame_mask != nullptr && b < p.B && j < p.Sk) ? __ldg(p.frame_mask + (int64_t)b * p.frame_mask_stride + j) : 0.f;
+    fmv[u] = (p.frame_mask != nullptr && b < p.B && j < p.Sk) ? __ldg(p.frame_mask + (int64_t)b * p.frame_mask_stride + j) : 0.f;
+  }
+}
+__device__ __forceinline__ bool a64_fold_terms(const A64Params& p, const float (&fmv)[4], float* kb, float* kc, int lane) {
+  bool any_cut = false;
+  float b4[4], c4[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int j = (lane * 4 + u) & 63;
+    const float fm = fmv[u];
     const bool cut = ((p.flags & KIT_MASK_REPEAT_INC) && fm == 1.f) || (p.flags & KIT_MASK_TRIANGLE);
-    kb[idx] = (j >= p.Sk) ? -INFINITY : ((p.flags & KIT_MASK_KEYPAD_ADD) ? fm * A64_LOG2E : 0.f);
-    kc[idx] = cut ? (float)j : -1.f;
+    b4[u] = (j >= p.Sk) ? -INFINITY : ((p.flags & KIT_MASK_KEYPAD_ADD) ? fm * A64_LOG2E : 0.f);
+    c4[u] = cut ? (float)j : -1.f;
     any_cut |= cut;
   }
+  *reinterpret_cast<float4*>(kb + lane * 4) = make_float4(b4[0], b4[1], b4[2], b4[3]);
+  *reinterpret_cast<float4*>(kc + lane * 4) = make_float4(c4[0], c4[1], c4[2], c4[3]);
   return __any_sync(0xffffffffu, any_cut);
 }
 
@@ -202,6 +213,32 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_fwd_kernel(const __grid_co
     const uint32_t kb_s = smem_u32(kb) + sq * 256, kc_s = smem_u32(kc) + sq * 256;
     const float qif = (float)qi;
     const uint64_t sc2 = pk2(p.scale2, p.scale2);
+    // The output of unit n (O / l, log-sum-exp) is drained after the softmax of unit n + 1: the P V products complete while
+    // this group works on the next score tile instead of being waited for.
+    struct Pending { int idx, b, h; uint32_t ph; float l, m; } pend = {0, 0, 0, 0, 1.f, 0.f};
+    bool have_pend = false;
+    auto drain = [&]() {
+      mbar_wait(&pv_done[pend.idx], pend.ph);
+      tc_fence_after();
+      uint32_t o[32];
+      tmem_ld32(tmem_base + lane_base + uint32_t(256 + pend.idx * 32), o);
+      tmem_ld_wait();
+      tc_fence_before();
+      if (pend.b < p.B && qi < p.Sq) {
+        const float inv = 1.f / pend.l;
+        bf16* dst = p.out + ((int64_t)pend.b * p.Sq + qi) * p.ldo + pend.h * 32;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float f[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(o[8 * e + t]) * inv;
+          store8(dst + 8 * e, f);
+        }
+        if (p.lse != nullptr) p.lse[((int64_t)pend.b * p.NH + pend.h) * p.Sq + qi] = (pend.m + log2f(pend.l)) * A64_LN2;
+      }
+    };
+    float fmv[4];
+    if ((int)blockIdx.x < p.units) a64_load_fm(p, (int)blockIdx.x / p.packs, lane, fmv);
     int iu = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
       const int sl = iu & 1, idx = sl * 2 + grp;
@@ -209,7 +246,8 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_fwd_kernel(const __grid_co
       const int pair = u / p.packs, hp = u % p.packs;
       const int b = pair * 2 + sq, h = hp * 2 + grp;
       __syncwarp();
-      const bool need_cut = a64_key_terms(p, pair, kb, kc, lane);
+      const bool need_cut = a64_fold_terms(p, fmv, kb, kc, lane);
+      if (u + (int)gridDim.x < p.units) a64_load_fm(p, (u + (int)gridDim.x) / p.packs, lane, fmv);
       __syncwarp();
       mbar_wait(&s_full[idx], ph);
       tc_fence_after();
@@ -261,7 +299,7 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_fwd_kernel(const __grid_co
       float r0, r1, r2, r3, r4, r5, r6, r7;
       up2(rs2[0], r0, r1); up2(rs2[1], r2, r3); up2(rs2[2], r4, r5); up2(rs2[3], r6, r7);
       const float l = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
-      // P buffer idx is free: this group waited for pv_done of the unit that used it last (two units ago) before it went on
+      // P buffer idx was last read by the P V product of two units ago, whose completion this group waited for in drain()
       const uint32_t p_row = smem_u32(s.p[idx]) + prow * 128;
       const uint32_t sw = prow & 7;
 #pragma unroll
@@ -270,26 +308,11 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_fwd_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[idx]);
-      // ---- O / l -> out, log-sum-exp
-      mbar_wait(&pv_done[idx], ph);
-      tc_fence_after();
-      uint32_t o[32];
-      tmem_ld32(tmem_base + lane_base + uint32_t(256 + idx * 32), o);
-      tmem_ld_wait();
-      tc_fence_before();
-      if (b < p.B && qi < p.Sq) {
-        const float inv = 1.f / l;
-        bf16* dst = p.out + ((int64_t)b * p.Sq + qi) * p.ldo + h * 32;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float f[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(o[8 * e + t]) * inv;
-          store8(dst + 8 * e, f);
-        }
-        if (p.lse != nullptr) p.lse[((int64_t)b * p.NH + h) * p.Sq + qi] = (m_ref + log2f(l)) * A64_LN2;
-      }
+      if (have_pend) drain();
+      pend = Pending{idx, b, h, ph, l, m_ref};
+      have_pend = true;
     }
+    if (have_pend) drain();
   }
   tc_fence_before();
   __syncthreads();
@@ -442,15 +465,55 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_bwd_kernel(const __grid_co
     const uint32_t kb_s = smem_u32(kb) + sq * 256, kc_s = smem_u32(kc) + sq * 256;
     const float qif = (float)qi;
     const uint64_t sc2 = pk2(p.scale2, p.scale2);
+    // The gradients of unit n (dQ / dK / dV accumulators) are drained in the middle of unit n + 1 -- after its P / dS values are
+    // computed, before they are written to the shared tiles the products of unit n still read -- so the 24 MMAs of a unit
+    // run under the next unit's exponentials instead of being waited for.
+    struct Pending { int b, h; uint32_t ph; } pend = {0, 0, 0};
+    bool have_pend = false;
+    auto drain_one = [&](uint32_t col, bf16* base, int64_t ld, int n_rows) {
+      uint32_t o[32];
+      tmem_ld32(tmem_base + lane_base + col, o);
+      tmem_ld_wait();
+      if (pend.b < p.B && qi < n_rows) {
+        bf16* dst = base + ((int64_t)pend.b * n_rows + qi) * ld + pend.h * 32;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float f[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(o[8 * e + t]);
+          store8(dst + 8 * e, f);
+        }
+      }
+    };
+    auto drain = [&]() {   // dQ (row = query), dK / dV (row = key) -> global
+      mbar_wait(&grad_full[grp], pend.ph);
+      tc_fence_after();
+      drain_one(uint32_t(256 + grp * 32), p.dq, p.ld_dq, p.Sq);
+      drain_one(uint32_t(320 + grp * 32), p.dk, p.ld_dk, p.Sk);
+      drain_one(uint32_t(384 + grp * 32), p.dv, p.ld_dv, p.Sk);
+      tc_fence_before();
+    };
+    auto load_lse = [&](int u) {
+      const int bb = (u / p.packs) * 2 + sq, hh = (u % p.packs) * 2 + grp;
+      return (bb < p.B && qi < p.Sq) ? __ldg(p.lse_in + ((int64_t)bb * p.NH + hh) * p.Sq + qi) * A64_LOG2E : INFINITY;
+    };
+    float fmv[4], lse_next = INFINITY;
+    if ((int)blockIdx.x < p.units) {
+      a64_load_fm(p, (int)blockIdx.x / p.packs, lane, fmv);
+      lse_next = load_lse((int)blockIdx.x);
+    }
     int iu = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
       const uint32_t ph = iu & 1;
       const int pair = u / p.packs, hp = u % p.packs;
       const int b = pair * 2 + sq, h = hp * 2 + grp;
-      const bool row_ok = b < p.B && qi < p.Sq;
-      const float lse2 = row_ok ? __ldg(p.lse_in + ((int64_t)b * p.NH + h) * p.Sq + qi) * A64_LOG2E : INFINITY;
+      const float lse2 = lse_next;
       __syncwarp();
-      const bool need_cut = a64_key_terms(p, pair, kb, kc, lane);
+      const bool need_cut = a64_fold_terms(p, fmv, kb, kc, lane);
+      if (u + (int)gridDim.x < p.units) {
+        a64_load_fm(p, (u + (int)gridDim.x) / p.packs, lane, fmv);
+        lse_next = load_lse(u + (int)gridDim.x);
+      }
       __syncwarp();
       mbar_wait(&sdp_full[grp], ph);
       tc_fence_after();
@@ -503,6 +566,7 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_bwd_kernel(const __grid_co
         pp[c] = pack_bf16(x[2 * c], x[2 * c + 1]);
         dd[c] = pack_bf16(a0, a1);
       }
+      if (have_pend) drain();   // the previous unit's products have read the P / dS tiles; its accumulators are free after this
       const uint32_t p_row = smem_u32(s.p[grp]) + prow * 128, ds_row = smem_u32(s.ds[grp]) + prow * 128;
       const uint32_t sw = prow & 7;
 #pragma unroll
@@ -514,29 +578,10 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_bwd_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[grp]);
-      // ---- dQ (row = query), dK / dV (row = key) -> global
-      mbar_wait(&grad_full[grp], ph);
-      tc_fence_after();
-      auto drain = [&](uint32_t col, bf16* base, int64_t ld, int n_rows) {
-        uint32_t o[32];
-        tmem_ld32(tmem_base + lane_base + col, o);
-        tmem_ld_wait();
-        if (b < p.B && qi < n_rows) {
-          bf16* dst = base + ((int64_t)b * n_rows + qi) * ld + h * 32;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float f[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(o[8 * e + t]);
-            store8(dst + 8 * e, f);
-          }
-        }
-      };
-      drain(uint32_t(256 + grp * 32), p.dq, p.ld_dq, p.Sq);
-      drain(uint32_t(320 + grp * 32), p.dk, p.ld_dk, p.Sk);
-      drain(uint32_t(384 + grp * 32), p.dv, p.ld_dv, p.Sk);
-      tc_fence_before();
+      pend = Pending{b, h, ph};
+      have_pend = true;
     }
+    if (have_pend) drain();
   }
   tc_fence_before();
   __syncthreads();
