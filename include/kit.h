@@ -12,6 +12,12 @@
  *     a negative code and leaves a message for kit_last_error() (thread local).  Unsupported
  *     shapes are errors: there is no CPU fallback.
  *   - tensors are dense row-major fp32 unless stated; "bf16" = __nv_bfloat16.
+ *
+ * Numerical deviations from the reference (each bounded by a test)
+ *   - GEMM / attention operands are bf16 with fp32 accumulation (north_star: 2e-2 relative on outputs, loss, gradients).
+ *   - GELU: nn.Transformer(activation="gelu") (model.py:87) is the erf form; the kernels evaluate
+ *     0.5 x (1 + tanh(x (c0 + c1 x^2 + c2 x^4))) with coefficients fitted to the erf form: |gelu - gelu_erf| <= 2.6e-5
+ *     absolute, |gelu' - gelu_erf'| <= 1.1e-4 (csrc/common.cuh; tests/test_kernels_gpu.py::test_gelu_matches_erf_form).
  */
 #ifndef KIT_B200_H_
 #define KIT_B200_H_

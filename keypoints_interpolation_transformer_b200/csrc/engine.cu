@@ -912,6 +912,13 @@ extern "C" int kit_engine_create(const KitModelConfig* cfg, int32_t batch, int32
   return KIT_OK;
 }
 extern "C" int kit_engine_destroy(KitEngine* e) {
+  if (e != nullptr) {
+    for (auto& ev : e->ev_pool) {   // profiling events (kit_engine_set_profiling)
+      cudaEventDestroy(ev.first);
+      cudaEventDestroy(ev.second);
+    }
+    e->ev_pool.clear();
+  }
   delete e;
   return KIT_OK;
 }

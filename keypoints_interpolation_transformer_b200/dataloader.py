@@ -117,18 +117,23 @@ class KeypointBatcher:
         return PP.aug_arm(angles)
 
     def batch(self, indices, want_bf16=False):
+        """One batch.  Host policy: per sequence, in the reference's order -- the augmentation draws of
+        ``__getitem__`` (dataloader.py:649-663), then the missing-block draws of ``put_missing_frames`` (:674) -- so a
+        seeded batch consumes the RNG streams exactly like the reference's DataLoader iterating the same indices."""
         idx = torch.as_tensor(indices, device=self.device, dtype=torch.long)
         B = idx.numel()
-        augs = [self._draw_aug() for _ in range(B)]
         if self.device_policy:
+            augs = [self._draw_aug() for _ in range(B)]
             src_t, msk_t = missing.draw_sources_device(B, self.T, self.dataset_name, self._policy_seed,
                                                        offset=self._policy_calls, device=self.device,
                                                        config=missing.DATASET_CONFIG)
             self._policy_calls += 1
         else:
+            augs = []
             src = np.empty((B, self.T), dtype=np.int32)
             msk = np.empty((B, self.T), dtype=np.float32)
             for b in range(B):
+                augs.append(self._draw_aug())
                 src[b], msk[b] = missing.draw_sources(self.T, self.is_random_missing, self.dataset_name, self.rng, self.nprng,
                                                       missing.DATASET_CONFIG)
             src_t, msk_t = torch.from_numpy(src), torch.from_numpy(msk)

@@ -9,7 +9,9 @@ data-parallel all-reduce work on a few large contiguous ranges.
 
 There is no CPU path: ``forward`` requires the module to be on a CUDA device.
 """
+import collections
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -32,25 +34,53 @@ def positional_table(max_len, dim):
     return pe.unsqueeze(0).transpose(0, 1)
 
 
+class _SlotLease:
+    """Marks one engine slot busy between a grad-enabled forward and its backward (or the release of its autograd graph):
+    a second forward of the same shape before that backward gets its own engine instead of overwriting the first one's
+    saved activations (gradient accumulation, ``(l1 + l2).backward()``)."""
+
+    def __init__(self, module, key, slot):
+        self.busy, self.key, self.slot = module._busy_slots, key, slot
+        self.busy.setdefault(key, set()).add(slot)
+
+    def release(self):
+        s = self.busy.get(self.key)
+        if s is not None:
+            s.discard(self.slot)
+
+    def __del__(self):
+        self.release()
+
+
 class _CompleterFn(torch.autograd.Function):
     """Autograd bridge of the compatibility path: one node for the whole model."""
 
     @staticmethod
-    def forward(ctx, module, engine, x_enc, xes, x_dec, xds, enc_mask, dec_mask, zero_masked, out_shape, *params):
+    def forward(ctx, module, engine, lease, x_enc, xes, x_dec, xds, enc_mask, dec_mask, zero_masked, out_shape, *params):
         pred = torch.empty(out_shape, dtype=torch.float32, device=x_enc.device)
         engine.forward(x_enc, xes, x_dec, xds, enc_mask, dec_mask, pred, zero_masked)
-        ctx.module, ctx.engine = module, engine
+        engine._generation = getattr(engine, "_generation", 0) + 1
+        ctx.module, ctx.engine, ctx.lease, ctx.generation = module, engine, lease, engine._generation
         return pred
 
     @staticmethod
     def backward(ctx, dpred):
         module, engine = ctx.module, ctx.engine
+        if engine._generation != ctx.generation:
+            raise K.KitError("KeypointCompleter.backward: the engine that holds this forward's activations has run another "
+                             "forward since (its slot lease was released early); re-run the forward")
         dpred = dpred.contiguous().float()
+        # The engine accumulates into the model's gradient arena, and after attach_flat_grads() every p.grad is a VIEW of that
+        # arena: the arena's content is set aside, this backward's gradients are taken out as a fresh tensor (autograd owns what
+        # we return and adds it to p.grad itself), and the arena is restored -- nothing is wiped, nothing is counted twice.
+        keep = module.flat_grads.clone()
         module.flat_grads.zero_()
         engine.backward(dpred)
-        snap = module.flat_grads.clone()            # autograd owns what we return
+        snap = module.flat_grads.clone()
+        module.flat_grads.copy_(keep)
+        ctx.lease.release()
         grads = tuple(snap[o:o + n].view(s) for (o, n, s) in module._param_slices)
-        return (None,) * 10 + grads
+        return (None,) * 11 + grads
 
 
 class KeypointCompleter(nn.Module):
@@ -67,7 +97,8 @@ class KeypointCompleter(nn.Module):
         self._param_names, self._param_slices, self._buffer_names = [], [], []
         object.__setattr__(self, "flat_params", flat)
         object.__setattr__(self, "flat_grads", None)
-        self._engines = {}
+        self._engines = collections.OrderedDict()   # (batch, seq_len, training, slot) -> StepEngine, least recently used first
+        self._busy_slots = {}                       # (batch, seq_len) -> slots whose forward awaits its backward
         self._dirty = True
         # register the reference's tree of names; tensors are views of the arena
         order = sorted(self.layout.entries.items(), key=lambda kv: kv[1][0])
@@ -137,7 +168,8 @@ class KeypointCompleter(nn.Module):
         for name, off, numel, shape in self._buffer_names:
             parent, _, leaf = name.rpartition(".")
             mods[parent]._buffers[leaf] = flat[off:off + numel].view(shape)
-        self._engines = {}
+        self._engines = collections.OrderedDict()
+        self._busy_slots = {}
         self._dirty = True
 
     def _apply(self, fn, recurse=True):
@@ -155,7 +187,7 @@ class KeypointCompleter(nn.Module):
     def ensure_flat_grads(self):
         if self.flat_grads is None or self.flat_grads.device != self.flat_params.device:
             object.__setattr__(self, "flat_grads", torch.zeros(self.layout.trainable, device=self.flat_params.device))
-            self._engines = {}
+            self._engines = collections.OrderedDict()
         return self.flat_grads
 
     def attach_flat_grads(self):
@@ -166,18 +198,30 @@ class KeypointCompleter(nn.Module):
         return g
 
     # ------------------------------------------------------------------ engines
-    def engine_for(self, batch, seq_len, training, slot=0):
-        """``slot``: independent engines (own workspace) of the same shape, one per concurrent stream of
-        ``train.TrainStep(streams=...)``."""
+    ENGINE_CACHE = int(os.environ.get("KIT_ENGINE_CACHE", "8"))
+
+    def engine_for(self, batch, seq_len, training, slot=0, pin=False):
+        """One engine (activation workspace + kernel plans) per (batch, seq_len, training, slot).  ``slot``: independent
+        engines of the same shape (concurrent streams of ``train.TrainStep(streams=...)``, outstanding autograd forwards).
+        The cache is bounded (``KIT_ENGINE_CACHE`` engines, least recently used evicted first): the reference feeds
+        variable-length videos at batch 1 (A1_train.py:244), and every new length would otherwise keep a workspace forever.
+        ``pin``: never evict (engines a captured CUDA graph points into)."""
         if not self.flat_params.is_cuda:
             raise K.KitError("KeypointCompleter.forward needs a CUDA device: this build has no CPU path")
         key = (batch, seq_len, bool(training), slot)
         eng = self._engines.get(key)
         if eng is None:
             grads = self.ensure_flat_grads() if training else None
-            eng = StepEngine(self.layout, batch, seq_len, self.flat_params, grads, training=training)
+            with torch.cuda.device(self.flat_params.device):
+                eng = StepEngine(self.layout, batch, seq_len, self.flat_params, grads, training=training)
             eng._fresh = False
+            eng._pinned = False
             self._engines[key] = eng
+            self._evict()
+        else:
+            self._engines.move_to_end(key)
+        if pin:
+            eng._pinned = True
         if self.training or self._dirty or not eng._fresh:
             eng.refresh_weights()
             eng._fresh = True
@@ -187,6 +231,20 @@ class KeypointCompleter(nn.Module):
                     if other is not eng:
                         other._fresh = False
         return eng
+
+    def _evict(self):
+        if len(self._engines) <= self.ENGINE_CACHE:
+            return
+        newest = next(reversed(self._engines))
+        for key in list(self._engines):
+            if len(self._engines) <= self.ENGINE_CACHE:
+                break
+            eng = self._engines[key]
+            busy = key[3] in self._busy_slots.get((key[0], key[1]), ())
+            if key == newest or eng._pinned or busy:
+                continue
+            torch.cuda.current_stream(self.flat_params.device).synchronize()   # its kernels may still be running
+            del self._engines[key]
 
     # ------------------------------------------------------------------ forward (model.py:100-170)
     def forward(self, inputs, filled=None, src_pad_mask=None, tgt_pad_mask=None, src_mask=None, tgt_mask=None,
@@ -261,12 +319,16 @@ class KeypointCompleter(nn.Module):
             enc_mask = make_mask(pad, K.MASK_KEYPAD_ADD if pad is not None else 0, sb, sbb, sbh)
             dec_mask = make_mask(tpad, K.MASK_KEYPAD_ADD if tpad is not None else 0, tb, tbb, tbh)
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        eng = self.engine_for(B, T, training=need_grad)
         out_shape = (B, T, K2 // 2, 2)
         if need_grad:
-            pred = _CompleterFn.apply(self, eng, x, T * K2, xf, T * K2, enc_mask, dec_mask, bool(zero_masked), out_shape,
+            busy = self._busy_slots.get((B, T), ())
+            slot = next(i for i in range(len(busy) + 1) if i not in busy)      # the lowest slot with no forward awaiting its backward
+            eng = self.engine_for(B, T, training=True, slot=slot)
+            lease = _SlotLease(self, (B, T), slot)
+            pred = _CompleterFn.apply(self, eng, lease, x, T * K2, xf, T * K2, enc_mask, dec_mask, bool(zero_masked), out_shape,
                                       *self.parameters())
         else:
+            eng = self.engine_for(B, T, training=False)
             pred = torch.empty(out_shape, dtype=torch.float32, device=dev)
             eng.forward(x, T * K2, xf, T * K2, enc_mask, dec_mask, pred, bool(zero_masked))
         return pred[0] if unbatched else pred

@@ -18,6 +18,18 @@ from .euclidean_loss import EuclideanLoss, fused_loss
 from .optim import FlatAdam
 
 
+def fused_criterion_kind(criterion):
+    """The fused-loss kind that computes exactly ``criterion(pred, y)``, or None when the criterion must be called itself."""
+    from .euclidean_loss import EuclideanDistanceLoss, MSELoss
+    if type(criterion) is EuclideanLoss:
+        return "euclid"
+    if type(criterion) is EuclideanDistanceLoss:
+        return "distance"
+    if type(criterion) is MSELoss or (type(criterion) is torch.nn.MSELoss and criterion.reduction == "mean"):
+        return "mse"
+    return None
+
+
 class TrainStep:
     """fwd + loss + bwd + (all-reduce) + Adam for one batch laid out as the dataloader yields it:
     inputs [B,T+1,K,2] (SOS + hold-filled frames), sota [B,T,K,2], mask [B,T+1] (A1_train.py:91-135).
@@ -44,9 +56,18 @@ class TrainStep:
             raise ValueError("use_graph=True needs FlatAdam(capturable=True): the step count must live on the device")
         self._graphs = {}        # (input pointers, shape) -> (CUDAGraph, static loss)
         self._eager_calls = 0
-        self.kind = {"mse": K.LOSS_MSE, "euclid": K.LOSS_EUCLID}[criterion]
+        self.kind = {"mse": K.LOSS_MSE, "euclid": K.LOSS_EUCLID, "distance": K.LOSS_DISTANCE}[criterion]
         self.zero_masked = zero_masked
         self.reducer = reducer
+        if reducer is not None:
+            # gradients are SUMMED over the ranks: Adam applies 1 / world (equal local batches: mean of means = global mean)
+            scale = 1.0 / max(1, reducer.world)
+            cur = getattr(self.optimizer, "grad_scale", None)
+            if cur is None:
+                raise ValueError("TrainStep(reducer=...) needs an optimizer with a grad_scale attribute (optim.FlatAdam)")
+            if cur not in (1.0, scale):
+                raise ValueError(f"optimizer.grad_scale = {cur} but the reducer spans {reducer.world} ranks (expected {scale})")
+            self.optimizer.grad_scale = scale
         self.pred = None
         self.last_launches = 0
 
@@ -88,7 +109,7 @@ class TrainStep:
             lo, hi = s * Bs, (s + 1) * Bs
             side.wait_event(fork)
             with torch.cuda.stream(side):
-                eng = model.engine_for(Bs, T, training=True, slot=s)
+                eng = model.engine_for(Bs, T, training=True, slot=s, pin=self.use_graph)
                 inp, msk = inputs[lo:hi], mask[lo:hi]
                 enc_mask = make_mask(msk[:, :-1], K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD)
                 dec_mask = make_mask(msk[:, 1:], K.MASK_REPEAT_INC)
@@ -118,7 +139,7 @@ class TrainStep:
         assert mask.dtype == torch.float32 and mask.is_contiguous() and sota.is_contiguous()
         if self.streams > 1:
             return self._forward_backward_split(inputs, sota, mask)
-        eng = model.engine_for(B, T, training=True)
+        eng = model.engine_for(B, T, training=True, pin=self.use_graph)   # a captured graph points into its workspace
         grads = model.ensure_flat_grads()
         x_dec = inputs[:, 1:]                                   # A1_train.py:94 -- a pointer offset
         enc_mask = make_mask(mask[:, :-1], K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD)     # x_mask  (A1_train.py:99,117,121)
@@ -279,11 +300,16 @@ def train_epoch(model, dataloader, criterion, optimizer, device):
     ``torch.optim`` optimizer the autograd-compatible module path runs, call for call like A1."""
     model.train()
     losses = []
-    fused = isinstance(optimizer, FlatAdam)
+    # The fused step evaluates the loss inside the engine: only criteria it implements exactly are routed there.  Anything
+    # else (WeightedMSELoss, nn.L1Loss, an MSELoss with a non-default reduction, a user criterion) is called as the reference
+    # calls it -- criterion(pred, y) through the autograd-compatible module path -- whatever the optimizer.
+    kind = fused_criterion_kind(criterion)
+    fused = isinstance(optimizer, FlatAdam) and kind is not None
     step = None
     if fused:
-        kind = "euclid" if isinstance(criterion, EuclideanLoss) else "mse"
         step = TrainStep(model, optimizer, criterion=kind)
+    elif isinstance(optimizer, FlatAdam):
+        model.attach_flat_grads()      # loss.backward() accumulates into views of the arena FlatAdam steps on
     for i, data in enumerate(dataloader):
         inputs, sota, mask = data
         inputs = inputs.to(device).float().contiguous()

@@ -244,6 +244,52 @@ def test_keypoint_batcher_device_policy_feeds_the_step():
     assert torch.equal(inputs[:, 1:].cpu()[~m], raw[~m])                         # untouched frames pass through
 
 
+def test_keypoint_batcher_with_augmentation_follows_the_reference_dispatch():
+    """KeypointBatcher with augmentation ON against LSP_Dataset.__getitem__'s sequence of calls (dataloader.py:649-675) made
+    with the drop-in functions that are themselves pinned to the reference's outputs (test_augmentations_match_reference,
+    test_missing_frames_and_sos_match_reference): same global RNG streams, same per-sequence order (augmentation draws, then
+    the missing-block draws), so a seeded batch equals the reference's DataLoader over the same indices."""
+    import random
+    from keypoints_interpolation_transformer_b200 import augmentation
+    from keypoints_interpolation_transformer_b200 import dataloader as dl
+    Kp, T, N = 21, 40, 12
+    ids = {"pose": list(range(0, 13)), "left_hand": list(range(13, 17)), "rigth_hand": list(range(17, 21))}
+    body = {"pose_chest_middle_up": 0, "pose_left_shoulder": 1, "pose_left_elbow": 2, "pose_left_wrist": 3,
+            "pose_right_shoulder": 4, "pose_right_elbow": 5, "pose_right_wrist": 6, "pose_right_eye": 7}
+    g = torch.Generator().manual_seed(11)
+    raw = torch.rand(N, T, Kp, 2, generator=g) * 0.8 + 0.1
+    raw[torch.rand(N, T, Kp, generator=g) < 0.03] = 0.0
+    bt = dl.KeypointBatcher(raw, ids, body, dataset_name="AUTSL", normalize=False, have_augmentation=True, augmentations_prob=0.5)
+    random.seed(123)
+    np.random.seed(123)
+    inputs, sota, mask = bt.batch(list(range(N)))
+    # the reference's __getitem__ over the same indices with the same global streams
+    random.seed(123)
+    np.random.seed(123)
+    aug = augmentation.augmentation(ids, body)
+    kinds = set()
+    for b in range(N):
+        x = raw[b].clone()
+        if random.random() < 0.5:
+            sel = random.randrange(4)
+            kinds.add(sel)
+            if sel == 0:
+                aug.augment_rotate(x, angle_range=(-15, 15))
+            if sel == 1:
+                aug.augment_shear(x, "perspective", squeeze_ratio=(-0.15, 0.15))
+            if sel == 2:
+                aug.augment_shear(x, "squeeze", squeeze_ratio=(-0.15, 0.15))
+            if sel == 3:
+                aug.augment_arm_joint_rotate(x, 0.5, angle_range=(-15, 15))
+        miss, m = dl.put_missing_frames(x.clone().detach(), False, "AUTSL")
+        miss, m = dl.add_sos(miss, m)
+        assert (sota[b].cpu() - x).abs().max().item() <= 1e-6, b
+        assert torch.equal(mask[b].cpu(), m.cpu()), b                                  # bit exact
+        assert (inputs[b].cpu() - miss.cpu()).abs().max().item() <= 1e-6, b
+        assert torch.equal(sota[b].cpu() == 0, x == 0), b                              # zero pattern exact
+    assert len(kinds) >= 3      # the seed exercises the dispatch
+
+
 def test_cubic_interpolation_kernel(golden_dir):
     """kit_cubic_interpolate (the evaluation's cubic-spline baseline, 3_test_cubic_interpolation.py:32-58) against outputs of
     the reference's own function (extrapolation at both ends, exact zeros as missing, 3- / 2-sample and empty series), the

@@ -116,6 +116,33 @@ def test_gemm_wgrad_accumulates(Kr, M, N, ldc):
         assert torch.equal(c[:, N:], c0[:, N:])      # columns outside N untouched
 
 
+def test_gelu_matches_erf_form():
+    """The kernels' GELU (csrc/common.cuh: 0.5 x (1 + tanh(x (c0 + c1 x^2 + c2 x^4))), MUFU.TANH) against the reference's erf form
+    (nn.Transformer(activation="gelu"), model.py:87), value and derivative, in fp32 through the generic epilogue of the GEMM
+    (A = x, B = identity, so the accumulator is x exactly).  Bound = the fit (2.6e-5 / 1.1e-4, stated in kit.h) + the 2^-11
+    relative error of tanh.approx; the bf16 rounding of every stored activation (2^-9 relative) is 8 x larger."""
+    M, N = 4096, 64
+    x = _bf(torch.linspace(-12.0, 12.0, M * N).view(M, N)).to(DEV)
+    eye = _bf(torch.eye(N)).to(DEV)
+    z = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    out = torch.empty(M, N, device=DEV)
+    K.check(K.lib().kit_gemm_bf16(0, K.ptr(x), N, K.ptr(eye), N, K.ptr(out), N, M, N, N, None, None, 0, K.OUT_F32, K.ACT_GELU,
+                                  K.ptr(z), N, 1, _sp()))
+    xd = x.double()
+    ref = 0.5 * xd * (1 + torch.erf(xd / math.sqrt(2.0)))
+    assert torch.equal(z, x)
+    err = (out.double() - ref).abs()
+    assert (err <= 3e-5 + 2.6e-4 * xd.abs()).all(), float((err - 2.6e-4 * xd.abs()).max())
+    assert float(err[xd.abs() < 0.5].max()) < 1e-4
+    # derivative: out = acc * gelu'(aux) with acc = aux = x
+    K.check(K.lib().kit_gemm_bf16(0, K.ptr(x), N, K.ptr(eye), N, K.ptr(out), N, M, N, N, None, None, 0, K.OUT_F32, K.ACT_GELU_BWD,
+                                  K.ptr(x), N, 1, _sp()))
+    dref = 0.5 * (1 + torch.erf(xd / math.sqrt(2.0))) + xd * torch.exp(-xd * xd / 2) / math.sqrt(2 * math.pi)
+    derr = (out.double() - xd * dref).abs() / xd.abs().clamp_min(1e-3)
+    # the fit contributes 1.1e-4; the rest is tanh.approx's 2^-11 entering through 1 - t^2 (times 0.5 x u'(x) <= ~2.5)
+    assert float(derr.max()) < 3e-3, float(derr.max())
+
+
 # ------------------------------------------------------------------------------- attention
 def _attn_ref(q, k, v, bias):
     d = q.shape[-1]

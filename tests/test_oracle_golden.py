@@ -199,3 +199,30 @@ def test_cubic_interpolation_matches_reference(golden_dir):
         np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-7)
         keep = (g[f"mask{n}"] == 0)[:, None, None] & (g[f"data{n}"] != 0)
         assert np.array_equal(got[keep], g[f"data{n}"][keep])          # samples are kept bit-exactly
+
+
+@pytest.mark.parametrize("name", ["completer_small_k54", "completer_small_k71"])
+def test_torch_reference_matches_reference_goldens(golden_dir, name):
+    """oracle/torch_reference.StockCompleter (the nn.Transformer restatement bench.py times as gpu_baseline / cpu_baseline) loads
+    the reference's state_dict keys and reproduces the reference's own outputs, loss and gradient norms."""
+    from oracle import torch_reference as tr
+    g = _load(golden_dir, name)
+    K, H, L, NH = (int(g[k]) for k in ("K", "H", "L", "NH"))
+    m = tr.StockCompleter(2 * K, H, L, NH)
+    missing, unexpected = m.load_state_dict(ko.deterministic_state_dict(2 * K, H, L), strict=True)
+    assert not missing and not unexpected
+    inputs, gt, mask = (torch.from_numpy(g[k]) for k in ("inputs", "gt", "mask"))
+    x_mask, y_mask = mask[:, :-1], mask[:, 1:]
+    pred = m(inputs[:, :-1], inputs[:, 1:], src_pad_mask=x_mask, src_mask=tr.repeat_inc_masks(x_mask, NH),
+             tgt_mask=tr.repeat_inc_masks(y_mask, NH))
+    ref_pred = torch.from_numpy(g["pred"])
+    assert (pred - ref_pred).abs().max().item() <= 1e-4 * max(1.0, ref_pred.abs().max().item())
+    loss = torch.nn.functional.mse_loss(pred, gt)
+    assert abs(loss.item() - float(g["loss_mse"].mean())) <= 1e-5 * max(1.0, abs(loss.item()))
+    loss.backward()
+    grads = dict(m.named_parameters())
+    for n, ref_norm in zip([str(n) for n in g["grad_names"]], g["grad_norms"]):
+        got = grads[n].grad.norm().item()
+        assert abs(got - ref_norm) <= 2e-4 * max(ref_norm, 1e-3), (n, got, ref_norm)
+    # the one-sequence Python-loop mask of the A1-faithful baseline equals the vectorised one
+    assert torch.equal(tr.get_mask_loop(x_mask[0], x_mask.shape[1]), tr.repeat_inc_masks(x_mask[:1], 1)[0])
