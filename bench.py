@@ -314,13 +314,24 @@ def gpu_run(args, c):
             reducer = parallel.BucketReducer(m.flat_grads, m.layout.buckets)
             dist.broadcast(m.flat_params, src=0)
         # the step is captured once per input slot as a CUDA graph (a chain of graphs under data parallelism) and replayed
-        step = train.TrainStep(m, opt, criterion="mse", reducer=reducer, use_graph=use_graph, streams=args.streams)
+        raw_mode = args.config == "train" and args.streams == 1 and not args.batch_layout
+        if raw_mode:
+            # BASELINE configs[1] from RAW keypoints: the random policy (augmentation + missing blocks, dataloader.py:649-675),
+            # the fused pre-pass (normalize_pose, augmentation, hold-fill, SOS, A1 slices) and the train step, all inside the
+            # timed step (train.RawTrainStep)
+            from keypoints_interpolation_transformer_b200 import preprocess as PP
+            pp = PP.Prepass(KP, dev, list(range(KP)), list(range(29, KP)), 5, 6, 2, [[0, 5, 7, 9], [0, 6, 8, 10]])
+            pol = PP.DevicePolicy("AUTSL", seed=42 + rank, have_augmentation=True, augmentations_prob=0.5, has_arms=True, device=dev)
+            step = train.RawTrainStep(m, pp, pol, opt, criterion="mse", normalize=True, reducer=reducer, use_graph=use_graph)
+        else:
+            step = train.TrainStep(m, opt, criterion="mse", reducer=reducer, use_graph=use_graph, streams=args.streams)
 
         def run(batch):
             return step(*batch)
     else:
         m.eval()
         use_graph = False
+        raw_mode = False
         ev = train.EvalStep(m)
 
         def run(batch):
@@ -334,6 +345,12 @@ def gpu_run(args, c):
         parts = synthetic.synthetic_batch(gen_b, T, KP, seed=42 + 97 * rank + i, smooth=True)
         if gen_b < B:
             parts = tuple(t.repeat((B + gen_b - 1) // gen_b, *([1] * (t.dim() - 1)))[:B].contiguous() for t in parts)
+        if raw_mode:      # the raw keypoints [B,T,K,2]: the synthetic ground truth with a plausible shoulder line / eye height
+            raw = parts[1].clone()
+            raw[:, :, 5, 0] = 0.40 + 0.02 * raw[:, :, 5, 0]
+            raw[:, :, 6, 0] = 0.60 + 0.02 * raw[:, :, 6, 0]
+            raw[:, :, 2, 1] = 0.30 + 0.02 * raw[:, :, 2, 1]
+            parts = (raw.contiguous(),)
         hb = tuple(t.pin_memory() for t in parts)
         host.append(hb)
         devb.append(tuple(t.to(dev, non_blocking=True) for t in hb))
@@ -441,7 +458,12 @@ def gpu_run(args, c):
     value = seqs / (ms * 1e-3)
     e2e = seqs / (ms_e2e * 1e-3)
     cpu = cpu_reference_run(steps=2, warmup=1, c=c, detail=True) if (world == 1 and not args.no_cpu_baseline) else None
-    gpu_base = gpu_baseline_run(m, c, devb[0], dev) if (world == 1 and not args.no_gpu_baseline) else None
+    base_batch = devb[0]
+    if raw_mode:           # the stock module takes the dataloader layout: one batch through the stand-alone pre-pass (untimed)
+        src, miss, aug = pol.draw(B, T)
+        res = pp(devb[0][0], src, miss, normalize=True, aug_dev=aug)
+        base_batch = (res["inputs"], res["y"], res["mask"])
+    gpu_base = gpu_baseline_run(m, c, base_batch, dev) if (world == 1 and not args.no_gpu_baseline) else None
     # ---- HBM roofline of the fused per-frame passes (pre-pass, loss) at BASELINE configs[3] size, measured live
     frame = None
     if world == 1 and not args.no_framepass and args.config == "train":
@@ -472,6 +494,10 @@ def gpu_run(args, c):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(c), "parallelism": f"dp{world}", "global_batch": B * world,
                    "cuda_graph": bool(is_train and step.use_graph), "streams": args.streams,
+                   "step_input": ("raw keypoints [B,T,K,2]: device-drawn policy (augmentation p=0.5 + missing blocks) + fused pre-pass "
+                                  "(normalize_pose, augmentation, hold-fill, SOS, bf16 operands) run INSIDE every timed step "
+                                  "(train.RawTrainStep; dataloader.py:623-686 + A1_train.py:89-135)") if raw_mode
+                   else "dataloader layout (inputs [B,T+1,K,2], sota, mask): pre-processing outside the step",
                    "l2": "no flush needed: each step streams GBs of activations/weights (>> 126 MB L2); a ring of "
                          f"{ring} distinct device-resident batches",
                    "model_flops_per_seq": seq_flops, "model_tflops": seq_flops * value / 1e12,
@@ -568,6 +594,8 @@ def main():
     ap.add_argument("--no-framepass", action="store_true", help="skip the pre-pass / loss HBM roofline leg")
     ap.add_argument("--streams", type=int, default=1, help="concurrent sub-batch chains per step (train.TrainStep streams)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying its CUDA graph")
+    ap.add_argument("--batch-layout", action="store_true",
+                    help="train config: feed pre-processed (inputs, sota, mask) batches instead of raw keypoints (round-1 behaviour)")
     args = ap.parse_args()
     c = dict(CONFIGS[args.config])
     if args.batch:

@@ -134,6 +134,10 @@ int kit_engine_forward(KitEngine* e, const float* x_enc, int64_t x_enc_batch_str
 typedef void (*KitBucketCallback)(int32_t bucket, void* user);
 int kit_engine_backward(KitEngine* e, const float* dpred, KitBucketCallback bucket_done, void* user,
                         void* stream);
+/* The engine's own bf16 operand buffers [B*T, k2p] (k2p = input_size rounded up to 8): kit_prepass can write its x_enc_bf16 /
+ * x_dec_bf16 outputs straight into them, after which kit_engine_forward is called with x_enc = x_dec = NULL ("operands are in
+ * place": no packing pass; zero_masked_enc must then have been applied by the pre-pass). */
+int kit_engine_operands(KitEngine* e, void** x_enc_bf16, void** x_dec_bf16, int32_t* k2p);
 /* Debug/inspection: copy out a named internal activation as fp32 (tests only). */
 int kit_engine_debug_read(KitEngine* e, const char* name, float* out, int64_t out_floats, void* stream);
 /* Number of kernels the last forward / backward call launched (bench.py's gpu_launches). */
@@ -206,6 +210,23 @@ typedef struct KitMissingStats {
 } KitMissingStats;
 int kit_draw_missing(const KitMissingStats* stats, int32_t B, int32_t T, uint64_t seed, uint64_t offset,
                      int32_t* src_index, float* frame_missing, int32_t* blocks, int32_t* n_blocks, void* stream);
+
+/* The whole per-batch random policy of LSP_Dataset.__getitem__ (dataloader.py:649-675) on the device: which augmentation with
+ * which parameters (p = prob, uniform choice of rotate / perspective / squeeze / arm-joint rotate; augmentation.py:132,166-185,
+ * 221-224) and the missing blocks of kit_draw_missing, on Philox streams whose offset is a DEVICE counter (8 bytes, advanced by
+ * the call) -- so a CUDA graph holding the step draws fresh values at every replay.  aug_out [B] KitSeqAug (with aug_policy) feeds
+ * kit_prepass; aug_draws [B,12] doubles (optional, tests): {selected kind or -1, scalar draws 0 / 1, coin, 8 arm angles (NaN =
+ * coin failed)}. */
+typedef struct KitAugPolicy {
+  float prob;      /* augmentations_prob (dataloader.py:649) */
+  float angle_deg; /* 15: rotate and arm-joint angles are U(-angle, angle) degrees (dataloader.py:654,663) */
+  float squeeze;   /* 0.15: shear ratios U(-s, s) (dataloader.py:657,660) */
+  float arm_prob;  /* 0.5 (dataloader.py:663) */
+  int32_t has_arms; /* 0: the skeleton has no arm chains -- selection 3 leaves the sequence unchanged */
+} KitAugPolicy;
+int kit_draw_policy(const KitMissingStats* stats, const KitAugPolicy* aug_policy, int32_t B, int32_t T, uint64_t seed,
+                    uint64_t* counter_dev, int32_t* src_index, float* frame_missing, KitSeqAug* aug_out, double* aug_draws,
+                    void* stream);
 
 /* The cubic-spline baseline of the evaluation (3_test_cubic_interpolation.py:32-58): frames with mask == 1 and every exact 0
  * are missing; each (keypoint, coordinate) series is filled by the not-a-knot cubic spline through its remaining samples

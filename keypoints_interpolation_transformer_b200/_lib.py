@@ -51,6 +51,11 @@ class KitMissingStats(C.Structure):
                 ("samples", C.c_int32)]
 
 
+class KitAugPolicy(C.Structure):
+    _fields_ = [("prob", C.c_float), ("angle_deg", C.c_float), ("squeeze", C.c_float), ("arm_prob", C.c_float),
+                ("has_arms", C.c_int32)]
+
+
 BUCKET_CALLBACK = C.CFUNCTYPE(None, C.c_int32, C.c_void_p)
 
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -81,6 +86,8 @@ _SIGNATURES = {
     "kit_cubic_interpolate": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P]),
     "kit_get_mask": (C.c_int, [_P, _I32, _I32, _P, _P]),
     "kit_draw_missing": (C.c_int, [C.POINTER(KitMissingStats), _I32, _I32, C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P]),
+    "kit_draw_policy": (C.c_int, [C.POINTER(KitMissingStats), C.POINTER(KitAugPolicy), _I32, _I32, C.c_uint64, _P, _P, _P, _P, _P, _P]),
+    "kit_engine_operands": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I32)]),
     "kit_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P]),
     "kit_adam_step_dev": (C.c_int, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _P]),
     "kit_gemm_bf16": (C.c_int, [_I32, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P, _I64, _I32, _I32, _P,

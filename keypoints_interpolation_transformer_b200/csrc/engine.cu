@@ -636,11 +636,13 @@ static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const f
   prof_reset(e);
   e->enc_mask = em ? *em : KitAttnMask{};
   e->dec_mask = dm ? *dm : KitAttnMask{};
-  const float* zm = (zero_masked && em) ? em->frame_mask : nullptr;
-  KIT_REQUIRE(!zero_masked || zm != nullptr, "zero_masked_enc needs enc_mask.frame_mask");
-  e->launches += 2;
-  KIT_TRY(pack_frames(x_enc, xes, B, T, IN, zm, em ? em->frame_mask_stride : 0, e->xe, e->K2p, e->st));
-  KIT_TRY(pack_frames(x_dec, xds, B, T, IN, nullptr, 0, e->xd, e->K2p, e->st));
+  if (x_enc != nullptr) {   // else: the pre-pass wrote the bf16 operands straight into xe / xd (kit_engine_operands)
+    const float* zm = (zero_masked && em) ? em->frame_mask : nullptr;
+    KIT_REQUIRE(!zero_masked || zm != nullptr, "zero_masked_enc needs enc_mask.frame_mask");
+    e->launches += 2;
+    KIT_TRY(pack_frames(x_enc, xes, B, T, IN, zm, em ? em->frame_mask_stride : 0, e->xe, e->K2p, e->st));
+    KIT_TRY(pack_frames(x_dec, xds, B, T, IN, nullptr, 0, e->xd, e->K2p, e->st));
+  }
   // model.py:120-137 (embedding, token norm, PE, SwiGLU) for both branches
   KIT_TRY(eg(e, 0, e->xe, e->K2p, e->wb + L.emb_i.wb, L.emb_i.ld, e->ei_raw, H, (int)M, H, e->K2p, e->params + L.emb_i.b,
              nullptr, 0, OUT_BF16, ACT_NONE, nullptr, 0));
@@ -966,7 +968,7 @@ extern "C" int kit_engine_forward(KitEngine* e, const float* x_enc, int64_t x_en
                                   int32_t zero_masked_enc, float* pred, void* stream) {
   KIT_REQUIRE(e && e->bound, "kit_engine_forward: engine not bound");
   KIT_REQUIRE(e->weights_fresh, "kit_engine_forward: call kit_engine_refresh_weights after binding / updating parameters");
-  KIT_REQUIRE(x_enc && x_dec && pred, "kit_engine_forward: null tensor");
+  KIT_REQUIRE(pred != nullptr && (x_enc == nullptr) == (x_dec == nullptr), "kit_engine_forward: pred is required; x_enc / x_dec are both given or both NULL");
   e->st = (cudaStream_t)stream;
   return engine_forward(e, x_enc, x_enc_batch_stride, x_dec, x_dec_batch_stride, enc_mask, dec_mask, zero_masked_enc, pred);
 }
@@ -978,6 +980,14 @@ extern "C" int kit_engine_backward(KitEngine* e, const float* dpred, KitBucketCa
   KIT_REQUIRE(dpred != nullptr, "kit_engine_backward: dpred is null");
   e->st = (cudaStream_t)stream;
   return engine_backward(e, dpred, bucket_done, user);
+}
+
+extern "C" int kit_engine_operands(KitEngine* e, void** x_enc_bf16, void** x_dec_bf16, int32_t* k2p) {
+  KIT_REQUIRE(e && e->bound, "kit_engine_operands: engine not bound");
+  if (x_enc_bf16) *x_enc_bf16 = e->xe;
+  if (x_dec_bf16) *x_dec_bf16 = e->xd;
+  if (k2p) *k2p = e->K2p;
+  return KIT_OK;
 }
 
 extern "C" int kit_engine_debug_read(KitEngine* e, const char* name, float* out, int64_t out_floats, void* stream) {

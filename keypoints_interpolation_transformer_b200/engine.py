@@ -104,6 +104,13 @@ class StepEngine:
             1 if zero_masked_enc else 0, K.ptr(pred), K.stream_ptr()))
         self.fwd_launches = K.lib().kit_engine_last_launches(self._h)
 
+    def operand_ptrs(self):
+        """(x_enc, x_dec) device pointers of the engine's own bf16 operand buffers [B*T, k2p] and k2p (kit_engine_operands): the
+        pre-pass writes into them and ``forward(None, 0, None, 0, ...)`` skips the packing pass."""
+        xe, xd, k2p = C.c_void_p(), C.c_void_p(), C.c_int32()
+        K.check(K.lib().kit_engine_operands(self._h, C.byref(xe), C.byref(xd), C.byref(k2p)))
+        return xe, xd, k2p.value
+
     def backward(self, dpred, bucket_callback=None):
         cb = K.BUCKET_CALLBACK(lambda b, _u: bucket_callback(b)) if bucket_callback is not None else None
         K.check(K.lib().kit_engine_backward(self._h, K.ptr(dpred), cb, None, K.stream_ptr()))

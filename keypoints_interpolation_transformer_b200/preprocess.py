@@ -61,6 +61,37 @@ def aug_arm(angles):
     return a
 
 
+class DevicePolicy:
+    """The per-batch random policy of ``LSP_Dataset.__getitem__`` (dataloader.py:649-675) drawn ON THE DEVICE (kit_draw_policy):
+    augmentation selection and parameters + missing blocks, Philox streams (seed, device counter) -- the reference's
+    distributions, not its draws; ``dataloader.KeypointBatcher`` keeps the host path in the reference's RNG order."""
+
+    def __init__(self, dataset_name="AUTSL", seed=0, have_augmentation=True, augmentations_prob=0.5, has_arms=True, device="cuda",
+                 config=None):
+        from . import missing
+        cfg = (config or missing.DATASET_CONFIG)[dataset_name]
+        self.stats = K.KitMissingStats(cfg["mean_consecutive_missing"], cfg["std_consecutive_missing"],
+                                       cfg["mean_number_missing_blocks"], cfg["std_number_missing_blocks"], int(cfg["samples"]))
+        self.aug = K.KitAugPolicy(augmentations_prob, 15.0, 0.15, 0.5, 1 if has_arms else 0) if have_augmentation else None
+        self.seed = int(seed)
+        self.device = torch.device(device)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=self.device)      # Philox offset, advanced by every draw
+        self._bufs = {}
+
+    def draw(self, B, T, want_draws=False):
+        """-> (src_index [B,T] int32, frame_missing [B,T] fp32, aug [B * sizeof(KitSeqAug)] uint8 or None[, draws [B,12] fp64])."""
+        key = (B, T)
+        if key not in self._bufs:
+            self._bufs[key] = (torch.empty(B, T, dtype=torch.int32, device=self.device),
+                               torch.empty(B, T, dtype=torch.float32, device=self.device),
+                               torch.empty(B * C.sizeof(K.KitSeqAug), dtype=torch.uint8, device=self.device) if self.aug else None)
+        src, miss, aug = self._bufs[key]
+        draws = torch.empty(B, 12, dtype=torch.float64, device=self.device) if (want_draws and self.aug) else None
+        K.check(K.lib().kit_draw_policy(C.byref(self.stats), C.byref(self.aug) if self.aug else None, B, T, self.seed,
+                                        K.ptr(self.counter), K.ptr(src), K.ptr(miss), K.ptr(aug), K.ptr(draws), K.stream_ptr()))
+        return (src, miss, aug, draws) if want_draws else (src, miss, aug)
+
+
 class Prepass:
     """Static description of the skeleton (which keypoints are body / hands / shoulders / arms)."""
 
@@ -75,9 +106,34 @@ class Prepass:
         self.arm_chains = arm_chains if arm_chains is not None else [[0, 0, 0, 0], [0, 0, 0, 0]]
         self.k2p = (2 * K_points + 7) // 8 * 8
 
+    def _config(self, B, T, normalize, zero_masked_enc, k2p):
+        cfg = K.KitPrepassConfig()
+        cfg.B, cfg.T, cfg.K = B, T, self.K
+        cfg.normalize = 1 if normalize else 0
+        cfg.left_shoulder, cfg.right_shoulder, cfg.right_eye = self.ids
+        cfg.n_body = 0 if self.body is None else self.body.numel()
+        cfg.n_hand = 0 if self.hand is None else self.hand.numel()
+        for c in range(2):
+            for j in range(4):
+                cfg.arm_chain[c * 4 + j] = int(self.arm_chains[c][j])
+        cfg.zero_masked_enc = 1 if zero_masked_enc else 0
+        cfg.k2p = k2p
+        return cfg
+
+    def run(self, raw, src_index, frame_missing, aug_dev, y, mask, x_enc_ptr, x_dec_ptr, k2p, normalize=False, zero_masked_enc=False):
+        """The in-step form: every buffer is the caller's (no allocation), the bf16 operands go to raw device pointers (the
+        engine's own operand buffers), the fp32 ``inputs`` tensor nobody reads is not written.  ``aug_dev``: uint8 tensor
+        holding [B] KitSeqAug records (DevicePolicy.draw) or None."""
+        B, T = raw.shape[0], raw.shape[1]
+        cfg = self._config(B, T, normalize, zero_masked_enc, k2p)
+        K.check(K.lib().kit_prepass(C.byref(cfg), K.ptr(raw), K.ptr(src_index), K.ptr(frame_missing), K.ptr(aug_dev),
+                                    K.ptr(self.body), K.ptr(self.hand), K.ptr(y), None, K.ptr(mask), x_enc_ptr, x_dec_ptr,
+                                    K.stream_ptr()))
+
     def __call__(self, raw, src_index=None, frame_missing=None, augs=None, normalize=False, zero_masked_enc=False,
-                 want_inputs=True, want_bf16=False):
-        """raw [B,T,K,2] fp32 CUDA.  Returns dict(y, inputs, mask, x_enc, x_dec)."""
+                 want_inputs=True, want_bf16=False, aug_dev=None):
+        """raw [B,T,K,2] fp32 CUDA.  Returns dict(y, inputs, mask, x_enc, x_dec).  ``augs``: list of [B] KitSeqAug (host), or
+        ``aug_dev``: the records already on the device (DevicePolicy.draw)."""
         raw = raw.to(self.device).float().contiguous()
         B, T, Kp, _ = raw.shape
         assert Kp == self.K
@@ -98,7 +154,6 @@ class Prepass:
                 cfg.arm_chain[c * 4 + j] = int(self.arm_chains[c][j])
         cfg.zero_masked_enc = 1 if zero_masked_enc else 0
         cfg.k2p = self.k2p if want_bf16 else 0
-        aug_dev = None
         if augs is not None:
             assert len(augs) == B
             arr = (K.KitSeqAug * B)(*augs)

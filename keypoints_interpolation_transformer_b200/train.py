@@ -160,7 +160,7 @@ class TrainStep:
         self.last_launches = eng.fwd_launches + eng.bwd_launches + 3
         return loss
 
-    def _capture_chain(self, inputs, sota, mask):
+    def _capture_chain(self, *batch):
         """Data-parallel capture: [graph | bucket 0 ready | graph | bucket 1 ready | ... | last bucket ready | wait for the
         collectives | graph (Adam)].  The cuts are made from inside ``kit_engine_backward``'s bucket callback -- the capture of the running
         graph ends, a new one begins on the same stream and shares the memory pool -- so each all-reduce is enqueued on
@@ -183,12 +183,12 @@ class TrainStep:
             chain.append(("bucket", b))
             begin()
 
-        side = torch.cuda.Stream(device=inputs.device)
+        side = torch.cuda.Stream(device=batch[0].device)
         side.wait_stream(torch.cuda.current_stream())
         try:
             with torch.cuda.stream(side):
                 begin()
-                loss = self.forward_backward(inputs, sota, mask, _bucket_cb=cut)
+                loss = self.forward_backward(*batch, _bucket_cb=cut)
                 self.optimizer.step()      # backward ends with its last bucket: the graph opened by that cut holds Adam
                 self.last_launches += 2
                 end()
@@ -213,44 +213,45 @@ class TrainStep:
             else:
                 self.reducer.finish()
 
-    def _eager(self, inputs, sota, mask):
-        loss = self.forward_backward(inputs, sota, mask)
+    def _eager(self, *batch):
+        loss = self.forward_backward(*batch)
         self.optimizer.step()                                    # A1_train.py:135
         self.last_launches += 2                                  # adam + weight refresh at next forward
         return loss
 
-    def __call__(self, inputs, sota, mask):
-        """use_graph: the whole step (weight refresh, forward, loss, zero grads, backward, Adam -- ~280 kernel launches
+    def __call__(self, *batch):
+        """``batch`` = (inputs, sota, mask) as the dataloader yields them (``RawTrainStep``: the raw keypoint tensor).
+        use_graph: the whole step (weight refresh, forward, loss, zero grads, backward, Adam -- ~280 kernel launches
         with their programmatic-dependency edges) is captured once per distinct set of input buffers (e.g. the two slots of
         ``dataloader.DevicePrefetcher``) and replayed; the returned loss is the graph's static 0-dim tensor.  With a
         reducer (data parallelism) the capture is a chain of graphs cut at backward's bucket boundaries and the
         all-reduces are launched between the replays (``_capture_chain``)."""
         if not self.use_graph:
-            return self._eager(inputs, sota, mask)
-        key = (inputs.data_ptr(), sota.data_ptr(), mask.data_ptr(), tuple(inputs.shape))
+            return self._eager(*batch)
+        key = tuple(t.data_ptr() for t in batch) + (tuple(batch[0].shape),)
         entry = self._graphs.get(key)
         if entry is None:
             if self._eager_calls < 2 or len(self._graphs) >= 8:   # plans / attributes are set up by eager steps first
                 self._eager_calls += 1
-                return self._eager(inputs, sota, mask)
+                return self._eager(*batch)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             steps_before = self.optimizer.step_count
             try:
                 if self.reducer is not None:
-                    graph, loss = self._capture_chain(inputs, sota, mask)
+                    graph, loss = self._capture_chain(*batch)
                 else:
                     with torch.cuda.graph(graph):
-                        loss = self._eager(inputs, sota, mask)
+                        loss = self._eager(*batch)
             except Exception as exc:   # noqa: BLE001 -- a failed capture must not cost the step: fall back to launches
                 import warnings
                 warnings.warn(f"CUDA-graph capture of the train step failed ({exc!r}); continuing kernel by kernel")
                 self.use_graph = False
                 self.optimizer.step_count = steps_before
                 torch.cuda.synchronize()
-                return self._eager(inputs, sota, mask)
+                return self._eager(*batch)
             self.optimizer.step_count = steps_before              # capture enqueues nothing
-            entry = (graph, loss, (inputs, sota, mask))           # keep the buffers alive
+            entry = (graph, loss, batch)                          # keep the buffers alive
             self._graphs[key] = entry
         self.optimizer.sync_host_values()
         if self.reducer is not None:
@@ -259,6 +260,52 @@ class TrainStep:
             entry[0].replay()
         self.optimizer.step_count += 1
         return entry[1]
+
+
+class RawTrainStep(TrainStep):
+    """The train step FROM RAW KEYPOINTS: what ``LSP_Dataset.__getitem__`` (dataloader.py:623-686) and ``train_epoch``
+    (A1_train.py:89-135) do per sequence, for a whole batch on the device and inside the step -- the random policy
+    (which augmentation with which parameters, which frames go missing: ``preprocess.DevicePolicy`` = kit_draw_policy), the
+    fused pre-pass (normalize_pose, augmentation, hold-fill, SOS, the A1 slices as the engine's bf16 operands, the target
+    ``sota``, the frame mask: kit_prepass writing straight into the engine's operand buffers), forward, loss, backward, Adam.
+    ``step(raw)`` with raw [B,T,K,2] fp32 on the device; with ``use_graph`` the whole sequence replays as one CUDA graph
+    (the policy's Philox offset is a device counter, so every replay draws fresh values)."""
+
+    def __init__(self, model, prepass, policy, optimizer=None, criterion="mse", normalize=True, zero_masked=False, reducer=None,
+                 lr=5e-6, use_graph=False):
+        super().__init__(model, optimizer, criterion=criterion, zero_masked=zero_masked, reducer=reducer, lr=lr, use_graph=use_graph)
+        self.prepass, self.policy, self.normalize = prepass, policy, normalize
+        self.y = self.mask = None
+
+    def forward_backward(self, raw, _bucket_cb=None):
+        model = self.model
+        B, T, Kp = raw.shape[0], raw.shape[1], raw.shape[2]
+        assert raw.is_cuda and raw.dtype == torch.float32 and raw.is_contiguous()
+        eng = model.engine_for(B, T, training=True, pin=self.use_graph)
+        grads = model.ensure_flat_grads()
+        if self.pred is None or self.pred.shape != (B, T, Kp, 2):
+            self.pred = torch.empty(B, T, Kp, 2, device=raw.device)
+            self.y = torch.empty(B, T, Kp, 2, device=raw.device)
+            self.mask = torch.empty(B, T + 1, device=raw.device)
+        src, miss, aug = self.policy.draw(B, T)
+        xe, xd, k2p = eng.operand_ptrs()
+        self.prepass.run(raw, src, miss, aug, self.y, self.mask, xe, xd, k2p, normalize=self.normalize,
+                         zero_masked_enc=self.zero_masked)
+        enc_mask = make_mask(self.mask[:, :-1], K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD)     # x_mask  (A1_train.py:99,117,121)
+        dec_mask = make_mask(self.mask[:, 1:], K.MASK_REPEAT_INC)                          # y_mask  (A1_train.py:100,118)
+        eng.forward(None, 0, None, 0, enc_mask, dec_mask, self.pred, False)               # operands are in place
+        loss, dpred = fused_loss(self.pred, self.y, None, self.kind, want_grad=True)
+        grads.zero_()
+        if _bucket_cb is not None:
+            eng.backward(dpred, _bucket_cb)
+        elif self.reducer is not None:
+            self.reducer.begin()
+            eng.backward(dpred, self.reducer.bucket_ready)
+            self.reducer.finish()
+        else:
+            eng.backward(dpred)
+        self.last_launches = eng.fwd_launches + eng.bwd_launches + 3 + 5      # + policy (3) and pre-pass (2) launches
+        return loss
 
 
 class EvalStep:

@@ -290,6 +290,106 @@ def test_keypoint_batcher_with_augmentation_follows_the_reference_dispatch():
     assert len(kinds) >= 3      # the seed exercises the dispatch
 
 
+def test_device_policy_draws_the_reference_distribution():
+    """kit_draw_policy: the augmentation records written on the device equal what the host path builds from the SAME scalar
+    draws (preprocess.aug_* = augmentation.py:132,166-187,221-224 incl. the float64 homography), the selection frequencies are
+    those of dataloader.py:649-651 (p = 0.5, then uniform over 4), parameters stay in their ranges, the device counter
+    advances by one per call and consecutive calls draw different values."""
+    import math
+    from keypoints_interpolation_transformer_b200 import preprocess as PP
+    B, T = 4096, 64
+    pol = PP.DevicePolicy("AUTSL", seed=11, have_augmentation=True, augmentations_prob=0.5, has_arms=True, device=DEV)
+    src, miss, aug, draws = pol.draw(B, T, want_draws=True)
+    torch.cuda.synchronize()
+    assert int(pol.counter.item()) == 1
+    rec = np.frombuffer(aug.cpu().numpy().tobytes(), dtype=np.dtype(K.KitSeqAug))
+    d = draws.cpu().numpy()
+    sel = d[:, 0].astype(int)
+    freq = [(sel == k).mean() for k in (-1, 0, 1, 2, 3)]
+    assert abs(freq[0] - 0.5) < 0.03 and all(abs(f - 0.125) < 0.02 for f in freq[1:]), freq
+    src_c = np.array(((0, 1), (1, 1), (0, 0), (1, 0)), dtype=np.float32)
+    checked = {0: 0, 1: 0, 2: 0, 3: 0}
+    for b in range(0, B, 7):
+        r, k = rec[b], sel[b]
+        if k == -1:
+            assert r["kind"] == K.AUG_NONE
+            continue
+        if k == 0:
+            assert abs(d[b, 1]) <= math.radians(15) and r["kind"] == K.AUG_ROTATE
+            ref = PP.aug_rotate(d[b, 1])
+            assert abs(r["cos_t"] - ref.cos_t) <= 1e-7 and abs(r["sin_t"] - ref.sin_t) <= 1e-7
+        elif k in (1, 2):
+            assert r["kind"] == K.AUG_SHEAR
+            if k == 1:
+                a = d[b, 1]
+                assert abs(a) <= 0.15
+                dst = (np.array(((0 + a, 1 - a), (1, 1), (0 + a, 0 + a), (1, 0)), dtype=np.float32) if d[b, 3] == 1.0 else
+                       np.array(((0, 1), (1 - a, 1 - a), (0, 0), (1 - a, 0 + a)), dtype=np.float32))
+            else:
+                ml, mr = d[b, 1], d[b, 2]
+                assert abs(ml) <= 0.15 and abs(mr) <= 0.15
+                dst = np.array(((0 + ml, 1), (1 - mr, 1), (0 + ml, 0), (1 - mr, 0)), dtype=np.float32)
+            ref = PP.aug_shear(PP.perspective_matrix(src_c, dst))
+            assert np.allclose(np.array(r["mtx"]), np.array(list(ref.mtx)), rtol=0, atol=1e-12)
+            assert r["zero_x"] == np.float32(ref.zero_x) and r["zero_y"] == np.float32(ref.zero_y)
+        else:
+            assert r["kind"] == K.AUG_ARM_ROTATE
+            ang = [[None if math.isnan(d[b, 4 + c * 4 + j]) else d[b, 4 + c * 4 + j] for j in range(4)] for c in range(2)]
+            ref = PP.aug_arm(ang)
+            assert np.allclose(np.array(r["arm_cos"]), np.array(list(ref.arm_cos)), atol=1e-7)
+            assert np.allclose(np.array(r["arm_sin"]), np.array(list(ref.arm_sin)), atol=1e-7)
+        checked[k] += 1
+    assert all(v > 10 for v in checked.values()), checked
+    arm = d[sel == 3, 4:]
+    assert abs(np.isnan(arm).mean() - 0.5) < 0.05 and np.nanmax(np.abs(arm)) <= math.radians(15)
+    # missing blocks: same kernel as kit_draw_missing (statistics checked in test_device_missing_policy...)
+    m = miss.cpu().numpy()
+    assert set(np.unique(m)) <= {0.0, 1.0} and 0.2 < m.mean() < 0.7 and (src.cpu().numpy() < T).all()
+    src2, miss2, aug2, draws2 = pol.draw(B, T, want_draws=True)
+    torch.cuda.synchronize()
+    assert int(pol.counter.item()) == 2
+    assert not np.array_equal(np.nan_to_num(draws2.cpu().numpy()), np.nan_to_num(d))
+
+
+def test_raw_train_step_equals_prepass_plus_train_step():
+    """train.RawTrainStep (policy + pre-pass writing the engine's bf16 operands + step, A1_train.py:89-135 from raw keypoints)
+    against the same policy draws pushed through the stand-alone pre-pass and the batch-layout TrainStep: same loss and
+    gradients (the operands are the same bf16 roundings of the same fp32 values); and as a CUDA graph every replay draws a
+    fresh policy (device counter)."""
+    from keypoints_interpolation_transformer_b200 import model, optim, train
+    from keypoints_interpolation_transformer_b200 import preprocess as PP
+    Kp, H, L, NH, B, T = 21, 64, 2, 2, 6, 40
+    body, hand = list(range(0, 21)), list(range(13, 21))
+    chains = [[0, 1, 2, 3], [0, 4, 5, 6]]
+    torch.manual_seed(3)
+    m = model.KeypointCompleter(2 * Kp, H, L, NH).to(DEV)
+    m.train()
+    g = torch.Generator().manual_seed(5)
+    raw = (torch.rand(B, T, Kp, 2, generator=g) * 0.8 + 0.1).to(DEV)
+    raw[:, :, 9] = 0.0
+    pp = PP.Prepass(Kp, DEV, body, hand, 1, 4, 7, chains)
+    for zero_masked in (False, True):
+        pol = PP.DevicePolicy("AUTSL", seed=77, device=DEV)
+        step = train.RawTrainStep(m, pp, pol, optim.FlatAdam(m, lr=0.0), criterion="mse", normalize=True, zero_masked=zero_masked)
+        loss = step.forward_backward(raw)
+        torch.cuda.synchronize()
+        got = m.flat_grads.clone()
+        pol.counter.zero_()                                       # the same draws again
+        src, miss, aug = pol.draw(B, T)
+        res = pp(raw, src, miss, normalize=True, aug_dev=aug)
+        ref_step = train.TrainStep(m, optim.FlatAdam(m, lr=0.0), criterion="mse", zero_masked=zero_masked)
+        ref_loss = ref_step.forward_backward(res["inputs"], res["y"], res["mask"])
+        torch.cuda.synchronize()
+        assert torch.equal(step.y, res["y"]) and torch.equal(step.mask, res["mask"])
+        assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+        assert ((got - m.flat_grads).norm() / m.flat_grads.norm()).item() < 1e-3
+    pol = PP.DevicePolicy("AUTSL", seed=5, device=DEV)
+    gstep = train.RawTrainStep(m, pp, pol, optim.FlatAdam(m, lr=1e-4, capturable=True), criterion="mse", use_graph=True)
+    losses = [gstep(raw).item() for _ in range(6)]
+    assert gstep.use_graph and len(gstep._graphs) == 1
+    assert int(pol.counter.item()) == 6 and len(set(round(v, 7) for v in losses[2:])) > 1     # fresh draws at every replay
+
+
 def test_cubic_interpolation_kernel(golden_dir):
     """kit_cubic_interpolate (the evaluation's cubic-spline baseline, 3_test_cubic_interpolation.py:32-58) against outputs of
     the reference's own function (extrapolation at both ends, exact zeros as missing, 3- / 2-sample and empty series), the
