@@ -11,8 +11,14 @@
 //     selected by a +64 byte start address (K-major operands) or as an N = 32 slice (MN-major operands);
 //   * two softmax groups of four warps, one per head of the pack, one thread per (sequence, query) row: tcgen05.ld of the
 //     row's 64 scores, mask terms folded into two floats per key ({bias * log2 e, cut index}: -inf iff (j > i and m[j] = 1),
-//     + m[j] -- model.py:193-202, torch/nn/functional.py:6620), base-2 softmax, P as bf16 into the K-major swizzled layout
-//     the tensor core reads back for O = P V (V = MN-major B operand, N = 32).
+//     + m[j] -- model.py:193-202, torch/nn/functional.py:6620), three-input max (FMNMX3), base-2 softmax, P as bf16 into the
+//     K-major swizzled layout the tensor core reads back for O = P V (V = MN-major B operand, N = 32);
+//   * the MMA warp runs warp-uniform and issues under elect.sync, so operands stay in uniform registers (see a64_elect).
+//
+// What bounds these kernels is the NUMBER of tcgen05.mma instructions: a K = 16 step costs ~50-60 cycles whatever its N up to
+// 64 (tools/umma_rate.py: M = 64, N = 64: 63 cycles; N = 32: 52), and a (pair, head) needs 4 for S and 8 for O (forward), 8 + 24
+// (backward).  (An experiment that let the tensor core ADD the masks -- four more K-steps against a triangular constant and a
+// per-sequence diagonal matrix -- was correct but slower for exactly that reason: 8 more instructions per score tile.)
 //
 // Backward (recomputes P from the saved log-sum-exp):  S = Q K^T, dP = dO V^T  ->  P = 2^(S c + bias - lse),
 // delta = rowsum(P * dP) (= rowsum(dO * O)), dS = P (dP - delta) scale  ->  dV = P^T dO, dK = dS^T Q (P / dS tiles as MN-major
@@ -24,10 +30,11 @@
 namespace kit {
 
 constexpr int A64_TILE = 16384;   // [128 rows x 64 columns] bf16
+constexpr int A64_HALF = 8192;    // [64 rows x 64 columns] bf16
 constexpr float A64_LOG2E = 1.4426950408889634f, A64_LN2 = 0.6931471805599453f;
 
 struct A64Params {
-  int B, NH, Sq, Sk, packs, units;
+  int B, NH, Sq, Sk, packs, packs_shift, units;
   float scale, scale2;
   const float* frame_mask;
   int64_t frame_mask_stride;
@@ -42,6 +49,7 @@ struct A64Params {
   int64_t ld_dk;
   bf16* dv;
   int64_t ld_dv;
+  long long* trace;   // experiments only (KIT_A64_TRACE): clock64 marks of CTA 0, see kit_a64_trace_read
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
@@ -50,10 +58,66 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// Non-blocking probe of an mbarrier phase: mbarrier.try_wait may suspend the thread for a system-dependent time when the phase
+// is not complete -- in a loop that polls TWO queues that stalls the ready one behind the other (a clock trace showed the MMA
+// thread 1.3 k cycles inside try_wait(p_full) while the other head's score product could have been issued).
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// The MMA warp runs its loop with all 32 lanes on warp-uniform values and issues each tcgen05 instruction under an elect.sync
+// predicate: operands then live in uniform registers and consecutive UTCHMMA are back to back.  (Inside `if (lane == 0)` the
+// compiler cannot use the uniform datapath: every operand went through R2UR and an ELECT / BRA.U.ANY loop, ~120 cycles per
+// MMA whatever its shape -- tools/umma_rate.py -- which made the MMA thread the bottleneck of these kernels.)
+__device__ __forceinline__ bool a64_elect() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ bool a64_uniform(bool v) { return __shfl_sync(0xffffffffu, (int)v, 0) != 0; }
+// shared-memory matrix descriptors (128B swizzle, SBO = 1024): K-major (LBO unused) and MN-major (64-element atoms 8192 B apart);
+// a K = 16 step advances the start address by 32 B (K-major: +2 in descriptor units) or 16 rows = 2048 B (MN-major: +128)
+__device__ __forceinline__ uint64_t a64_desc_k(uint32_t addr) {
+  return ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32) | (uint64_t)((addr & 0x3FFFFu) >> 4);
+}
+__device__ __forceinline__ uint64_t a64_desc_mn(uint32_t addr) {
+  return ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32) | (uint64_t)(((addr & 0x3FFFFu) >> 4) | ((8192u >> 4) << 16));
+}
 __device__ __forceinline__ float a64_ex2(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+__device__ __forceinline__ float a64_max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float a64_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float a64_lg2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void a64_unit(const A64Params& p, int u, int& pair, int& hp) {
+  if (p.packs_shift >= 0) {
+    pair = u >> p.packs_shift;
+    hp = u & (p.packs - 1);
+  } else {
+    pair = u / p.packs;
+    hp = u - pair * p.packs;
+  }
 }
 // Folded mask terms of the 2 x 64 keys of a sequence pair, warp-private: kb = additive term in base 2 (-inf beyond Sk),
 // kc = the key's index when it is cut for every earlier query (repeat-inc with m[j] = 1, or triangle), else -1.  The frame-mask
@@ -105,6 +169,10 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_fwd_kernel(const __grid_co
   uint64_t* p_full = &s.bars[12];    // [4] P in shared memory (4 warps)
   uint64_t* pv_done = &s.bars[16];   // [4] O accumulated (tcgen05.commit)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto mark = [&](int slot) {
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && slot < 256) p.trace[slot] = clock64();
+  };
+  if (warp == 0) mark(0);
 
   if (warp == 0) {
     pdl_launch_dependents();
@@ -130,14 +198,19 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_fwd_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = s.tmem_slot;
   // tensor-memory columns: S[idx] at idx * 64, O[idx] at 256 + idx * 32   (idx = slot * 2 + head of the pack)
+  if (warp == 0) mark(1);
   pdl_wait();
+  if (warp == 0) mark(2);
 
   if (warp == 0) {
     if (lane == 0) {
       int iu = 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
-        const int sl = iu & 1, pair = u / p.packs, hp = u % p.packs;
+        const int sl = iu & 1;
+        int pair, hp;
+        a64_unit(p, u, pair, hp);
         mbar_wait(&kv_empty[sl], ((iu >> 1) & 1) ^ 1);
+        mark(8 + iu);
         mbar_arrive_expect_tx(&kv_full[sl], 3 * A64_TILE);
         tma_load_3d(s.q[sl], &tmQ, &kv_full[sl], hp * 64, 0, pair * 2);
         tma_load_3d(s.k[sl], &tmK, &kv_full[sl], hp * 64, 0, pair * 2);
@@ -146,57 +219,59 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_fwd_kernel(const __grid_co
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_bf16(64, 64, false, false);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(64, 32, false, true);
-      const int n_units = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-      const int total = n_units * 2;
-      int qk = 0, pv = 0;
-      uint32_t idle = 0;
-      // two in-order queues (as attention_tc.cu): S(n) needs its score columns drained and the unit's tiles; O(m) needs P(m)
-      while (pv < total) {
-        if (++idle > (1u << 24)) {   // a protocol bug becomes a trap instead of a hang
-          printf("kit: attn64_fwd MMA queue stalled (block %d, qk %d, pv %d)\n", blockIdx.x, qk, pv);
-          __trap();
+    constexpr uint32_t idesc_qk = make_idesc_bf16(64, 64, false, false);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(64, 32, false, true);
+    const bool leader = a64_elect();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int n_units = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = n_units * 2;
+    int qk = 0, pv = 0;
+    uint32_t idle = 0;
+    // two in-order queues (as attention_tc.cu): S(n) needs its score columns drained and the unit's tiles; O(m) needs P(m)
+    while (pv < total) {
+      if (++idle > (1u << 26)) {   // a protocol bug becomes a trap instead of a hang
+        if (leader) printf("kit: attn64_fwd MMA queue stalled (block %d, qk %d, pv %d)\n", blockIdx.x, qk, pv);
+        __trap();
+      }
+      if (qk < total) {
+        const int iu = qk >> 1, g = qk & 1, sl = iu & 1, idx = sl * 2 + g;
+        bool ready = mbar_test(&s_free[idx], ((iu >> 1) & 1) ^ 1);
+        if (ready && g == 0) ready = mbar_test(&kv_full[sl], (iu >> 1) & 1);
+        if (a64_uniform(ready)) {
+          tc_fence_after();
+          const uint64_t q_desc = a64_desc_k(smem_u32(s.q[sl]) + g * 64), k_desc = a64_desc_k(smem_u32(s.k[sl]) + g * 64);
+#pragma unroll
+          for (int sq = 0; sq < 2; ++sq)
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+              if (leader)
+                umma_bf16(tb + (uint32_t(16 * sq) << 16) + uint32_t(idx * 64), q_desc + (sq * A64_HALF + kk * 32) / 16,
+                          k_desc + (sq * A64_HALF + kk * 32) / 16, idesc_qk, kk > 0 ? 1u : 0u);
+          if (leader) umma_commit(&s_full[idx]);
+          mark(32 + qk);
+          ++qk;
+          idle = 0;
         }
-        if (qk < total) {
-          const int iu = qk >> 1, g = qk & 1, sl = iu & 1, idx = sl * 2 + g;
-          bool ready = mbar_try_wait(&s_free[idx], ((iu >> 1) & 1) ^ 1);
-          if (ready && g == 0) ready = mbar_try_wait(&kv_full[sl], (iu >> 1) & 1);
-          if (ready) {
-            tc_fence_after();
-            const uint32_t q_base = smem_u32(s.q[sl]) + g * 64, k_base = smem_u32(s.k[sl]) + g * 64;
+      }
+      if (pv < qk) {
+        const int iu = pv >> 1, g = pv & 1, sl = iu & 1, idx = sl * 2 + g;
+        if (a64_uniform(mbar_test(&p_full[idx], (iu >> 1) & 1))) {
+          tc_fence_after();
+          const uint64_t p_desc = a64_desc_k(smem_u32(s.p[idx])), v_desc = a64_desc_mn(smem_u32(s.v[sl]) + g * 64);
 #pragma unroll
-            for (int sq = 0; sq < 2; ++sq)
+          for (int sq = 0; sq < 2; ++sq)
 #pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const uint64_t adesc = make_smem_desc_sw128(q_base + sq * 8192 + kk * 32, 0, 1024);
-                const uint64_t bdesc = make_smem_desc_sw128(k_base + sq * 8192 + kk * 32, 0, 1024);
-                umma_bf16(tmem_base + (uint32_t(16 * sq) << 16) + uint32_t(idx * 64), adesc, bdesc, idesc_qk, kk > 0 ? 1u : 0u);
-              }
-            umma_commit(&s_full[idx]);
-            ++qk;
-            idle = 0;
-          }
-        }
-        if (pv < qk) {
-          const int iu = pv >> 1, g = pv & 1, sl = iu & 1, idx = sl * 2 + g;
-          if (mbar_try_wait(&p_full[idx], (iu >> 1) & 1)) {
-            tc_fence_after();
-            const uint32_t p_base = smem_u32(s.p[idx]), v_base = smem_u32(s.v[sl]) + g * 64;
-#pragma unroll
-            for (int sq = 0; sq < 2; ++sq)
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {   // 16 keys per MMA
-                const uint64_t adesc = make_smem_desc_sw128(p_base + sq * 8192 + kk * 32, 0, 1024);
-                const uint64_t bdesc = make_smem_desc_sw128(v_base + sq * 8192 + kk * 2048, 8192, 1024);
-                umma_bf16(tmem_base + (uint32_t(16 * sq) << 16) + uint32_t(256 + idx * 32), adesc, bdesc, idesc_pv, kk > 0 ? 1u : 0u);
-              }
+            for (int kk = 0; kk < 4; ++kk)   // 16 keys per MMA
+              if (leader)
+                umma_bf16(tb + (uint32_t(16 * sq) << 16) + uint32_t(256 + idx * 32), p_desc + (sq * A64_HALF + kk * 32) / 16,
+                          v_desc + (sq * A64_HALF + kk * 2048) / 16, idesc_pv, kk > 0 ? 1u : 0u);
+          if (leader) {
             umma_commit(&pv_done[idx]);
             if (g == 1) umma_commit(&kv_empty[sl]);
-            ++pv;
-            idle = 0;
           }
+          mark(48 + pv);
+          ++pv;
+          idle = 0;
         }
       }
     }
@@ -215,7 +290,7 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_fwd_kernel(const __grid_co
     const uint64_t sc2 = pk2(p.scale2, p.scale2);
     // The output of unit n (O / l, log-sum-exp) is drained after the softmax of unit n + 1: the P V products complete while
     // this group works on the next score tile instead of being waited for.
-    struct Pending { int idx, b, h; uint32_t ph; float l, m; } pend = {0, 0, 0, 0, 1.f, 0.f};
+    struct Pending { int idx; uint32_t ph; bf16* dst; float* lse; float l, m; } pend = {0, 0, nullptr, nullptr, 1.f, 0.f};
     bool have_pend = false;
     auto drain = [&]() {
       mbar_wait(&pv_done[pend.idx], pend.ph);
@@ -224,32 +299,45 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_fwd_kernel(const __grid_co
       tmem_ld32(tmem_base + lane_base + uint32_t(256 + pend.idx * 32), o);
       tmem_ld_wait();
       tc_fence_before();
-      if (pend.b < p.B && qi < p.Sq) {
-        const float inv = 1.f / pend.l;
-        bf16* dst = p.out + ((int64_t)pend.b * p.Sq + qi) * p.ldo + pend.h * 32;
+      if (pend.dst != nullptr) {
+        const float inv = a64_rcp(pend.l);
+        const uint64_t inv2 = pk2(inv, inv);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          float f[8];
+          uint32_t w[4];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(o[8 * e + t]) * inv;
-          store8(dst + 8 * e, f);
+          for (int t = 0; t < 4; ++t) {
+            float a, b;
+            up2(mul2(pk2(__uint_as_float(o[8 * e + 2 * t]), __uint_as_float(o[8 * e + 2 * t + 1])), inv2), a, b);
+            w[t] = pack_bf16(a, b);
+          }
+          *reinterpret_cast<uint4*>(pend.dst + 8 * e) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        if (p.lse != nullptr) p.lse[((int64_t)pend.b * p.NH + pend.h) * p.Sq + qi] = (pend.m + log2f(pend.l)) * A64_LN2;
+        if (pend.lse != nullptr) *pend.lse = (pend.m + a64_lg2(pend.l)) * A64_LN2;
       }
     };
     float fmv[4];
-    if ((int)blockIdx.x < p.units) a64_load_fm(p, (int)blockIdx.x / p.packs, lane, fmv);
+    int pair, hp;
+    if ((int)blockIdx.x < p.units) {
+      a64_unit(p, blockIdx.x, pair, hp);
+      a64_load_fm(p, pair, lane, fmv);
+    }
     int iu = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
       const int sl = iu & 1, idx = sl * 2 + grp;
       const uint32_t ph = (iu >> 1) & 1;
-      const int pair = u / p.packs, hp = u % p.packs;
+      a64_unit(p, u, pair, hp);
       const int b = pair * 2 + sq, h = hp * 2 + grp;
       __syncwarp();
       const bool need_cut = a64_fold_terms(p, fmv, kb, kc, lane);
-      if (u + (int)gridDim.x < p.units) a64_load_fm(p, (u + (int)gridDim.x) / p.packs, lane, fmv);
+      if (u + (int)gridDim.x < p.units) {
+        int pn, hn;
+        a64_unit(p, u + gridDim.x, pn, hn);
+        a64_load_fm(p, pn, lane, fmv);
+      }
       __syncwarp();
       mbar_wait(&s_full[idx], ph);
+      if (warp == 2) mark(64 + iu * 8);
       tc_fence_after();
       float x[64];
       uint32_t* xr = reinterpret_cast<uint32_t*>(x);
@@ -260,7 +348,8 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_fwd_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[idx]);
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (warp == 2) mark(65 + iu * 8);
+      // scale + mask terms (base 2)
 #pragma unroll
       for (int c4 = 0; c4 < 16; ++c4) {
         const uint4 kbw = lds128(kb_s + 16 * c4);
@@ -279,11 +368,16 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_fwd_kernel(const __grid_co
           }
           x[c] = v0;
           x[c + 1] = v1;
-          mx4[e] = fmaxf(mx4[e], v0);
-          mx4[e + 1] = fmaxf(mx4[e + 1], v1);
         }
       }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      // row maximum (key 0 is never masked: finite)
+      float mxa = a64_max3(x[0], x[1], x[2]), mxb = a64_max3(x[3], x[4], x[5]);
+#pragma unroll
+      for (int c = 6; c < 62; c += 4) {
+        mxa = a64_max3(mxa, x[c], x[c + 1]);
+        mxb = a64_max3(mxb, x[c + 2], x[c + 3]);
+      }
+      const float mx = a64_max3(fmaxf(mxa, mxb), x[62], x[63]);
       const float m_ref = (mx == -INFINITY) ? 0.f : mx;
       uint64_t rs2[4] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
       const uint64_t nm2 = pk2(-m_ref, -m_ref);
@@ -299,6 +393,7 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_fwd_kernel(const __grid_co
       float r0, r1, r2, r3, r4, r5, r6, r7;
       up2(rs2[0], r0, r1); up2(rs2[1], r2, r3); up2(rs2[2], r4, r5); up2(rs2[3], r6, r7);
       const float l = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+      if (warp == 2) mark(66 + iu * 8);
       // P buffer idx was last read by the P V product of two units ago, whose completion this group waited for in drain()
       const uint32_t p_row = smem_u32(s.p[idx]) + prow * 128;
       const uint32_t sw = prow & 7;
@@ -308,15 +403,22 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_fwd_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[idx]);
+      if (warp == 2) mark(67 + iu * 8);
       if (have_pend) drain();
-      pend = Pending{idx, b, h, ph, l, m_ref};
+      if (warp == 2) mark(68 + iu * 8);
+      const bool ok = b < p.B && qi < p.Sq;
+      pend.idx = idx; pend.ph = ph; pend.l = l; pend.m = m_ref;
+      pend.dst = ok ? p.out + ((int64_t)b * p.Sq + qi) * p.ldo + h * 32 : nullptr;
+      pend.lse = (ok && p.lse != nullptr) ? p.lse + ((int64_t)b * p.NH + h) * p.Sq + qi : nullptr;
       have_pend = true;
     }
     if (have_pend) drain();
+    if (warp == 2) mark(120);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (warp == 0) mark(121);
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -375,7 +477,9 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_bwd_kernel(const __grid_co
     if (lane == 0) {
       int iu = 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
-        const int sl = iu & 1, pair = u / p.packs, hp = u % p.packs;
+        const int sl = iu & 1;
+        int pair, hp;
+        a64_unit(p, u, pair, hp);
         mbar_wait(&t_empty[sl], ((iu >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&t_full[sl], 4 * A64_TILE);
         tma_load_3d(s.q[sl], &tmQ, &t_full[sl], hp * 64, 0, pair * 2);
@@ -386,70 +490,74 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_bwd_kernel(const __grid_co
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_kk = make_idesc_bf16(64, 64, false, false);   // S, dP
-      constexpr uint32_t idesc_mm = make_idesc_bf16(64, 32, true, true);     // dV, dK
-      constexpr uint32_t idesc_km = make_idesc_bf16(64, 32, false, true);    // dQ
-      const int n_units = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-      const int total = n_units * 2;
-      int sd = 0, gr = 0;
-      uint32_t idle = 0;
-      while (gr < total) {
-        if (++idle > (1u << 24)) {
-          printf("kit: attn64_bwd MMA queue stalled (block %d, sd %d, gr %d)\n", blockIdx.x, sd, gr);
-          __trap();
-        }
-        if (sd < total) {
-          const int iu = sd >> 1, g = sd & 1, sl = iu & 1;
-          bool ready = mbar_try_wait(&s_free[g], (iu & 1) ^ 1);
-          if (ready && g == 0) ready = mbar_try_wait(&t_full[sl], (iu >> 1) & 1);
-          if (ready) {
-            tc_fence_after();
-            const uint32_t q_base = smem_u32(s.q[sl]) + g * 64, k_base = smem_u32(s.k[sl]) + g * 64;
-            const uint32_t v_base = smem_u32(s.v[sl]) + g * 64, do_base = smem_u32(s.d_o[sl]) + g * 64;
+    constexpr uint32_t idesc_kk = make_idesc_bf16(64, 64, false, false);   // S, dP
+    constexpr uint32_t idesc_mm = make_idesc_bf16(64, 32, true, true);     // dV, dK
+    constexpr uint32_t idesc_km = make_idesc_bf16(64, 32, false, true);    // dQ
+    const bool leader = a64_elect();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int n_units = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = n_units * 2;
+    int sd = 0, gr = 0;
+    uint32_t idle = 0;
+    while (gr < total) {
+      if (++idle > (1u << 26)) {
+        if (leader) printf("kit: attn64_bwd MMA queue stalled (block %d, sd %d, gr %d)\n", blockIdx.x, sd, gr);
+        __trap();
+      }
+      if (sd < total) {
+        const int iu = sd >> 1, g = sd & 1, sl = iu & 1;
+        bool ready = mbar_test(&s_free[g], (iu & 1) ^ 1);
+        if (ready && g == 0) ready = mbar_test(&t_full[sl], (iu >> 1) & 1);
+        if (a64_uniform(ready)) {
+          tc_fence_after();
+          const uint64_t q_desc = a64_desc_k(smem_u32(s.q[sl]) + g * 64), k_desc = a64_desc_k(smem_u32(s.k[sl]) + g * 64);
+          const uint64_t v_desc = a64_desc_k(smem_u32(s.v[sl]) + g * 64), do_desc = a64_desc_k(smem_u32(s.d_o[sl]) + g * 64);
 #pragma unroll
-            for (int sq = 0; sq < 2; ++sq) {
-              const uint32_t lanes = uint32_t(16 * sq) << 16;
+          for (int sq = 0; sq < 2; ++sq) {
+            const uint32_t lanes = uint32_t(16 * sq) << 16;
 #pragma unroll
-              for (int kk = 0; kk < 2; ++kk)
-                umma_bf16(tmem_base + lanes + uint32_t(g * 64), make_smem_desc_sw128(q_base + sq * 8192 + kk * 32, 0, 1024),
-                          make_smem_desc_sw128(k_base + sq * 8192 + kk * 32, 0, 1024), idesc_kk, kk > 0 ? 1u : 0u);
+            for (int kk = 0; kk < 2; ++kk)
+              if (leader)
+                umma_bf16(tb + lanes + uint32_t(g * 64), q_desc + (sq * A64_HALF + kk * 32) / 16, k_desc + (sq * A64_HALF + kk * 32) / 16,
+                          idesc_kk, kk > 0 ? 1u : 0u);
 #pragma unroll
-              for (int kk = 0; kk < 2; ++kk)
-                umma_bf16(tmem_base + lanes + uint32_t(128 + g * 64), make_smem_desc_sw128(do_base + sq * 8192 + kk * 32, 0, 1024),
-                          make_smem_desc_sw128(v_base + sq * 8192 + kk * 32, 0, 1024), idesc_kk, kk > 0 ? 1u : 0u);
-            }
-            umma_commit(&sdp_full[g]);
-            ++sd;
-            idle = 0;
+            for (int kk = 0; kk < 2; ++kk)
+              if (leader)
+                umma_bf16(tb + lanes + uint32_t(128 + g * 64), do_desc + (sq * A64_HALF + kk * 32) / 16,
+                          v_desc + (sq * A64_HALF + kk * 32) / 16, idesc_kk, kk > 0 ? 1u : 0u);
           }
+          if (leader) umma_commit(&sdp_full[g]);
+          ++sd;
+          idle = 0;
         }
-        if (gr < sd) {
-          const int iu = gr >> 1, g = gr & 1, sl = iu & 1;
-          if (mbar_try_wait(&p_full[g], iu & 1)) {
-            tc_fence_after();
-            const uint32_t p_base = smem_u32(s.p[g]), ds_base = smem_u32(s.ds[g]);
-            const uint32_t q_base = smem_u32(s.q[sl]) + g * 64, k_base = smem_u32(s.k[sl]) + g * 64;
-            const uint32_t do_base = smem_u32(s.d_o[sl]) + g * 64;
+      }
+      if (gr < sd) {
+        const int iu = gr >> 1, g = gr & 1, sl = iu & 1;
+        if (a64_uniform(mbar_test(&p_full[g], iu & 1))) {
+          tc_fence_after();
+          const uint64_t pm_desc = a64_desc_mn(smem_u32(s.p[g])), dsm_desc = a64_desc_mn(smem_u32(s.ds[g])), dsk_desc = a64_desc_k(smem_u32(s.ds[g]));
+          const uint64_t q_desc = a64_desc_mn(smem_u32(s.q[sl]) + g * 64), k_desc = a64_desc_mn(smem_u32(s.k[sl]) + g * 64);
+          const uint64_t do_desc = a64_desc_mn(smem_u32(s.d_o[sl]) + g * 64);
 #pragma unroll
-            for (int sq = 0; sq < 2; ++sq) {
-              const uint32_t lanes = uint32_t(16 * sq) << 16;
+          for (int sq = 0; sq < 2; ++sq) {
+            const uint32_t lanes = uint32_t(16 * sq) << 16;
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {   // 16 queries (dV, dK) / 16 keys (dQ) per MMA
-                const uint32_t roff = sq * 8192 + kk * 2048;
-                umma_bf16(tmem_base + lanes + uint32_t(384 + g * 32), make_smem_desc_sw128(p_base + roff, 8192, 1024),
-                          make_smem_desc_sw128(do_base + roff, 8192, 1024), idesc_mm, kk > 0 ? 1u : 0u);
-                umma_bf16(tmem_base + lanes + uint32_t(320 + g * 32), make_smem_desc_sw128(ds_base + roff, 8192, 1024),
-                          make_smem_desc_sw128(q_base + roff, 8192, 1024), idesc_mm, kk > 0 ? 1u : 0u);
-                umma_bf16(tmem_base + lanes + uint32_t(256 + g * 32), make_smem_desc_sw128(ds_base + sq * 8192 + kk * 32, 0, 1024),
-                          make_smem_desc_sw128(k_base + roff, 8192, 1024), idesc_km, kk > 0 ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk) {   // 16 queries (dV, dK) / 16 keys (dQ) per MMA
+              const uint32_t roff = (sq * A64_HALF + kk * 2048) / 16;
+              if (leader) {
+                umma_bf16(tb + lanes + uint32_t(384 + g * 32), pm_desc + roff, do_desc + roff, idesc_mm, kk > 0 ? 1u : 0u);
+                umma_bf16(tb + lanes + uint32_t(320 + g * 32), dsm_desc + roff, q_desc + roff, idesc_mm, kk > 0 ? 1u : 0u);
+                umma_bf16(tb + lanes + uint32_t(256 + g * 32), dsk_desc + (sq * A64_HALF + kk * 32) / 16, k_desc + roff, idesc_km,
+                          kk > 0 ? 1u : 0u);
               }
             }
+          }
+          if (leader) {
             umma_commit(&grad_full[g]);
             if (g == 1) umma_commit(&t_empty[sl]);
-            ++gr;
-            idle = 0;
           }
+          ++gr;
+          idle = 0;
         }
       }
     }
@@ -468,50 +576,53 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_bwd_kernel(const __grid_co
     // The gradients of unit n (dQ / dK / dV accumulators) are drained in the middle of unit n + 1 -- after its P / dS values are
     // computed, before they are written to the shared tiles the products of unit n still read -- so the 24 MMAs of a unit
     // run under the next unit's exponentials instead of being waited for.
-    struct Pending { int b, h; uint32_t ph; } pend = {0, 0, 0};
+    struct Pending { uint32_t ph; bf16 *dq, *dk, *dv; } pend = {0, nullptr, nullptr, nullptr};
     bool have_pend = false;
-    auto drain_one = [&](uint32_t col, bf16* base, int64_t ld, int n_rows) {
+    auto drain_one = [&](uint32_t col, bf16* dst) {
       uint32_t o[32];
       tmem_ld32(tmem_base + lane_base + col, o);
       tmem_ld_wait();
-      if (pend.b < p.B && qi < n_rows) {
-        bf16* dst = base + ((int64_t)pend.b * n_rows + qi) * ld + pend.h * 32;
+      if (dst != nullptr) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float f[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(o[8 * e + t]);
-          store8(dst + 8 * e, f);
-        }
+        for (int e = 0; e < 4; ++e)
+          *reinterpret_cast<uint4*>(dst + 8 * e) =
+              make_uint4(pack_bf16(__uint_as_float(o[8 * e]), __uint_as_float(o[8 * e + 1])), pack_bf16(__uint_as_float(o[8 * e + 2]), __uint_as_float(o[8 * e + 3])),
+                         pack_bf16(__uint_as_float(o[8 * e + 4]), __uint_as_float(o[8 * e + 5])), pack_bf16(__uint_as_float(o[8 * e + 6]), __uint_as_float(o[8 * e + 7])));
       }
     };
     auto drain = [&]() {   // dQ (row = query), dK / dV (row = key) -> global
       mbar_wait(&grad_full[grp], pend.ph);
       tc_fence_after();
-      drain_one(uint32_t(256 + grp * 32), p.dq, p.ld_dq, p.Sq);
-      drain_one(uint32_t(320 + grp * 32), p.dk, p.ld_dk, p.Sk);
-      drain_one(uint32_t(384 + grp * 32), p.dv, p.ld_dv, p.Sk);
+      drain_one(uint32_t(256 + grp * 32), pend.dq);
+      drain_one(uint32_t(320 + grp * 32), pend.dk);
+      drain_one(uint32_t(384 + grp * 32), pend.dv);
       tc_fence_before();
     };
     auto load_lse = [&](int u) {
-      const int bb = (u / p.packs) * 2 + sq, hh = (u % p.packs) * 2 + grp;
-      return (bb < p.B && qi < p.Sq) ? __ldg(p.lse_in + ((int64_t)bb * p.NH + hh) * p.Sq + qi) * A64_LOG2E : INFINITY;
+      int pr, hh;
+      a64_unit(p, u, pr, hh);
+      const int bb = pr * 2 + sq;
+      return (bb < p.B && qi < p.Sq) ? __ldg(p.lse_in + ((int64_t)bb * p.NH + hh * 2 + grp) * p.Sq + qi) * A64_LOG2E : INFINITY;
     };
     float fmv[4], lse_next = INFINITY;
+    int pair, hp;
     if ((int)blockIdx.x < p.units) {
-      a64_load_fm(p, (int)blockIdx.x / p.packs, lane, fmv);
+      a64_unit(p, blockIdx.x, pair, hp);
+      a64_load_fm(p, pair, lane, fmv);
       lse_next = load_lse((int)blockIdx.x);
     }
     int iu = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++iu) {
       const uint32_t ph = iu & 1;
-      const int pair = u / p.packs, hp = u % p.packs;
+      a64_unit(p, u, pair, hp);
       const int b = pair * 2 + sq, h = hp * 2 + grp;
       const float lse2 = lse_next;
       __syncwarp();
       const bool need_cut = a64_fold_terms(p, fmv, kb, kc, lane);
       if (u + (int)gridDim.x < p.units) {
-        a64_load_fm(p, (u + (int)gridDim.x) / p.packs, lane, fmv);
+        int pn, hn;
+        a64_unit(p, u + gridDim.x, pn, hn);
+        a64_load_fm(p, pn, lane, fmv);
         lse_next = load_lse(u + (int)gridDim.x);
       }
       __syncwarp();
@@ -578,7 +689,11 @@ __global__ void __launch_bounds__(64 + 256, 1) attn64_bwd_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[grp]);
-      pend = Pending{b, h, ph};
+      const bool okq = b < p.B && qi < p.Sq, okk = b < p.B && qi < p.Sk;
+      pend.ph = ph;
+      pend.dq = okq ? p.dq + ((int64_t)b * p.Sq + qi) * p.ld_dq + h * 32 : nullptr;
+      pend.dk = okk ? p.dk + ((int64_t)b * p.Sk + qi) * p.ld_dk + h * 32 : nullptr;
+      pend.dv = okk ? p.dv + ((int64_t)b * p.Sk + qi) * p.ld_dv + h * 32 : nullptr;
       have_pend = true;
     }
     if (have_pend) drain();
@@ -599,6 +714,16 @@ bool attention_t64_supported(int NH, int Sq, int Sk, int d, const KitAttnMask* m
   return true;
 }
 
+static long long* g_a64_trace = nullptr;
+static long long* a64_trace_buf() {
+  const char* e = getenv("KIT_A64_TRACE");
+  if (e == nullptr || e[0] != '1') return nullptr;
+  if (g_a64_trace == nullptr) {
+    cudaMalloc(&g_a64_trace, 256 * sizeof(long long));
+    cudaMemset(g_a64_trace, 0, 256 * sizeof(long long));
+  }
+  return g_a64_trace;
+}
 static int a64_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -615,6 +740,9 @@ static void a64_params(A64Params& p, int B, int NH, int Sq, int Sk, const KitAtt
   p = A64Params{};
   p.B = B; p.NH = NH; p.Sq = Sq; p.Sk = Sk;
   p.packs = NH / 2;
+  p.packs_shift = -1;
+  for (int sh = 0; sh < 16; ++sh)
+    if ((1 << sh) == p.packs) p.packs_shift = sh;
   p.units = ((B + 1) / 2) * p.packs;
   p.scale = rsqrtf(32.f);
   p.scale2 = p.scale * A64_LOG2E;
@@ -655,6 +783,7 @@ int attention_t64_fwd(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, co
   A64Params p;
   a64_params(p, B, NH, Sq, Sk, mask);
   p.out = out; p.ldo = ldo; p.lse = lse;
+  p.trace = a64_trace_buf();
   return a64_launch(attn64_fwd_kernel, p.units, smem, st, tmQ, tmK, tmV, p);
 }
 
@@ -681,3 +810,11 @@ int attention_t64_bwd(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, co
 }
 
 }  // namespace kit
+
+// experiments: the clock64 marks of CTA 0 of the last attn64_fwd_kernel launch (KIT_A64_TRACE=1), 256 values
+extern "C" int kit_a64_trace_read(long long* out_host) {
+  if (kit::g_a64_trace == nullptr) return KIT_ERR_INVALID;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out_host, kit::g_a64_trace, 256 * sizeof(long long), cudaMemcpyDeviceToHost);
+  return KIT_OK;
+}

@@ -121,9 +121,69 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const uint8_t* __res
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// Issue rate of tcgen05.mma for a given shape: `reps` back-to-back instructions on zero-filled operand tiles by one thread,
+// clock64 from before the first issue to the completion of the commit.  out[0] = cycles until the last issue returned,
+// out[1] = cycles until all had completed.
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(uint32_t idesc, int reps, int a_mn, int b_mn, int a_tmem, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * PROBE_TILE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x * 16; i < 2 * PROBE_TILE_BYTES; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if ((threadIdx.x >> 5) == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x < 32) {   // warp-uniform loop, each instruction under elect.sync: operands stay in uniform registers
+    uint32_t el;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
+    const bool leader = el != 0;
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + PROBE_TILE_BYTES);
+    const uint64_t hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+    const uint64_t ad0 = hi | (uint64_t)(((a_base & 0x3FFFFu) >> 4) | (a_mn ? ((8192u >> 4) << 16) : 0u));
+    const uint64_t bd0 = hi | (uint64_t)(((b_base & 0x3FFFFu) >> 4) | (b_mn ? ((8192u >> 4) << 16) : 0u));
+    const uint32_t da = a_mn ? 128u : 2u, db = b_mn ? 128u : 2u;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; r += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (leader) {
+          if (a_tmem) umma_bf16_ts(tb, tb + 256 + k * 8, bd0 + k * db, idesc, (r + k) > 0 ? 1u : 0u);
+          else umma_bf16(tb, ad0 + k * da, bd0 + k * db, idesc, (r + k) > 0 ? 1u : 0u);
+        }
+      }
+    }
+    const long long t1 = clock64();
+    if (leader) umma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t2 = clock64();
+    if (leader) {
+      out[0] = t1 - t0;
+      out[1] = t2 - t0;
+    }
+  }
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 1) tmem_dealloc<512>(tmem_base);
+}
+
 }  // namespace kit
 
 using namespace kit;
+
+extern "C" int kit_umma_rate(uint32_t idesc, int32_t reps, int32_t a_mn, int32_t b_mn, int32_t a_tmem, long long* out_dev, void* stream) {
+  const int smem = 2 * PROBE_TILE_BYTES + 1024 + 64;
+  KIT_CHECK_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_rate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(idesc, reps, a_mn, b_mn, a_tmem, out_dev);
+  KIT_LAUNCH_CHECK();
+  return KIT_OK;
+}
 
 // args: the 17 int32 fields of ProbeArgs in declaration order (idesc first, as its bit pattern).
 extern "C" int kit_umma_probe(const void* a_bytes, int32_t a_len, const void* b_bytes, int32_t b_len, const int32_t* args_host,

@@ -81,8 +81,20 @@ def measure(shapes=((4096, 256, 71), (256, 64, 71)), peak=None, dev="cuda"):
                                           KL.stream_ptr()))
         ms = timeit(run_pre, flush=flush)
         by = B * (T * K * 8 + T * K * 8 + (T + 1) * K * 8 + (T + 1) * 4 + 2 * T * pp.k2p * 2 + T * 8)
-        out.append({"kernel": "prepass_kernel", "B": B, "T": T, "K": K, "ms": ms, "algorithmic_bytes": by,
-                    "GBps": by / ms / 1e6, "frac_of_measured_hbm": by / ms / 1e6 / peak})
+        out.append({"kernel": "prepass_kernel (stand-alone: y + fp32 inputs + mask + both bf16 operands)", "B": B, "T": T, "K": K, "ms": ms,
+                    "algorithmic_bytes": by, "GBps": by / ms / 1e6, "frac_of_measured_hbm": by / ms / 1e6 / peak})
+
+        # the in-step form (train.RawTrainStep): the fp32 `inputs` tensor nobody reads is not written; fraction on SURVEY.md
+        # 8(d)'s algorithmic bytes: read (T+1) K 8 + (T+1) 4, write 2 T K 8  (= 437 820 B per sequence at T = 256, K = 71)
+        def run_pre_step():
+            KL.check(KL.lib().kit_prepass(C.byref(cfg), KL.ptr(raw), KL.ptr(src_d), KL.ptr(msk_d), KL.ptr(aug_dev), KL.ptr(pp.body),
+                                          KL.ptr(pp.hand), KL.ptr(y), None, KL.ptr(mask), KL.ptr(xe), KL.ptr(xd), KL.stream_ptr()))
+        ms = timeit(run_pre_step, flush=flush)
+        by = B * ((T + 1) * K * 8 + (T + 1) * 4 + 2 * T * K * 8)
+        traffic = B * (T * K * 8 + T * K * 8 + (T + 1) * 4 + 2 * T * pp.k2p * 2 + T * 8)
+        out.append({"kernel": "prepass_kernel (in-step: y + mask + bf16 operands)", "B": B, "T": T, "K": K, "ms": ms,
+                    "algorithmic_bytes": by, "GBps": by / ms / 1e6, "frac_of_measured_hbm": by / ms / 1e6 / peak,
+                    "bytes_actually_moved": traffic, "bytes_definition": "SURVEY.md 8(d): read (T+1)K8 + (T+1)4, write 2TK8 per sequence"})
         pred = torch.rand(B, T, K, 2, device=dev)
 
         def run_loss():
