@@ -214,9 +214,17 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA)
-    if (lane == 0 && rank == 0) {
+    // The whole warp runs the loop on warp-uniform values and every tcgen05 instruction is issued under an elect.sync
+    // predicate: descriptors and addresses then stay in uniform registers and consecutive UTCHMMA are back to back.  Inside
+    // `if (lane == 0)` each operand went through R2UR and an ELECT / BRA.U.ANY loop (~120 cycles per MMA, tools/umma_rate.py)
+    // -- more than an N = 128 instruction takes on the tensor pipe.
+    if (__shfl_sync(0xffffffffu, rank, 0) == 0) {
       constexpr uint32_t idesc1 = make_idesc_bf16(256, FFN_FC, false, false);
       constexpr uint32_t idesc2 = make_idesc_bf16(256, FFN_H, false, false);
+      uint32_t el;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
+      const bool leader = el != 0;
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t x_base = smem_u32(x_s), h_base = smem_u32(h_s), ring_base = smem_u32(ring);
       uint32_t cnt = 0, gc = 0, hc = 0, it = 0;
       auto slot_wait = [&](uint32_t& s) {
@@ -241,11 +249,11 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
           for (int k = 0; k < 4; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(h_base + j * 16384 + k * 32, 0, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(ring_base + s * FFN_SLOT + k * 32, 0, 1024);
-            umma_bf16_cg2(tmem_base + 256, adesc, bdesc, idesc2, (c > 0 || j > 0 || k > 0) ? 1u : 0u);
+            if (leader) umma_bf16_cg2(tb + 256, adesc, bdesc, idesc2, (c > 0 || j > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit_cg2(&ring_empty[s], (uint16_t)3);
+          if (leader) umma_commit_cg2(&ring_empty[s], (uint16_t)3);
         }
-        umma_commit_cg2(h_empty, (uint16_t)3);
+        if (leader) umma_commit_cg2(h_empty, (uint16_t)3);
         ++hc;
       };
       for (int item = first_item; item < p.n_items; item += item_stride, ++it) {
@@ -267,16 +275,16 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
               for (int k = 0; k < 4; ++k) {
                 const uint64_t adesc = make_smem_desc_sw128(x_base + kb * 16384 + k * 32, 0, 1024);
                 const uint64_t bdesc = make_smem_desc_sw128(ring_base + s * FFN_SLOT + kk * 8192 + k * 32, 0, 1024);
-                umma_bf16_cg2(tmem_base + b * FFN_FC, adesc, bdesc, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+                if (leader) umma_bf16_cg2(tb + b * FFN_FC, adesc, bdesc, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
               }
             }
-            umma_commit_cg2(&ring_empty[s], (uint16_t)3);
+            if (leader) umma_commit_cg2(&ring_empty[s], (uint16_t)3);
           }
-          umma_commit_cg2(&acc1_full[b], (uint16_t)3);
+          if (leader) umma_commit_cg2(&acc1_full[b], (uint16_t)3);
           if (c >= 1) gemm2(c - 1);
         }
         gemm2(NC - 1);
-        umma_commit_cg2(acc2_full, (uint16_t)3);
+        if (leader) umma_commit_cg2(acc2_full, (uint16_t)3);
       }
     }
     __syncwarp();

@@ -548,7 +548,11 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (__shfl_sync(0xffffffffu, rank, 0) == 0) {
+      uint32_t el_;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el_));
+      const bool leader = el_ != 0;   // warp-uniform loop, tcgen05 instructions under elect.sync: operands stay in uniform registers
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       constexpr uint32_t idesc = make_idesc_bf16(BM * CL, BN, MODE == 1, MODE == 1);
       uint32_t cnt = 0, it = 0;
       for (int item = first_item; item < n_items; item += item_stride, ++it) {
@@ -558,7 +562,7 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
         const uint32_t as = BG ? 0 : (it & 1), aph = BG ? (it & 1) : ((it >> 1) & 1);
         mbar_wait(&tmem_empty[as], aph ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
+        const uint32_t tmem_d = tb + as * BN;
         const bool first_n = BG && ((item - split * tiles_mn) / groups_m) == 0 && p.bias_grad != nullptr;
         for (int kb = kb_begin; kb < kb_end; ++kb, ++cnt) {
           const int s = cnt % STAGES;
@@ -578,18 +582,26 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
               adesc = make_smem_desc_sw128(a_base + k * 16 * 128, BK * 128, 1024);
               bdesc = make_smem_desc_sw128(b_base + k * 16 * 128, BK * 128, 1024);
             }
-            if (CL == 1) umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
-            else umma_bf16_cg2(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            if (leader) {
+              if (CL == 1) umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+              else umma_bf16_cg2(tmem_d, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            }
             if (BG && first_n) {   // row sums of A^T: same A tile against all-ones, 16 columns at tmem column BN
               constexpr uint32_t idesc_ones = make_idesc_bf16(BM * CL, 16, true, true);
               const uint64_t odesc = make_smem_desc_sw128(smem_u32(ones_tile), 0, 0);
-              if (CL == 1) umma_bf16(tmem_base + BN, adesc, odesc, idesc_ones, (kb > kb_begin || k > 0) ? 1u : 0u);
-              else umma_bf16_cg2(tmem_base + BN, adesc, odesc, idesc_ones, (kb > kb_begin || k > 0) ? 1u : 0u);
+              if (leader) {
+                if (CL == 1) umma_bf16(tb + BN, adesc, odesc, idesc_ones, (kb > kb_begin || k > 0) ? 1u : 0u);
+                else umma_bf16_cg2(tb + BN, adesc, odesc, idesc_ones, (kb > kb_begin || k > 0) ? 1u : 0u);
+              }
             }
           }
-          if (CL == 1) umma_commit(&empty[s]); else umma_commit_cg2(&empty[s], (uint16_t)3);   // slot free in both CTAs
+          if (leader) {
+            if (CL == 1) umma_commit(&empty[s]); else umma_commit_cg2(&empty[s], (uint16_t)3);   // slot free in both CTAs
+          }
         }
-        if (CL == 1) umma_commit(&tmem_full[as]); else umma_commit_cg2(&tmem_full[as], (uint16_t)3);
+        if (leader) {
+          if (CL == 1) umma_commit(&tmem_full[as]); else umma_commit_cg2(&tmem_full[as], (uint16_t)3);
+        }
         if (it == 0) mark(5);
       }
     }

@@ -135,7 +135,11 @@ __global__ void __launch_bounds__(gemm_threads<WG_BN>(), 1) gemm_wgrad_group_ker
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (__shfl_sync(0xffffffffu, rank, 0) == 0) {
+      uint32_t el_;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el_));
+      const bool leader = el_ != 0;   // warp-uniform loop, tcgen05 instructions under elect.sync: operands stay in uniform registers
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       constexpr uint32_t idesc = make_idesc_bf16(BM * CL, BN, true, true);
       constexpr uint32_t idesc_ones = make_idesc_bf16(BM * CL, 16, true, true);
       const uint64_t odesc = make_smem_desc_sw128(smem_u32(ones_tile), 0, 0);
@@ -158,12 +162,14 @@ __global__ void __launch_bounds__(gemm_threads<WG_BN>(), 1) gemm_wgrad_group_ker
             const uint64_t adesc = make_smem_desc_sw128(a_base + k * 16 * 128, BK * 128, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(b_base + k * 16 * 128, BK * 128, 1024);
             const uint32_t acc = (kb > s.kb_begin || k > 0) ? 1u : 0u;
-            umma_bf16_cg2(tmem_base, adesc, bdesc, idesc, acc);
-            if (with_bias) umma_bf16_cg2(tmem_base + BN, adesc, odesc, idesc_ones, acc);
+            if (leader) {
+              umma_bf16_cg2(tb, adesc, bdesc, idesc, acc);
+              if (with_bias) umma_bf16_cg2(tb + BN, adesc, odesc, idesc_ones, acc);
+            }
           }
-          umma_commit_cg2(&empty[st], (uint16_t)3);
+          if (leader) umma_commit_cg2(&empty[st], (uint16_t)3);
         }
-        umma_commit_cg2(&tmem_full[0], (uint16_t)3);
+        if (leader) umma_commit_cg2(&tmem_full[0], (uint16_t)3);
         ++sidx;
       }
     }
