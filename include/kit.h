@@ -60,6 +60,9 @@ extern "C" {
 
 const char* kit_last_error(void);
 int kit_version(void);
+/* Leave n SMs (even, <= 64) free in every persistent kernel's grid: data-parallel training runs NCCL's all-reduce kernels beside
+ * backward (parallel.BucketReducer sets it together with NCCL_MAX_CTAS).  Call before the first engine is created. */
+int kit_set_sm_reserve(int32_t n);
 
 /* ------------------------------------------------------------------------------------------
  * Model description and parameter arena.  model.py:61-98 (constructor arguments) -- ff and max_len
@@ -246,6 +249,11 @@ int kit_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  * writes completed_steps (checkpoint restore) and lr (A1_train.py:42-54); the call advances completed_steps by one. */
 int kit_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, void* state,
                       float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* The same update over a sub-range of the arena (pointers already offset; 16-byte aligned, n a multiple of 4): data-parallel
+ * training steps each gradient bucket as soon as its all-reduce has completed.  advance_step != 0 on the first range of an
+ * optimiser step only (it advances completed_steps and recomputes the bias corrections). */
+int kit_adam_step_dev_range(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, void* state,
+                            float beta1, float beta2, float eps, float grad_scale, int32_t advance_step, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Building blocks exposed for unit tests (tests/ call these through the same ABI)

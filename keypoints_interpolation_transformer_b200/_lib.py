@@ -62,6 +62,7 @@ _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 _SIGNATURES = {
     "kit_last_error": (C.c_char_p, []),
     "kit_version": (C.c_int, []),
+    "kit_set_sm_reserve": (C.c_int, [_I32]),
     "kit_layout_num_entries": (_I32, [C.POINTER(KitModelConfig)]),
     "kit_layout_entry": (C.c_int, [C.POINTER(KitModelConfig), _I32, C.c_char_p, _I32, C.POINTER(_I64),
                                    C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I32)]),
@@ -90,6 +91,7 @@ _SIGNATURES = {
     "kit_engine_operands": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_I32)]),
     "kit_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _F, _P]),
     "kit_adam_step_dev": (C.c_int, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _P]),
+    "kit_adam_step_dev_range": (C.c_int, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _I32, _P]),
     "kit_gemm_bf16": (C.c_int, [_I32, _P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P, _I64, _I32, _I32, _P,
                                 _I64, _I32, _P]),
     "kit_ffn_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),

@@ -1137,7 +1137,7 @@ static int fwd_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, co
       KIT_REQUIRE(ctas_per_sm > 0, "attention forward tile kernel does not fit on an SM");
     }
     const int units = B * NH;
-    const int grid1 = units < sms * ctas_per_sm ? units : sms * ctas_per_sm;
+    const int grid1 = units < (sms - sm_reserve()) * ctas_per_sm ? units : (sms - sm_reserve()) * ctas_per_sm;
     launch_kernel(attn_fwd_tile_kernel<D>, dim3(grid1), dim3(AT_THREADS), smem, st, q, ldq, k, ldk, v, ldv, out, ldo, lse, NH, Sq, Sk,
                   units, rsqrtf((float)D), md);
     KIT_LAUNCH_CHECK();
@@ -1158,7 +1158,7 @@ static int fwd_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, co
     const int64_t units64 = (int64_t)B * NH * q_tiles;
     KIT_REQUIRE(units64 < (1ll << 31), "attention forward: too many (batch, head, query tile) units");
     const int units = (int)units64;
-    const int grid1 = units < sms * ctas_per_sm ? units : sms * ctas_per_sm;
+    const int grid1 = units < (sms - sm_reserve()) * ctas_per_sm ? units : (sms - sm_reserve()) * ctas_per_sm;
     launch_kernel(attn_fwd_stream_kernel<D>, dim3(grid1), dim3(AT_THREADS), smem, st, q, ldq, k, ldk, v, ldv, out, ldo, lse, NH, Sq, Sk,
                   q_tiles, k_tiles, units, rsqrtf((float)D), md);
     KIT_LAUNCH_CHECK();
@@ -1186,7 +1186,7 @@ static int bwd_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, co
       KIT_REQUIRE(ctas_per_sm > 0, "attention backward tile kernel does not fit on an SM");
     }
     const int units = B * NH;
-    const int grid1 = units < sms * ctas_per_sm ? units : sms * ctas_per_sm;
+    const int grid1 = units < (sms - sm_reserve()) * ctas_per_sm ? units : (sms - sm_reserve()) * ctas_per_sm;
     launch_kernel(attn_bwd_tile_kernel<D>, dim3(grid1), dim3(AT_THREADS), smem, st, q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq,
                   ld_dq, dk, ld_dk, dv, ld_dv, NH, Sq, Sk, units, rsqrtf((float)D), md);
     KIT_LAUNCH_CHECK();

@@ -752,7 +752,7 @@ static void a64_params(A64Params& p, int B, int NH, int Sq, int Sk, const KitAtt
 }
 template <typename... KArgs, typename... Args>
 static int a64_launch(void (*kernel)(KArgs...), int units, int smem, cudaStream_t st, Args... args) {
-  const int sms = a64_sms();
+  const int sms = a64_sms() - sm_reserve();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(units < sms ? units : sms);
   cfg.blockDim = dim3(64 + 256);

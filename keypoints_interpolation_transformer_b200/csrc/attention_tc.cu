@@ -427,7 +427,7 @@ static int launch_tc(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, con
   p.flags = (mask != nullptr && mask->frame_mask != nullptr) ? mask->flags : (mask != nullptr ? (mask->flags & KIT_MASK_TRIANGLE) : 0);
   p.out = out; p.ldo = ldo; p.lse = lse;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(p.units < sms ? p.units : sms);
+  cfg.gridDim = dim3(p.units < sms - sm_reserve() ? p.units : sms - sm_reserve());
   cfg.blockDim = dim3(64 + 256);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;

@@ -48,6 +48,7 @@ __device__ __forceinline__ void pdl_grid_sync() {
   pdl_launch_dependents();
 }
 bool pdl_enabled();   // errors.cu: KIT_PDL=0 turns the attribute off (A/B measurements)
+int sm_reserve();     // errors.cu: SMs the persistent kernels leave free for concurrent collectives (kit_set_sm_reserve)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};

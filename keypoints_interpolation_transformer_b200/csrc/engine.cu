@@ -38,6 +38,7 @@ struct Layout {
   int64_t trainable = 0, total = 0;
   int64_t wb_elems = 0;
   std::vector<std::pair<int64_t, int64_t>> buckets;  // in backward completion order
+  std::vector<char> dec_cut, enc_cut;                // [layer]: backward reports a finished bucket after this layer
   int64_t learned_i, learned_f, pe_i, pe_f;
   LinearW emb_i, emb_f, fc_final;
   SwiW swi_i, swi_f, swi_d;
@@ -161,17 +162,34 @@ static int build_layout(const KitModelConfig* c, Layout& L) {
   L.pe_f = lb.add("trig_filled_positional_encoder.pos_encoding", c->max_len, H, 1);
   L.total = lb.cur;
   (void)end_group_e;
-  // buckets in the order backward completes them
-  const int half = c->layers / 2;
+  // Buckets in the order backward completes them: the decoder stack, encoder layers 1.., and a small tail -- the all-reduce of
+  // the LAST bucket cannot overlap anything, so it holds only encoder layer 0 and the embedding / pre-transformer group (5.9 MB
+  // of the 72 MB arena; it was a quarter of the arena with four equal buckets).  Finer buckets (KIT_BUCKET_LAYERS = layers per
+  // bucket) measured slower on 2 and 8 GPUs: every cut is one more graph launch and one more collective (profiles/r02_dp.md).
+  L.dec_cut.assign(c->layers, 0);
+  L.enc_cut.assign(c->layers, 0);
+  int per = 0;   // layers per bucket (KIT_BUCKET_LAYERS: A/B measurements; 0 = one bucket per stack + the tail)
+  if (const char* v = getenv("KIT_BUCKET_LAYERS")) per = atoi(v);
+  for (int l = 1; l < c->layers; ++l) {
+    L.dec_cut[l] = (per > 0 && l % per == 0) ? 1 : 0;
+    L.enc_cut[l] = ((per > 0 && l % per == 0) || l == 1) ? 1 : 0;
+  }
   L.buckets.clear();
-  if (half > 0) {
-    L.buckets.push_back({dec_begin[half], L.trainable});
-    L.buckets.push_back({dec_begin[0], dec_begin[half]});
-    L.buckets.push_back({enc_begin[half], end_enc});
-    L.buckets.push_back({0, enc_begin[half]});
-  } else {
-    L.buckets.push_back({dec_begin[0], L.trainable});
-    L.buckets.push_back({0, dec_begin[0]});
+  {
+    int64_t hi = L.trainable;
+    for (int l = c->layers - 1; l >= 1; --l)
+      if (L.dec_cut[l]) {
+        L.buckets.push_back({dec_begin[l], hi});
+        hi = dec_begin[l];
+      }
+    L.buckets.push_back({dec_begin[0], hi});   // decoder finished
+    hi = end_enc;
+    for (int l = c->layers - 1; l >= 1; --l)
+      if (L.enc_cut[l]) {
+        L.buckets.push_back({enc_begin[l], hi});
+        hi = enc_begin[l];
+      }
+    L.buckets.push_back({0, hi});              // encoder layer 0 (and below) + embeddings, learned PEs, the two input SwiGLUs
   }
   // bf16 GEMM operands
   lb.add_wb(L.emb_i); lb.add_wb(L.emb_f);
@@ -700,7 +718,7 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
   const int H = L.cfg.hidden, NH = L.cfg.heads, d = H / NH, IN = L.cfg.input_size, FF = L.cfg.ff;
   const int B = e->B, T = e->T;
   const int64_t M = e->M;
-  const int nl = L.cfg.layers, half = nl / 2;
+  const int nl = L.cfg.layers;
   e->active = &e->bwd_plans;
   e->cursor = 0;
   e->group_cursor = 0;
@@ -771,9 +789,9 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
       top_done = false;
     }
     dy = e->g0;
-    if (half > 0 && l == half) done();
+    if (L.dec_cut[l]) done();
   }
-  done();  // decoder finished (bucket 1, or bucket 0 for a 1-layer model)
+  done();  // decoder finished
   // filled branch: SwiGLU, token-norm/PE, embedding  (g3 = residual gradient from the head)
   KIT_TRY(swiglu_bwd(e, dy, e->ef, L.swi_f, e->sf12, e->sfg, e->g1, e->g2));  // g2 = d ef
   e->launches++;
@@ -817,7 +835,7 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
       top_done = false;
     }
     dx = e->g0;
-    if (half > 0 && l == half) done();
+    if (L.enc_cut[l]) done();
   }
   // input branch
   KIT_TRY(swiglu_bwd(e, dx, e->ei, L.swi_i, e->si12, e->sig, e->g1, e->g2));

@@ -20,7 +20,26 @@ bool pdl_enabled() {
   }();
   return on;
 }
+// SMs the persistent kernels leave free (kit_set_sm_reserve / KIT_SM_RESERVE): under data parallelism the NCCL all-reduce
+// kernels run beside backward; the compute kernels are ONE wave of persistent CTAs that fill an SM, so a collective's CTAs
+// could only start at kernel boundaries and then displaced CTAs of the next kernel into a second wave (+7 % on every kernel
+// with the collectives resident, SCALE_r01).  With a few SMs reserved the two never compete.
+static int g_sm_reserve = -1;
+int sm_reserve() {
+  if (g_sm_reserve < 0) {
+    const char* v = getenv("KIT_SM_RESERVE");
+    g_sm_reserve = v != nullptr ? atoi(v) : 0;
+    if (g_sm_reserve < 0 || g_sm_reserve > 64) g_sm_reserve = 0;
+    g_sm_reserve &= ~1;   // CTA pairs
+  }
+  return g_sm_reserve;
+}
+void set_sm_reserve(int n) { g_sm_reserve = (n < 0 || n > 64) ? 0 : (n & ~1); }
 }  // namespace kit
 
+extern "C" int kit_set_sm_reserve(int32_t n) {
+  kit::set_sm_reserve(n);
+  return KIT_OK;
+}
 extern "C" const char* kit_last_error(void) { return kit::get_error(); }
 extern "C" int kit_version(void) { return KIT_ABI_VERSION; }

@@ -125,7 +125,7 @@ int gemm_init_attributes() {
 // EPI_ADD_LNBWD stages the saved-sum tiles through the operand ring once the accumulator is complete: one 256-row item per CTA pair
 bool gemm_lnbwd_supported(int M) {
   if (gemm_init_attributes()) return false;
-  return (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM) <= g_num_sms / 2;
+  return (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM) <= (g_num_sms - sm_reserve()) / 2;
 }
 
 static bool aligned16(const void* ptr, int64_t ld_elems, size_t esize) {
@@ -173,7 +173,7 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
     if ((rc = make_tensor_map_2d(&plan->tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, GEMM_BK))) return rc;
     if ((rc = make_tensor_map_2d(&plan->tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, GEMM_BK))) return rc;
     splits = split_k;
-    if (splits <= 0) splits = (g_num_sms / cl) / groups;   // about one work item per CTA (pair)
+    if (splits <= 0) splits = ((g_num_sms - sm_reserve()) / cl) / groups;   // about one work item per CTA (pair)
   }
   // epilogue kind: outputs (and the residual / GELU' input) through shared memory + TMA whenever tensor maps can describe them
   const size_t esize = (out_kind == OUT_BF16) ? 2 : 4;
@@ -198,7 +198,7 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
       else if (act == ACT_GELU_BWD && addend == nullptr && aligned16(aux, ld_aux, 2)) epi = EPI_GELU_BWD;
     }
   }
-  if (epi == EPI_ADD_LNBWD && groups > g_num_sms / cl) epi = EPI_ADD;   // the fused kind stages through the operand ring: one item per CTA
+  if (epi == EPI_ADD_LNBWD && groups > (g_num_sms - sm_reserve()) / cl) epi = EPI_ADD;   // the fused kind stages through the operand ring: one item per CTA
   plan->epi = epi;
   p.bias_grad = (mode == 1 && epi == EPI_F32) ? bias_grad : nullptr;   // else the caller sums the columns of dy itself
   p.lnb = LnBwdArgs{nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -235,7 +235,7 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
   p.kb_per_split = (kb_total + splits - 1) / splits;
   p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
   const int items = groups * p.splits;   // work items per CTA (pair)
-  const int max_clusters = g_num_sms / cl;
+  const int max_clusters = (g_num_sms - sm_reserve()) / cl;
   plan->grid = (items < max_clusters ? items : max_clusters) * cl;
   return KIT_OK;
 }
@@ -320,7 +320,7 @@ int wgrad_group_plan(WgradGroupPlan* plan, const WgradProblemDesc* probs, int n,
     plan->maps.c[i] = plan->maps.c[0];
   }
   p.total_units = units;
-  const int max_clusters = g_num_sms / WG_CL;
+  const int max_clusters = (g_num_sms - sm_reserve()) / WG_CL;
   const int clusters = units < max_clusters ? units : max_clusters;
   p.units_per_cluster = (units + clusters - 1) / clusters;
   plan->grid = ((units + p.units_per_cluster - 1) / p.units_per_cluster) * WG_CL;
@@ -391,7 +391,7 @@ int ffn_fwd_plan(FfnPlan* plan, const bf16* x, int64_t ldx, const bf16* w1, int6
     if (g_ffn_trace != nullptr) cudaMemset(g_ffn_trace, 0, 256 * sizeof(long long));
     p.trace = g_ffn_trace;
   }
-  const int max_clusters = g_num_sms / 2;
+  const int max_clusters = (g_num_sms - sm_reserve()) / 2;
   plan->grid = (p.n_items < max_clusters ? p.n_items : max_clusters) * 2;
   return KIT_OK;
 }

@@ -701,12 +701,12 @@ int ln_bwd(const bf16* dy, const bf16* s_saved, const float* mean, const float* 
   if (H == 256 && addend == nullptr && rows_variant == 1) {   // every row of a warp in flight at once
     constexpr int R = 7, W = 16;
     const int64_t want = ceil_div(M, W * R);
-    const unsigned grid = (unsigned)(want < sms ? (want < 1 ? 1 : want) : sms);
+    const unsigned grid = (unsigned)(want < sms - sm_reserve() ? (want < 1 ? 1 : want) : sms - sm_reserve());
     launch_kernel(ln_bwd_rows_kernel<W, R>, dim3(grid), dim3(W * 32), 3 * W * 256 * sizeof(float), st, dy, s_saved, mean, rstd, gamma, dx,
                   dgamma, dbeta, dxsum, M);
   } else if (H <= 256) {   // 16 warps x 16 KB of column partials; one block per SM (103 registers x 512 threads)
     const int64_t want = ceil_div(M, 16 * 2);
-    const unsigned grid = (unsigned)(want < sms ? (want < 1 ? 1 : want) : sms);
+    const unsigned grid = (unsigned)(want < sms - sm_reserve() ? (want < 1 ? 1 : want) : sms - sm_reserve());
     launch_kernel(ln_bwd_kernel<1, 16>, dim3(grid), dim3(512), 0, st, dy, s_saved, mean, rstd, gamma, addend, dx, dgamma, dbeta, dxsum, M, H);
   } else {
     KIT_NV_DISPATCH(H, (launch_kernel(ln_bwd_kernel<NV, ROW_WARPS>, dim3(reduce_blocks(M)), dim3(256), 0, st, dy, s_saved, mean, rstd, gamma,

@@ -72,6 +72,24 @@ class FlatAdam:
                                       float(self.grad_scale), K.stream_ptr()))
         self.model.mark_dirty()
 
+    @torch.no_grad()
+    def step_range(self, lo, hi, first):
+        """Adam over arena range [lo, hi) (``capturable`` mode): data-parallel training steps each gradient bucket as soon as its
+        all-reduce has completed.  ``first``: the first range of this optimiser step (advances the step count)."""
+        if not self.capturable:
+            raise K.KitError("FlatAdam.step_range needs capturable=True (step count on the device)")
+        self._state()
+        g = self.model.ensure_flat_grads()
+        grp = self.param_groups[0]
+        st = self._device_state()
+        if first:
+            self.step_count += 1
+        K.check(K.lib().kit_adam_step_dev_range(K.ptr(self.model.flat_params[lo:hi]), K.ptr(g[lo:hi]), K.ptr(self.exp_avg[lo:hi]),
+                                                K.ptr(self.exp_avg_sq[lo:hi]), hi - lo, K.ptr(st), float(grp["betas"][0]),
+                                                float(grp["betas"][1]), float(grp["eps"]), float(self.grad_scale),
+                                                1 if first else 0, K.stream_ptr()))
+        self.model.mark_dirty()
+
     def state_dict(self):
         self._state()
         return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),

@@ -70,6 +70,23 @@ class TrainStep:
             self.optimizer.grad_scale = scale
         self.pred = None
         self.last_launches = 0
+        self._defer_finish = False    # _eager / the graph chain: the collectives are waited for bucket by bucket by _optimizer_step
+
+    def _optimizer_step(self):
+        """A1_train.py:135.  Under data parallelism with a range-capable optimiser, every gradient bucket is stepped as soon
+        as ITS all-reduce has completed (in the order backward finished them), so Adam on the early buckets runs while the
+        last ones are still on the wire."""
+        red = self.reducer
+        if red is None or self.streams > 1 or not getattr(self.optimizer, "capturable", False) or not hasattr(self.optimizer, "step_range"):
+            if red is not None:
+                red.finish()
+            self.optimizer.step()
+            self.last_launches += 2
+            return
+        for b, (lo, hi) in enumerate(red.buckets):
+            red.wait_bucket(b)
+            self.optimizer.step_range(lo, hi, first=(b == 0))
+        self.last_launches += 1 + len(red.buckets)
 
     def _forward_backward_split(self, inputs, sota, mask):
         """The ``streams > 1`` step: fork the current stream into ``streams`` side streams, one sub-batch each, join."""
@@ -154,7 +171,8 @@ class TrainStep:
         elif self.reducer is not None:
             self.reducer.begin()
             eng.backward(dpred, self.reducer.bucket_ready)
-            self.reducer.finish()
+            if not self._defer_finish:
+                self.reducer.finish()
         else:
             eng.backward(dpred)
         self.last_launches = eng.fwd_launches + eng.bwd_launches + 3
@@ -178,10 +196,13 @@ class TrainStep:
             chain.append(("graph", cur[0]))
             cur[0] = None
 
+        n_buckets = len(self.reducer.buckets)
+
         def cut(b):
             end()
             chain.append(("bucket", b))
-            begin()
+            if b < n_buckets - 1:         # backward ends with its last bucket: nothing is left to capture
+                begin()
 
         side = torch.cuda.Stream(device=batch[0].device)
         side.wait_stream(torch.cuda.current_stream())
@@ -189,10 +210,9 @@ class TrainStep:
             with torch.cuda.stream(side):
                 begin()
                 loss = self.forward_backward(*batch, _bucket_cb=cut)
-                self.optimizer.step()      # backward ends with its last bucket: the graph opened by that cut holds Adam
-                self.last_launches += 2
-                end()
-                chain.insert(len(chain) - 1, ("finish", None))
+                if cur[0] is not None:     # (a backward that reported fewer buckets than the layout lists)
+                    end()
+                chain.append(("adam", None))     # stepped bucket by bucket between the replays (_optimizer_step)
         except Exception:
             if cur[0] is not None:
                 try:
@@ -211,12 +231,15 @@ class TrainStep:
             elif kind == "bucket":
                 self.reducer.bucket_ready(x)
             else:
-                self.reducer.finish()
+                self._optimizer_step()
 
     def _eager(self, *batch):
-        loss = self.forward_backward(*batch)
-        self.optimizer.step()                                    # A1_train.py:135
-        self.last_launches += 2                                  # adam + weight refresh at next forward
+        self._defer_finish = self.reducer is not None and self.streams == 1
+        try:
+            loss = self.forward_backward(*batch)
+        finally:
+            self._defer_finish = False
+        self._optimizer_step()                                   # A1_train.py:135
         return loss
 
     def __call__(self, *batch):
@@ -255,10 +278,10 @@ class TrainStep:
             self._graphs[key] = entry
         self.optimizer.sync_host_values()
         if self.reducer is not None:
-            self._replay_chain(entry[0])
+            self._replay_chain(entry[0])          # (the optimiser is stepped between the replays and counts its own steps)
         else:
             entry[0].replay()
-        self.optimizer.step_count += 1
+            self.optimizer.step_count += 1
         return entry[1]
 
 
@@ -301,7 +324,8 @@ class RawTrainStep(TrainStep):
         elif self.reducer is not None:
             self.reducer.begin()
             eng.backward(dpred, self.reducer.bucket_ready)
-            self.reducer.finish()
+            if not self._defer_finish:
+                self.reducer.finish()
         else:
             eng.backward(dpred)
         self.last_launches = eng.fwd_launches + eng.bwd_launches + 3 + 5      # + policy (3) and pre-pass (2) launches

@@ -401,7 +401,8 @@ def test_graph_replayed_step_matches_eager_step():
 
 def test_chained_graph_step_with_reducer_matches_eager_step():
     """The data-parallel form of the captured step: a chain of graphs cut at backward's bucket boundaries, the bucket
-    callbacks (the all-reduces; no-ops in a one-process world) issued between them, Adam in the last graph."""
+    callbacks (the all-reduces; no-ops in a one-process world) issued between them, then Adam bucket by bucket (each range as
+    soon as its all-reduce has completed)."""
     from keypoints_interpolation_transformer_b200 import parallel
     Kp, H, L, NH, B, T = 54, 64, 2, 4, 4, 16
     batches = [tuple(t.to(DEV) for t in ko.synthetic_batch(B, T, Kp, seed=40 + i)) for i in range(2)]
@@ -423,7 +424,7 @@ def test_chained_graph_step_with_reducer_matches_eager_step():
         if use_graph:
             assert step.use_graph and len(step._graphs) == 2 and opt.step_count == 8
             chain = next(iter(step._graphs.values()))[0]
-            assert [k for k, _ in chain].count("graph") == nb + 1 and [k for k, _ in chain][-2] == "finish"
+            assert [k for k, _ in chain].count("graph") == nb and [k for k, _ in chain][-1] == "adam"
         results.append((losses, m.flat_params[:m.layout.trainable].clone()))
     (l0, p0), (l1, p1) = results
     assert np.allclose(l0, l1, rtol=2e-3, atol=1e-6), (l0, l1)

@@ -5,6 +5,8 @@ NCCL all-reduce (parallel.BucketReducer, overlapped with backward) and compare: 
 import os
 import sys
 
+os.environ.setdefault("KIT_DP_COMPRESS", "none")    # this check is about the fp32 path: sharded == global to reduction-order noise
+
 import torch
 import torch.distributed as dist
 
