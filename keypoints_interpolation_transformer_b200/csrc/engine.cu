@@ -46,6 +46,11 @@ struct Layout {
   std::vector<DecW> dec;
   LNW enc_norm, dec_norm;
   std::vector<WeightDesc> wdescs;
+  // The cross-attention key / value projections of ALL decoder layers read the same tensor (the encoder output): their weights
+  // are kept a second time as one [layers * 2H, H] B operand (and its transpose [H, layers * 2H]) so the forward is one GEMM with
+  // N = layers * 2H and the gradient with respect to the encoder output one GEMM with K = layers * 2H.
+  int64_t kvcat_wb = -1, kvcat_wbT = -1;
+  int kvcat_n = 0;   // layers * 2H
 };
 
 static int64_t up8(int64_t x) { return round_up(x, 8); }
@@ -205,6 +210,18 @@ static int build_layout(const KitModelConfig* c, Layout& L) {
   }
   lb.add_wb(L.swi_d.fc12); lb.add_wb(L.swi_d.fc3);
   lb.add_wb(L.fc_final);
+  L.kvcat_n = c->layers * 2 * H;
+  L.kvcat_wb = lb.wcur;
+  lb.wcur = round_up(lb.wcur + (int64_t)L.kvcat_n * H, 64);
+  L.kvcat_wbT = lb.wcur;
+  lb.wcur = round_up(lb.wcur + (int64_t)H * L.kvcat_n, 64);
+  for (int l = 0; l < c->layers; ++l) {   // rows H .. 3H of in_proj_weight (torch/nn/functional.py:6360 _in_projection_packed)
+    WeightDesc d;
+    d.src_off = L.dec[l].ca.in.w + (int64_t)H * H; d.rows = 2 * H; d.cols = H;
+    d.dst_off = L.kvcat_wb + (int64_t)l * 2 * H * H; d.dst_ld = H; d.rows_pad = 2 * H; d.cols_pad = H;
+    d.dstT_off = L.kvcat_wbT + (int64_t)l * 2 * H; d.dstT_ld = L.kvcat_n;
+    L.wdescs.push_back(d);
+  }
   L.wb_elems = lb.wcur;
   return KIT_OK;
 }
@@ -218,7 +235,7 @@ struct Buf {
 };
 
 struct EncAct { bf16 *qkv, *ao, *s1, *x1, *z, *hh, *s2, *x2; float *lse, *st1, *st2; };
-struct DecAct { bf16 *qkv, *ao, *s1, *y1, *qc, *kvc, *aoc, *s2, *y2, *z, *hh, *s3, *y3; float *lse, *lsec, *st1, *st2, *st3; };
+struct DecAct { bf16 *qkv, *ao, *s1, *y1, *qc, *kvc, *aoc, *s2, *y2, *z, *hh, *s3, *y3; float *lse, *lsec, *st1, *st2, *st3; };   // kvc: this layer's columns of kv_all
 
 }  // namespace kit
 
@@ -271,7 +288,9 @@ struct KitEngine {
   float *st_encn, *st_decn;
   std::vector<EncAct> ea;
   std::vector<DecAct> da;
-  bf16 *g0, *g1, *g1b, *g1c, *g2, *g3, *gmem, *gff, *gqkv, *gqc, *gkv, *g2h;
+  bf16 *g0, *g1, *g1b, *g1c, *g2, *g3, *gmem, *gff, *gqkv, *gqc, *gkv, *g2h;   // gkv: [M, layers * 2H], one column block per decoder layer
+  bf16* kv_all;     // [M, layers * 2H]: cross-attention keys / values of every decoder layer (one GEMM over the encoder output)
+  float* kv_bias;   // [layers * 2H]: the in_proj_bias[H:3H] slices gathered at weight-refresh time
   float* dq_acc;
 
   int64_t alloc(const std::string& name, int64_t elems, int esize, int64_t ld) {
@@ -303,6 +322,8 @@ static void plan_workspace(KitEngine* e) {
     e->alloc(n, M * H, 2, H);
   for (const char* n : {"si12", "sf12", "sd12"}) e->alloc(n, M * 2 * H, 2, 2 * H);
   e->alloc("dp", M * e->K2p, 2, e->K2p);
+  e->alloc("kv_all", M * L.kvcat_n, 2, L.kvcat_n);
+  e->alloc("kv_bias", L.kvcat_n, 4, 0);
   e->alloc("st_encn", 2 * M, 4, 0);
   e->alloc("st_decn", 2 * M, 4, 0);
   const int n_saved = e->training ? L.cfg.layers : 1;
@@ -321,7 +342,6 @@ static void plan_workspace(KitEngine* e) {
   for (int l = 0; l < n_saved; ++l) {
     const std::string p = "dec" + std::to_string(l) + ".";
     e->alloc(p + "qkv", M * 3 * H, 2, 3 * H);
-    e->alloc(p + "kvc", M * 2 * H, 2, 2 * H);
     for (const char* n : {"ao", "s1", "y1", "qc", "aoc", "s2", "y2", "s3", "y3"}) e->alloc(p + n, M * H, 2, H);
     e->alloc(p + "z", zh_elems, 2, FF);
     e->alloc(p + "hh", zh_elems, 2, FF);
@@ -334,13 +354,14 @@ static void plan_workspace(KitEngine* e) {
   for (const char* n : {"g0", "g1", "g1b", "g1c", "g2", "g3", "gmem", "gqc"}) e->alloc(n, gm * H, 2, H);
   e->alloc("gff", gm * FF, 2, FF);
   e->alloc("gqkv", gm * 3 * H, 2, 3 * H);
-  e->alloc("gkv", gm * 2 * H, 2, 2 * H);
+  e->alloc("gkv", gm * L.kvcat_n, 2, L.kvcat_n);
   e->alloc("g2h", gm * 2 * H, 2, 2 * H);
   e->alloc("dq_acc", (e->training && e->T > 64) ? M * H + M * NH : 8, 4, H);
 }
 
 static void resolve_pointers(KitEngine* e) {
   const Layout& L = e->L;
+  const int H = L.cfg.hidden;
   e->wb = wsptr<bf16>(e, "wb");
   e->wdesc_dev = wsptr<WeightDesc>(e, "wdesc");
   e->tile_prefix_dev = wsptr<int>(e, "tile_prefix");
@@ -350,6 +371,8 @@ static void resolve_pointers(KitEngine* e) {
   KIT_P(dp); KIT_P(g0); KIT_P(g1); KIT_P(g1b); KIT_P(g1c); KIT_P(gqc); KIT_P(g2); KIT_P(g3); KIT_P(gmem); KIT_P(gff); KIT_P(gqkv); KIT_P(gkv); KIT_P(g2h);
 #undef KIT_P
   e->dq_acc = wsptr<float>(e, "dq_acc");
+  e->kv_all = wsptr<bf16>(e, "kv_all");
+  e->kv_bias = wsptr<float>(e, "kv_bias");
   e->st_encn = wsptr<float>(e, "st_encn");
   e->st_decn = wsptr<float>(e, "st_decn");
   e->ea.resize(L.cfg.layers);
@@ -364,7 +387,7 @@ static void resolve_pointers(KitEngine* e) {
     const std::string q = "dec" + std::to_string(e->training ? l : 0) + ".";
     DecAct& d = e->da[l];
     d.qkv = wsptr<bf16>(e, q + "qkv"); d.ao = wsptr<bf16>(e, q + "ao"); d.s1 = wsptr<bf16>(e, q + "s1");
-    d.y1 = wsptr<bf16>(e, q + "y1"); d.qc = wsptr<bf16>(e, q + "qc"); d.kvc = wsptr<bf16>(e, q + "kvc");
+    d.y1 = wsptr<bf16>(e, q + "y1"); d.qc = wsptr<bf16>(e, q + "qc"); d.kvc = e->kv_all + (int64_t)l * 2 * H;
     d.aoc = wsptr<bf16>(e, q + "aoc"); d.s2 = wsptr<bf16>(e, q + "s2"); d.y2 = wsptr<bf16>(e, q + "y2");
     d.z = wsptr<bf16>(e, q + "z"); d.hh = wsptr<bf16>(e, q + "hh"); d.s3 = wsptr<bf16>(e, q + "s3");
     d.y3 = wsptr<bf16>(e, q + "y3");
@@ -686,6 +709,9 @@ static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const f
   e->launches++;
   KIT_TRY(add_ln_fwd(x, nullptr, e->params + L.enc_norm.g, e->params + L.enc_norm.b, nullptr, e->mem, e->st_encn,
                      e->st_encn + M, M, H, e->st));
+  // cross-attention keys / values of all decoder layers: kv_all = mem Wkv_cat^T + b (N = layers * 2H)
+  KIT_TRY(eg(e, 0, e->mem, H, e->wb + L.kvcat_wb, H, e->kv_all, L.kvcat_n, (int)M, L.kvcat_n, H, e->kv_bias, nullptr, 0, OUT_BF16,
+             ACT_NONE, nullptr, 0));
   // decoder (transformer.py:1147-1153 + final norm :163); cross-attention is unmasked
   const bf16* y = e->y0;
   for (int l = 0; l < L.cfg.layers; ++l) {
@@ -695,8 +721,7 @@ static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const f
     KIT_TRY(eattn_fwd(e, a.qkv, 3 * H, a.qkv + H, 3 * H, a.qkv + 2 * H, 3 * H, a.ao, H, a.lse, &e->dec_mask));
     KIT_TRY(linear_add_ln_fwd(e, a.ao, H, w.sa.out, a.s1, y, w.n1, a.y1, a.st1));
     KIT_TRY(linear_fwd(e, a.y1, H, w.ca.in, 0, H, a.qc, H, nullptr, 0));
-    KIT_TRY(linear_fwd(e, e->mem, H, w.ca.in, H, 2 * H, a.kvc, 2 * H, nullptr, 0));
-    KIT_TRY(eattn_fwd(e, a.qc, H, a.kvc, 2 * H, a.kvc + H, 2 * H, a.aoc, H, a.lsec, nullptr));
+    KIT_TRY(eattn_fwd(e, a.qc, H, a.kvc, L.kvcat_n, a.kvc + H, L.kvcat_n, a.aoc, H, a.lsec, nullptr));
     KIT_TRY(linear_add_ln_fwd(e, a.aoc, H, w.ca.out, a.s2, a.y1, w.n2, a.y2, a.st2));
     KIT_TRY(ffn_block_fwd(e, a.y2, w.l1, w.l2, a.z, a.hh, a.s3, w.n3, a.y3, a.st3));
     y = a.y3;
@@ -743,7 +768,6 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
   KIT_TRY(ln_bwd(e->g1, e->da[nl - 1].y3, e->st_decn, e->st_decn + M, e->params + L.dec_norm.g, nullptr, e->g0,
                  e->grads + L.dec_norm.g, e->grads + L.dec_norm.b, nullptr, M, H, e->st));
   bf16* dy = e->g0;  // gradient w.r.t. the current layer's output
-  bool mem_grad_started = false;
   bool top_done = false;   // the LayerNorm backward at the top of this layer already ran in the previous layer's last GEMM (-> g1)
   bool bd = true;
   for (int l = nl - 1; l >= 0; --l) {
@@ -764,12 +788,11 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
     // cross-attention block
     pend.push_back({e->g1b, H, a.aoc, H, &w.ca.out, 0, H, bd});
     KIT_TRY(linear_dgrad(e, e->g1b, H, w.ca.out, 0, H, e->g2, H, nullptr, 0));  // g2 = d aoc
-    KIT_TRY(eattn_bwd(e, a.qc, H, a.kvc, 2 * H, a.kvc + H, 2 * H, a.aoc, H, e->g2, H, a.lsec, e->gqc, H, e->gkv, 2 * H,
-                      e->gkv + H, 2 * H, nullptr));
+    bf16* gkv = e->gkv + (int64_t)l * 2 * H;   // this layer's columns of the [M, layers * 2H] key / value gradient
+    KIT_TRY(eattn_bwd(e, a.qc, H, a.kvc, L.kvcat_n, a.kvc + H, L.kvcat_n, a.aoc, H, e->g2, H, a.lsec, e->gqc, H, gkv, L.kvcat_n,
+                      gkv + H, L.kvcat_n, nullptr));
     pend.push_back({e->gqc, H, a.y1, H, &w.ca.in, 0, H, false});
-    pend.push_back({e->gkv, 2 * H, e->mem, H, &w.ca.in, H, 2 * H, false});
-    KIT_TRY(linear_dgrad(e, e->gkv, 2 * H, w.ca.in, H, 2 * H, e->gmem, H, mem_grad_started ? e->gmem : nullptr, H));
-    mem_grad_started = true;
+    pend.push_back({gkv, L.kvcat_n, e->mem, H, &w.ca.in, H, 2 * H, false});
     // d y1 = gqc Wq + g1b, then the backward of norm1 -> g1c = d s1
     KIT_TRY(dgrad_then_lnbwd(e, e->gqc, H, w.ca.in, 0, H, e->g1b, e->g2, e->g1c, a.s1, a.st1, w.n1, e->grads + w.sa.out.b, &bd));
     // self-attention block
@@ -801,7 +824,9 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
              ACT_NONE, nullptr, 0));
   e->launches++;
   KIT_TRY(colsum(e->g1, H, e->grads + L.emb_f.b, M, H, e->st));
-  // ---- encoder
+  // ---- encoder.  d mem = gkv Wkv_cat: the key / value gradients of all decoder layers in one GEMM with K = layers * 2H
+  KIT_TRY(eg(e, 0, e->gkv, L.kvcat_n, e->wb + L.kvcat_wbT, L.kvcat_n, e->gmem, H, (int)M, H, L.kvcat_n, nullptr, nullptr, 0, OUT_BF16,
+             ACT_NONE, nullptr, 0));
   e->launches++;
   KIT_TRY(ln_bwd(e->gmem, e->ea[nl - 1].x2, e->st_encn, e->st_encn + M, e->params + L.enc_norm.g, nullptr, e->g0,
                  e->grads + L.enc_norm.g, e->grads + L.enc_norm.b, nullptr, M, H, e->st));
@@ -847,6 +872,14 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
   KIT_TRY(colsum(e->g1, H, e->grads + L.emb_i.b, M, H, e->st));
   done();
   return KIT_OK;
+}
+
+// kv_bias[l * n + i] = params[base + l * stride + i]: the in_proj_bias[H:3H] slices of the decoder layers' cross-attention
+__global__ void gather_kv_bias_kernel(const float* __restrict__ params, int64_t base, int64_t stride, int n, int layers,
+                                      float* __restrict__ out) {
+  pdl_grid_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * layers) out[i] = params[base + (int64_t)(i / n) * stride + (i % n)];
 }
 
 __global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int64_t n) {
@@ -977,6 +1010,14 @@ extern "C" int kit_engine_refresh_weights(KitEngine* e, void* stream) {
   KIT_REQUIRE(e && e->bound, "kit_engine_refresh_weights: engine not bound");
   KIT_TRY(weight_refresh(e->params, e->wb, e->wdesc_dev, e->tile_prefix_dev, (int)e->L.wdescs.size(), e->total_tiles,
                          (cudaStream_t)stream));
+  {
+    const Layout& L = e->L;
+    const int H = L.cfg.hidden, nl = L.cfg.layers;
+    const int64_t base = L.dec[0].ca.in.b + H, stride = nl > 1 ? L.dec[1].ca.in.b - L.dec[0].ca.in.b : 0;
+    launch_kernel(gather_kv_bias_kernel, dim3((unsigned)ceil_div((int64_t)L.kvcat_n, 256)), dim3(256), 0, (cudaStream_t)stream,
+                  (const float*)e->params, base, stride, 2 * H, nl, e->kv_bias);
+    KIT_LAUNCH_CHECK();
+  }
   e->weights_fresh = true;
   return KIT_OK;
 }

@@ -132,7 +132,7 @@ class StepEngine:
 
     def debug_read(self, name):
         lib = K.lib()
-        out = torch.empty(self.workspace.numel() // 2 if False else self._buf_elems(name), device=self.params.device)
+        out = torch.empty(self._buf_elems(name), device=self.params.device)
         K.check(lib.kit_engine_debug_read(self._h, name.encode(), K.ptr(out), out.numel(), K.stream_ptr()))
         return out
 
@@ -143,7 +143,11 @@ class StepEngine:
         base = name.split(".")[-1]
         if base in ("qkv", "gqkv"):
             return M * 3 * H
-        if base in ("kvc", "si12", "sf12", "sd12", "gkv", "g2h"):
+        if base in ("kv_all", "gkv"):
+            return M * 2 * H * c.layers
+        if base == "kv_bias":
+            return 2 * H * c.layers
+        if base in ("si12", "sf12", "sd12", "g2h"):
             return M * 2 * H
         if base in ("z", "hh", "gff"):
             return M * FF

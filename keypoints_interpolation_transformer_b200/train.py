@@ -81,12 +81,12 @@ class TrainStep:
             if red is not None:
                 red.finish()
             self.optimizer.step()
-            self.last_launches += 2
+            self.last_launches += 3      # adam + weight refresh and cross-attention bias gather at the next forward
             return
         for b, (lo, hi) in enumerate(red.buckets):
             red.wait_bucket(b)
             self.optimizer.step_range(lo, hi, first=(b == 0))
-        self.last_launches += 1 + len(red.buckets)
+        self.last_launches += 2 + len(red.buckets)
 
     def _forward_backward_split(self, inputs, sota, mask):
         """The ``streams > 1`` step: fork the current stream into ``streams`` side streams, one sub-batch each, join."""

@@ -19,7 +19,8 @@ if __name__ == "__main__":
     print(f"{'shape':34s} {'issue cyc/MMA':>14s} {'complete cyc/MMA':>17s}")
     for (M, N, a_mn, b_mn, a_tmem) in [(64, 64, 0, 0, 0), (64, 32, 0, 1, 0), (64, 32, 1, 1, 0), (64, 64, 0, 0, 1), (64, 32, 0, 1, 1),
                                         (128, 64, 0, 0, 0), (128, 128, 0, 0, 0), (128, 32, 0, 1, 0), (128, 32, 1, 1, 0), (128, 64, 1, 1, 0),
-                                        (128, 128, 0, 0, 1), (128, 32, 0, 1, 1), (128, 256, 0, 0, 0), (128, 192, 0, 0, 0)]:
+                                        (128, 128, 0, 0, 1), (128, 32, 0, 1, 1), (128, 256, 0, 0, 0), (128, 192, 0, 0, 0),
+                                        (128, 256, 0, 0, 1), (128, 64, 0, 0, 1), (128, 192, 0, 0, 1)]:
         for _ in range(2):
             K.check(fn(idesc(M, N, bool(a_mn), bool(b_mn)), reps, a_mn, b_mn, a_tmem, out.data_ptr(), None))
             torch.cuda.synchronize()
