@@ -31,6 +31,13 @@ namespace kit {
 
 constexpr int FFN_H = 256;
 constexpr int FFN_FC = 128;
+// FFN_XT (an experiment kept behind KIT_FFN_XT, default off -- it measured no faster, see gemm.cu ffn_xt_mask): the x tile is
+// copied into tensor memory once per item (tcgen05.st by the epilogue warps, 128 columns of bf16 pairs) and GEMM1 takes its A
+// operand from there.  tools/umma_rate.py: an M = 128, N = 128 tcgen05.mma costs 112 cycles with both
+// operands in shared memory (48 of them the A read, which does not overlap the math) and 79 with A in tensor memory.  The 512
+// columns then hold acc1 (128, single-buffered: GEMM1(c + 1) waits for EPI1(c)'s tcgen05.ld, which GEMM2(c - 1) covers on the
+// pipe), x (128) and acc2 (256).
+// A template parameter (KIT_FFN_XT=0 at plan time selects the shared-memory A operand: A/B measurements).
 template <bool BWD> constexpr int ffn_ring() { return BWD ? 3 : 5; }    // 16 KB weight slots
 template <bool BWD> constexpr int ffn_zbufs() { return BWD ? 2 : 1; }   // z chunk buffers: TMA-in (double-buffered) / staging out
 constexpr int FFN_SLOT = 16384;
@@ -61,6 +68,7 @@ struct FfnPlan {
   FfnParams p;
   int grid;
   int bwd;
+  int xt;   // x tile as a tensor-memory A operand (FFN_XT)
 };
 
 #ifdef KIT_FFN_IMPL   // the kernel is compiled into gemm.cu only
@@ -85,9 +93,33 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
   }
 }
+__device__ __forceinline__ void umma_bf16_ts_cg2(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-template <bool BWD>
+template <bool BWD, bool FFN_XT>
 __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_constant__ CUtensorMap tmX,
                                                              const __grid_constant__ CUtensorMap tmW1,
                                                              const __grid_constant__ CUtensorMap tmW2,
@@ -117,8 +149,9 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
   uint64_t* z_full = acc2_empty + 1;    // [2]  BWD: the z chunk has landed (local)
   uint64_t* z_empty = z_full + 2;       // [2]  BWD: the epilogue warps have read it (local, 16 arrivals)
   uint64_t* s_bars = z_empty + 2;       // [16][2] BWD + LayerNorm backward: the saved-sum tiles (local)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_bars + 2 * FFN_EPI_WARPS);
-  constexpr int N_BARS = 2 * FFN_RING + 16 + 2 * FFN_EPI_WARPS;
+  uint64_t* xt_full = s_bars + 2 * FFN_EPI_WARPS;   // FFN_XT: both CTAs' epilogue warps have copied x into tensor memory (leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xt_full + 1);
+  constexpr int N_BARS = 2 * FFN_RING + 16 + 2 * FFN_EPI_WARPS + 1;
   const bool store_h = BWD || p.store_zh, store_z = !BWD && p.store_zh;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -143,7 +176,7 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
       uint64_t* b = &ring_full[i];
       uint32_t count = 1;
       if (b == x_empty || b == z_empty || b == z_empty + 1) count = FFN_EPI_WARPS;
-      else if (b == acc1_empty || b == acc1_empty + 1 || b == h_full || b == h_full + 1 || b == acc2_empty) count = 2 * FFN_EPI_WARPS;
+      else if (b == acc1_empty || b == acc1_empty + 1 || b == h_full || b == h_full + 1 || b == acc2_empty || b == xt_full) count = 2 * FFN_EPI_WARPS;
       mbar_init(b, count);
     }
     fence_barrier_init();
@@ -188,9 +221,15 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
         const int m0 = (item * 2 + rank) * 128;
         mbar_wait(x_empty, (it & 1) ^ 1);   // the final epilogue of the previous item has read the residual
         if (it == 0) pdl_wait();
-        if (rank == 0) mbar_arrive_expect_tx(x_full, 2 * FFN_X_BYTES);
+        if (FFN_XT) {   // each CTA's epilogue warps wait for THEIR tile (local barrier) before copying it into tensor memory
+          mbar_arrive_expect_tx(x_full, FFN_X_BYTES);
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) tma_load_2d_cg2(x_s + kb * 16384, &tmX, x_full, kb * 64, m0);
+          for (int kb = 0; kb < 4; ++kb) tma_load_2d(x_s + kb * 16384, &tmX, x_full, kb * 64, m0);
+        } else {
+          if (rank == 0) mbar_arrive_expect_tx(x_full, 2 * FFN_X_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) tma_load_2d_cg2(x_s + kb * 16384, &tmX, x_full, kb * 64, m0);
+        }
         auto load_z = [&](int c) {   // BWD: z[m0 .. +128, c*128 .. +128] -> z_s[zc & 1], two [128 x 64] k-block tiles
           const uint32_t zb = zc & 1;
           mbar_wait(&z_empty[zb], ((zc >> 1) & 1) ^ 1);
@@ -257,11 +296,11 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
         ++hc;
       };
       for (int item = first_item; item < p.n_items; item += item_stride, ++it) {
-        mbar_wait(x_full, it & 1);
+        if (FFN_XT) mbar_wait_cluster(xt_full, it & 1); else mbar_wait(x_full, it & 1);
         tc_fence_after();
         for (int c = 0; c < NC; ++c, ++gc) {
-          const uint32_t b = gc & 1;
-          mbar_wait(&acc1_empty[b], ((gc >> 1) & 1) ^ 1);   // EPI1 two chunks ago has drained this accumulator
+          const uint32_t b = FFN_XT ? 0u : (gc & 1);
+          mbar_wait(&acc1_empty[b], (FFN_XT ? (gc & 1) : ((gc >> 1) & 1)) ^ 1);   // EPI1 two chunks ago (FFN_XT: of the previous chunk) has drained this accumulator
           tc_fence_after();
           if (it == 0) mark(1 + c);
 #pragma unroll
@@ -275,7 +314,10 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
               for (int k = 0; k < 4; ++k) {
                 const uint64_t adesc = make_smem_desc_sw128(x_base + kb * 16384 + k * 32, 0, 1024);
                 const uint64_t bdesc = make_smem_desc_sw128(ring_base + s * FFN_SLOT + kk * 8192 + k * 32, 0, 1024);
-                if (leader) umma_bf16_cg2(tb + b * FFN_FC, adesc, bdesc, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+                if (leader) {
+                  if (FFN_XT) umma_bf16_ts_cg2(tb, tb + FFN_FC + kb * 32 + k * 8, bdesc, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+                  else umma_bf16_cg2(tb + b * FFN_FC, adesc, bdesc, idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+                }
               }
             }
             if (leader) umma_commit_cg2(&ring_empty[s], (uint16_t)3);
@@ -304,9 +346,26 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
       const int m0 = (item * 2 + rank) * 128;
       const int row0 = m0 + q * 32;
       if (it == 0) pdl_wait();
+      if (FFN_XT) {   // x[row, 64 cg .. 64 cg + 64) = k-block cg of the tile: 32 words of bf16 pairs -> tensor-memory columns 128 + 32 cg ..
+        mbar_wait(x_full, it & 1);
+        uint32_t xr[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 v = lds128(x_u32 + cg * 16384 + row * 128 + ((uint32_t(j) ^ sw) << 4));
+          xr[4 * j] = v.x; xr[4 * j + 1] = v.y; xr[4 * j + 2] = v.z; xr[4 * j + 3] = v.w;
+        }
+        tmem_st32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(FFN_FC + cg * 32), xr);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(xt_full); else mbar_arrive_cluster_release(xt_full, 0);
+        }
+      }
       for (int c = 0; c < NC; ++c, ++gc) {
-        const uint32_t b = gc & 1;
-        mbar_wait(&acc1_full[b], (gc >> 1) & 1);
+        const uint32_t zq = gc & 1;                          // z chunk buffer (BWD)
+        const uint32_t b = FFN_XT ? 0u : (gc & 1);           // accumulator
+        mbar_wait(&acc1_full[b], FFN_XT ? (gc & 1) : ((gc >> 1) & 1));
         tc_fence_after();
         if (it == 0 && warp == 2) mark(33 + c);
         uint32_t r[32];
@@ -320,12 +379,12 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const __grid_consta
         const int col0 = c * FFN_FC + cg * 32;   // hidden unit of r[0]
         uint32_t zp[16], hp[16];
         if (BWD) {   // dz = dh * gelu'(z): this lane's 64 bytes of the z chunk the producer prefetched
-          mbar_wait(&z_full[b], (gc >> 1) & 1);
+          mbar_wait(&z_full[zq], (gc >> 1) & 1);
           uint4 zin[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) zin[i] = lds128(z_u32 + b * FFN_HC_BYTES + hz_off + ((uint32_t((cg & 1) * 4 + i) ^ sw) << 4));
+          for (int i = 0; i < 4; ++i) zin[i] = lds128(z_u32 + zq * FFN_HC_BYTES + hz_off + ((uint32_t((cg & 1) * 4 + i) ^ sw) << 4));
           __syncwarp();
-          if (lane == 0) mbar_arrive(&z_empty[b]);
+          if (lane == 0) mbar_arrive(&z_empty[zq]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float v[8];

@@ -350,6 +350,13 @@ int wgrad_group_launch(const WgradGroupPlan* plan, cudaStream_t stream) {
 static long long* g_ffn_trace = nullptr;
 bool ffn_fwd_supported(int H, int FF) { return H == FFN_H && FF >= FFN_FC && FF % FFN_FC == 0; }
 
+// KIT_FFN_XT: bit 0 = forward, bit 1 = backward take the resident tile from tensor memory.  Default OFF: measured no faster
+// (profiles/r02_summary.md: the chunk loop is paced by the 16 epilogue warps -- tcgen05.ld, GELU, pack, store -- not by the
+// tensor pipe, and the single-buffered acc1 the 512 columns then allow costs the training variants 2-5 %).
+static int ffn_xt_mask() {
+  const char* v = getenv("KIT_FFN_XT");
+  return v != nullptr ? atoi(v) : 0;
+}
 int ffn_fwd_plan(FfnPlan* plan, const bf16* x, int64_t ldx, const bf16* w1, int64_t ldw1, const bf16* w2, int64_t ldw2,
                  const float* b1, const float* b2, bf16* z, bf16* hh, int64_t ldzh, bf16* s, int64_t lds, bf16* y, int64_t ldy,
                  const float* gamma, const float* beta, float* mean, float* rstd, float eps, int M, int H, int FF, int store_zh) {
@@ -363,9 +370,13 @@ int ffn_fwd_plan(FfnPlan* plan, const bf16* x, int64_t ldx, const bf16* w1, int6
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, []() {
-    attr_err = cudaFuncSetAttribute(ffn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ffn_smem<false>());
+    attr_err = cudaFuncSetAttribute(ffn_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ffn_smem<false>());
     if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(ffn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ffn_smem<true>());
+      attr_err = cudaFuncSetAttribute(ffn_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ffn_smem<false>());
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(ffn_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ffn_smem<true>());
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(ffn_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ffn_smem<true>());
   });
   KIT_REQUIRE(attr_err == cudaSuccess, "fused FFN: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   if ((rc = make_tensor_map_2d(&plan->tmX, x, (uint64_t)H, (uint64_t)M, (uint64_t)ldx * 2, 64, 128))) return rc;
@@ -385,6 +396,7 @@ int ffn_fwd_plan(FfnPlan* plan, const bf16* x, int64_t ldx, const bf16* w1, int6
   p.store_zh = store_zh;
   p.lnb = LnBwdArgs{nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
   plan->bwd = 0;
+  plan->xt = ffn_xt_mask() & 1;
   p.trace = nullptr;
   if (getenv("KIT_FFN_TRACE") != nullptr) {
     if (g_ffn_trace == nullptr && cudaMalloc(&g_ffn_trace, 256 * sizeof(long long)) != cudaSuccess) g_ffn_trace = nullptr;
@@ -410,6 +422,7 @@ int ffn_bwd_plan(FfnPlan* plan, const bf16* g, int64_t ldg, const bf16* w2t, int
   plan->p.ln_mean = plan->p.ln_rstd = nullptr;
   plan->p.store_zh = 0;
   plan->bwd = 1;
+  plan->xt = (ffn_xt_mask() >> 1) & 1;
   if (lnb != nullptr && lnb->s != nullptr) {
     KIT_REQUIRE(aligned16(lnb->s, lnb->ld_s, 2) && aligned16(lnb->gamma, 0, 4), "fused FFN backward: LayerNorm tensors must be 16-byte aligned");
     plan->p.lnb = *lnb;   // tmY (unused by the backward otherwise) becomes the load map of the saved sum: [32 x 32] boxes
@@ -434,12 +447,15 @@ int ffn_launch(const FfnPlan* plan, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  if (plan->bwd)
-    KIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_kernel<true>, plan->tmX, plan->tmW1, plan->tmW2, plan->tmZ, plan->tmHh, plan->tmS,
-                                      plan->tmY, plan->p));
-  else
-    KIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_kernel<false>, plan->tmX, plan->tmW1, plan->tmW2, plan->tmZ, plan->tmHh, plan->tmS,
-                                      plan->tmY, plan->p));
+#define KIT_FFN_LAUNCH(B, X)                                                                                              \
+  KIT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_kernel<B, X>, plan->tmX, plan->tmW1, plan->tmW2, plan->tmZ, plan->tmHh, plan->tmS, \
+                                    plan->tmY, plan->p))
+  if (plan->bwd) {
+    if (plan->xt) KIT_FFN_LAUNCH(true, true); else KIT_FFN_LAUNCH(true, false);
+  } else {
+    if (plan->xt) KIT_FFN_LAUNCH(false, true); else KIT_FFN_LAUNCH(false, false);
+  }
+#undef KIT_FFN_LAUNCH
   return KIT_OK;
 }
 

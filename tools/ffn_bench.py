@@ -56,6 +56,18 @@ def main():
         K.check(lib.kit_gemm_bf16(0, K.ptr(hs[j]), FF, K.ptr(w2), FF, K.ptr(s), H, M, H, FF, K.ptr(b2), K.ptr(xs[j]), H, K.OUT_BF16,
                                   K.ACT_NONE, None, 0, 1, sp))
 
+    w2t, w1t = w2.t().contiguous(), w1.t().contiguous()
+    gs = [torch.randn(M, H, device=dev).to(bf) for _ in range(nbuf)]
+    dzs = [torch.empty(M, FF, dtype=bf, device=dev) for _ in range(nbuf)]
+    dx = torch.empty(M, H, dtype=bf, device=dev)
+    for zt in zs:
+        zt.copy_(torch.randn(M, FF, device=dev))
+
+    def bwd():
+        j = i[0] % nbuf
+        i[0] += 1
+        K.check(lib.kit_ffn_bwd(K.ptr(gs[j]), K.ptr(w2t), K.ptr(w1t), K.ptr(zs[j]), K.ptr(dzs[j]), K.ptr(dx), M, H, FF, sp))
+
     fl = 4.0 * M * H * FF
     if os.environ.get("FFN_DBG_SWEEP"):
         for dbg, what in ((0, "all on"), (1, "no GELU"), (2, "no GEMM2 MMAs"), (4, "no GEMM1 MMAs"), (6, "no MMAs"), (8, "no h sts"),
@@ -63,7 +75,8 @@ def main():
             os.environ["KIT_FFN_DBG"] = str(dbg)
             print(f"dbg={dbg:2d} {what:28s}: {timeit(fused(0)):8.1f} us")
         return
-    for name, fn in (("fused train (z, h stored)", fused(1)), ("fused inference", fused(0)), ("two GEMMs (gelu + residual, no LN)", two_gemm)):
+    for name, fn in (("fused train (z, h stored)", fused(1)), ("fused inference", fused(0)), ("fused backward (z read, dz stored)", bwd),
+                     ("two GEMMs (gelu + residual, no LN)", two_gemm)):
         us = timeit(fn)
         print(f"{name:40s} M={M} FF={FF}: {us:8.1f} us  {fl / us / 1e6:7.1f} TFLOP/s")
 
