@@ -305,6 +305,7 @@ def gpu_run(args, c):
     torch.manual_seed(42)
     m = model.KeypointCompleter(2 * KP, H, L, NH).to(dev)
     reducer = None
+    step = None
     if is_train:
         m.train()
         use_graph = not args.no_graph     # world > 1: a chain of graphs cut at the all-reduce buckets (train.TrainStep)
@@ -434,6 +435,8 @@ def gpu_run(args, c):
     eager_ms /= prof_steps
     if rank != 0:
         if world > 1:
+            if step is not None and hasattr(step, "release_graphs"):
+                step.release_graphs()
             dist.barrier()
             dist.destroy_process_group()
         return
@@ -541,6 +544,8 @@ def gpu_run(args, c):
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
+        if step is not None and hasattr(step, "release_graphs"):
+            step.release_graphs()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -56,6 +56,10 @@ class TrainStep:
             raise ValueError("use_graph=True needs FlatAdam(capturable=True): the step count must live on the device")
         self._graphs = {}        # (input pointers, shape) -> (CUDAGraph, static loss)
         self._eager_calls = 0
+        # KIT_DP_SINGLE_GRAPH=1: capture the data-parallel step as ONE graph holding the NCCL all-reduces (side-stream fork /
+        # join inside the capture) instead of the chain.  release_graphs() must run before destroy_process_group().
+        import os
+        self.single_graph = os.environ.get("KIT_DP_SINGLE_GRAPH", "0") == "1"
         self.kind = {"mse": K.LOSS_MSE, "euclid": K.LOSS_EUCLID, "distance": K.LOSS_DISTANCE}[criterion]
         self.zero_masked = zero_masked
         self.reducer = reducer
@@ -261,7 +265,7 @@ class TrainStep:
             graph = torch.cuda.CUDAGraph()
             steps_before = self.optimizer.step_count
             try:
-                if self.reducer is not None:
+                if self.reducer is not None and not self.single_graph:
                     graph, loss = self._capture_chain(*batch)
                 else:
                     with torch.cuda.graph(graph):
@@ -277,12 +281,18 @@ class TrainStep:
             entry = (graph, loss, batch)                          # keep the buffers alive
             self._graphs[key] = entry
         self.optimizer.sync_host_values()
-        if self.reducer is not None:
+        if isinstance(entry[0], list):
             self._replay_chain(entry[0])          # (the optimiser is stepped between the replays and counts its own steps)
         else:
             entry[0].replay()
             self.optimizer.step_count += 1
         return entry[1]
+
+    def release_graphs(self):
+        """Drops the captured graphs (call before ``destroy_process_group()`` when a graph holds collectives)."""
+        torch.cuda.synchronize()
+        self._graphs.clear()
+        torch.cuda.synchronize()
 
 
 class RawTrainStep(TrainStep):

@@ -3,7 +3,7 @@
 N=$1
 run() {
   name=$1; shift
-  env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/dp_$name.json 2> gpurun_out/dp_$name.err
+  env "$@" timeout -k 10 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/dp_$name.json 2> gpurun_out/dp_$name.err
   python - "$name" <<'PY'
 import json, sys
 name = sys.argv[1]
@@ -17,6 +17,11 @@ except Exception as e:
     print(open(f"gpurun_out/dp_{name}.err").read()[-1500:])
 PY
 }
+if [ "$2" = "sg" ]; then
+run chain KIT_DP_SINGLE_GRAPH=0
+run single KIT_DP_SINGLE_GRAPH=1
+exit 0
+fi
 if [ "$2" = "v2" ]; then
 run bf16_b0 KIT_BUCKET_LAYERS=0
 run bf16_b2 KIT_BUCKET_LAYERS=2
