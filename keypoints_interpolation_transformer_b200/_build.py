@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkit_b200.so")
-SOURCES = ["errors.cu", "gemm.cu", "rowops.cu", "attention.cu", "attention_tc.cu", "attention_t64.cu", "framepass.cu", "cubic.cu", "probe.cu", "engine.cu"]
+SOURCES = ["errors.cu", "gemm.cu", "rowops.cu", "attention.cu", "attention_tc.cu", "attention_tcb.cu", "attention_t64.cu", "framepass.cu", "cubic.cu", "probe.cu", "engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -1266,6 +1266,25 @@ int attention_bwd(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const 
     if (attention_t64_supported(NH, Sq, Sk, d, mask, ptrs, lds, 7))
       return attention_t64_bwd(q, ldq, k, ldk, v, ldv, dout, ld_do, lse, dq, ld_dq, dk, ld_dk, dv, ld_dv, B, NH, Sq, Sk, mask, st);
   }
+  {
+    const void* ptrs[6] = {q, k, v, dout, dk, dv};
+    const int64_t lds[6] = {ldq, ldk, ldv, ld_do, ld_dk, ld_dv};
+    if (attention_bwd_tc_supported(NH, Sq, Sk, d, mask, ptrs, lds, 6, dq_acc)) {   // long sequences on tcgen05 (attention_tcb.cu)
+      const int64_t n_rows = (int64_t)B * Sq, n = n_rows * NH * d;
+      KIT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)n * sizeof(float), st));
+      float* delta = dq_acc + n;   // workspace tail: [B, NH, Sq]
+      if (d == 32)
+        launch_kernel(attn_delta_kernel<32>, dim3((unsigned)ceil_div(n_rows * NH, 256)), dim3(256), 0, st, o, ldo, dout, ld_do, delta, NH, Sq, n_rows);
+      else
+        launch_kernel(attn_delta_kernel<64>, dim3((unsigned)ceil_div(n_rows * NH, 256)), dim3(256), 0, st, o, ldo, dout, ld_do, delta, NH, Sq, n_rows);
+      KIT_LAUNCH_CHECK();
+      rc = attention_bwd_tc(q, ldq, k, ldk, v, ldv, dout, ld_do, lse, delta, dq_acc, dk, ld_dk, dv, ld_dv, B, NH, Sq, Sk, d, mask, st);
+      if (rc) return rc;
+      launch_kernel(dq_convert_kernel, dim3((unsigned)ceil_div(n / 8, 256)), dim3(256), 0, st, (const float*)dq_acc, dq, ld_dq, n_rows, NH * d);
+      KIT_LAUNCH_CHECK();
+      return KIT_OK;
+    }
+  }
   const MaskDev md = to_dev(mask);
   switch (d) {
     case 16: return bwd_launch<16>(q, ldq, k, ldk, v, ldv, o, ldo, dout, ld_do, lse, dq, ld_dq, dk, ld_dk, dv, ld_dv, dq_acc, B, NH, Sq, Sk, md, st);

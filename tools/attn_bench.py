@@ -76,7 +76,7 @@ def bench_bwd(B, NH, S, d, flags, n=10):
     us = a.elapsed_time(b) / n * 1e3
     fl = 10.0 * B * NH * S * S * d
     print(f"attention bwd B={B} NH={NH} S={S} d={d}: {us:9.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  "
-          f"(KIT_ATTN_T64={os.environ.get('KIT_ATTN_T64', '1')})")
+          f"(KIT_ATTN_T64={os.environ.get('KIT_ATTN_T64', '1')} KIT_ATTN_TC={os.environ.get('KIT_ATTN_TC', '1')})")
 
 
 if __name__ == "__main__":
@@ -86,6 +86,13 @@ if __name__ == "__main__":
             print(f"KIT_ATTN_T64={env}")
             bench(256, 8, 64, 32, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD, n=50)
             bench_bwd(256, 8, 64, 32, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD, n=50)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "long":    # long-sequence backward: tcgen05 (attention_tcb.cu) against the mma.sync streaming kernel
+        for env in ("1", "0"):
+            os.environ["KIT_ATTN_TC"] = env
+            bench_bwd(64, 8, 512, 64, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD)
+            bench_bwd(256, 8, 256, 32, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD)
+            bench_bwd(16, 8, 2048, 64, K.MASK_REPEAT_INC)
         sys.exit(0)
     bench(64, 8, 512, 64, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD)
     bench(1024, 8, 256, 32, K.MASK_REPEAT_INC | K.MASK_KEYPAD_ADD)
