@@ -17,6 +17,14 @@ except Exception as e:
     print(open(f"gpurun_out/dp_{name}.err").read()[-1500:])
 PY
 }
+if [ "$2" = "final" ]; then
+run final_r8 KIT_COLLECTIVE_SMS=8
+run final_r16 KIT_COLLECTIVE_SMS=16
+env timeout -k 10 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --config scaled > gpurun_out/r02_scaled_dp$N.json 2> gpurun_out/r02_scaled_dp$N.err
+python -c "
+import json; d=json.load(open('gpurun_out/r02_scaled_dp$N.json')); print('scaled', d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'])" || tail -c 1500 gpurun_out/r02_scaled_dp$N.err
+exit 0
+fi
 if [ "$2" = "sg" ]; then
 run chain KIT_DP_SINGLE_GRAPH=0
 run single KIT_DP_SINGLE_GRAPH=1
