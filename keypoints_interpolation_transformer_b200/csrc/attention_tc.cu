@@ -306,7 +306,11 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
       if (lane == 0) mbar_arrive(&s_free[sl]);
       half(16);
       const float mx = fmaxf(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), fmaxf(fmaxf(mx4[4], mx4[5]), fmaxf(mx4[6], mx4[7])));
-      const float m_new = fmaxf(m_run, mx);
+      // Lazy rescale: a stale reference is as good as the true row maximum while x - m_ref stays small (P <= 2^8 is exact enough
+      // in bf16, l and O are fp32), so the running sum and O_g (a tcgen05.ld / st round trip) are rescaled only when some row of
+      // the warp has a new maximum more than 2^8 above its reference -- after the first tiles that is rare.
+      const bool any_grow = __any_sync(0xffffffffu, mx > m_run + 8.f);
+      const float m_new = any_grow ? fmaxf(m_run, mx) : m_run;
       const float m_ref = (m_new == -INFINITY) ? 0.f : m_new;
       const float corr = ex2f(m_run - m_ref);
       uint64_t rs2[4] = {pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f), pk2(0.f, 0.f)};
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
       // the previous step of this slot has been accumulated (P buffer free); the previous tile of this head too (O stable)
       if (n >= 2) mbar_wait(&pv_done[sl], ((n - 2) >> 1) & 1);
       tc_fence_after();
-      if (j > 0) {   // O_g *= corr (this head's D columns)
+      if (j > 0 && any_grow) {   // O_g *= corr (this head's D columns)
 #pragma unroll
         for (int c = 0; c < D / 32; ++c) {
           uint32_t o[32];

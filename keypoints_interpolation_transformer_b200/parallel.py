@@ -33,7 +33,9 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
-COLLECTIVE_SMS = int(os.environ.get("KIT_COLLECTIVE_SMS", "8"))
+# SMs left to NCCL's kernels (and NCCL_MAX_CTAS): 8 on 2 GPUs, 16 from 4 GPUs up (8 GPUs: 4.30 ms per step against 4.35 with 8,
+# profiles/r02_dp.md)
+COLLECTIVE_SMS = int(os.environ.get("KIT_COLLECTIVE_SMS", "16" if int(os.environ.get("WORLD_SIZE", "1")) >= 4 else "8"))
 
 
 def reserve_sms_for_collectives(n=None):
