@@ -143,9 +143,29 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    // The whole warp runs the loop on warp-uniform values and issues every tcgen05 instruction under an elect.sync predicate
+    // (operands stay in uniform registers, consecutive UTCHMMA are back to back -- attention_t64.cu), and the barriers are PROBED
+    // (mbarrier.test_wait): try_wait may suspend the thread for a system-dependent time, which stalled the ready queue behind
+    // the other one.
+    {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, false, false);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);   // B = V tile [keys][64 columns]: MN-major
+      uint32_t el;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(el));
+      const bool leader = el != 0;
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      auto probe = [&](uint64_t* bar, uint32_t parity) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        return ok != 0;
+      };
+      auto uniform = [&](bool v) { return __shfl_sync(0xffffffffu, (int)v, 0) != 0; };
       auto issue_pv = [&](int m, int j, int jt, int g) {   // O_g += P[m & 1] V_j   (m = global step)
         const int sl = m & 1;
         tc_fence_after();
@@ -154,25 +174,31 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
         for (int kk = 0; kk < 8; ++kk) {   // 16 keys per MMA
           const uint64_t adesc = make_smem_desc_sw128(p_base + (kk >> 2) * ATC_TILE + (kk & 3) * 32, 0, 1024);
           const uint64_t bdesc = make_smem_desc_sw128(v_base + kk * 16 * 128, 64 * 128, 1024);
-          umma_bf16(tmem_base + 256 + g * 64, adesc, bdesc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          if (leader) umma_bf16(tb + 256 + g * 64, adesc, bdesc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
         }
-        umma_commit(&pv_done[sl]);
-        if (g == G - 1) umma_commit(&kv_empty[jt & 1]);   // every MMA that reads this K / V stage has been issued
+        if (leader) {
+          umma_commit(&pv_done[sl]);
+          if (g == G - 1) umma_commit(&kv_empty[jt & 1]);   // every MMA that reads this K / V stage has been issued
+        }
       };
       // Two in-order queues, issued as their inputs become ready: Q K^T of step n needs its score slot drained (s_free, early in
-      // step n - 2 of the same group) and the K / V stage; P V of step m needs P (p_full, the end of softmax step m).  Issuing
-      // strictly QK(n), PV(n - 1), QK(n + 1), ... made every group wait ~1.3 k cycles for a score tile that could have been ready.
+      // step n - 2 of the same group) and the K / V stage; P V of step m needs P (p_full, the end of softmax step m).  The score
+      // product of step n + 2 is issued as soon as step n's scores are in registers, so it is complete long before its group asks.
       const int n_units = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const int total = n_units * NS;
       int qk = 0, pv = 0;
+      uint32_t idle = 0;
       while (pv < total) {
-        bool progressed = false;
-        if (qk < total && qk < pv + 2) {
+        if (++idle > (1u << 27)) {   // a protocol bug becomes a trap instead of a hang
+          if (leader) printf("kit: attn_fwd_tc MMA queue stalled (block %d, qk %d, pv %d of %d)\n", blockIdx.x, qk, pv, total);
+          __trap();
+        }
+        if (qk < total) {
           const int iuq = qk / NS, ns = qk % NS, j = ns / G, g = ns % G, sl = qk & 1, jt = iuq * p.n_ktiles + j;
-          bool ready = mbar_try_wait(&s_free[sl], ((qk >> 1) & 1) ^ 1);
-          if (ready && ns == 0) ready = mbar_try_wait(&q_full[iuq & 1], (iuq >> 1) & 1);
-          if (ready && g == 0) ready = mbar_try_wait(&kv_full[jt & 1], (jt >> 1) & 1);
-          if (ready) {
+          bool ready = probe(&s_free[sl], ((qk >> 1) & 1) ^ 1);
+          if (ready && ns == 0) ready = probe(&q_full[iuq & 1], (iuq >> 1) & 1);
+          if (ready && g == 0) ready = probe(&kv_full[jt & 1], (jt >> 1) & 1);
+          if (uniform(ready)) {
             tc_fence_after();
             const uint32_t q_buf = smem_u32(s.q[iuq & 1][0]), k_base = smem_u32(s.k[jt & 1]);
 #pragma unroll
@@ -181,23 +207,24 @@ __global__ void __launch_bounds__(64 + 256, 1) attn_fwd_tc_kernel(const __grid_c
               const uint32_t a_off = (D == 64) ? g * ATC_TILE : g * D * 2, b_off = (D == 64) ? 0 : g * D * 2;
               const uint64_t adesc = make_smem_desc_sw128(q_buf + a_off + kk * 32, 0, 1024);
               const uint64_t bdesc = make_smem_desc_sw128(k_base + b_off + kk * 32, 0, 1024);
-              umma_bf16(tmem_base + sl * 128, adesc, bdesc, idesc_qk, kk > 0 ? 1u : 0u);
+              if (leader) umma_bf16(tb + sl * 128, adesc, bdesc, idesc_qk, kk > 0 ? 1u : 0u);
             }
-            umma_commit(&s_full[sl]);
-            if (ns == NS - 1) umma_commit(&q_empty[iuq & 1]);   // the producer may refill this Q buffer
+            if (leader) {
+              umma_commit(&s_full[sl]);
+              if (ns == NS - 1) umma_commit(&q_empty[iuq & 1]);   // the producer may refill this Q buffer
+            }
             ++qk;
-            progressed = true;
+            idle = 0;
           }
         }
         if (pv < qk) {
           const int iup = pv / NS, ns = pv % NS, j = ns / G, g = ns % G, jt = iup * p.n_ktiles + j;
-          if (mbar_try_wait(&p_full[pv & 1], (pv >> 1) & 1)) {
+          if (uniform(probe(&p_full[pv & 1], (pv >> 1) & 1))) {
             issue_pv(pv, j, jt, g);
             ++pv;
-            progressed = true;
+            idle = 0;
           }
         }
-        (void)progressed;
       }
     }
     __syncwarp();
