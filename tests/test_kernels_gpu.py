@@ -233,6 +233,54 @@ def _attention_case(B, NH, S, d, flags, explicit):
     assert _rel(heads(dq[:, 2 * H:]), vf.grad) < 2e-2
 
 
+@pytest.mark.parametrize("B,NH,Sq,Sk,d,flags", [
+    (2, 4, 130, 200, 64, K.MASK_KEYPAD_ADD), (3, 8, 256, 100, 32, 0), (2, 2, 70, 300, 64, K.MASK_KEYPAD_ADD),
+    (2, 4, 300, 129, 32, K.MASK_KEYPAD_ADD)])
+def test_attention_cross_lengths(B, NH, Sq, Sk, d, flags, monkeypatch):
+    """Query and key sequences of different lengths (the cross-attention call shape of the decoder layers, model.py:141-145 ->
+    torch/nn/modules/transformer.py:1147, when encoder and decoder inputs differ in length): the tcgen05 long-sequence forward
+    (attention_tc.cu) and backward (attention_tcb.cu), then the mma.sync kernels, against fp32 torch."""
+    for tc in ("1", "0"):
+        monkeypatch.setenv("KIT_ATTN_TC", tc)
+        H = NH * d
+        g = torch.Generator(device="cpu").manual_seed(B * 1000 + Sq + Sk)
+        q = _bf(torch.randn(B * Sq, H, generator=g)).to(DEV)
+        kv = _bf(torch.randn(B * Sk, 2 * H, generator=g)).to(DEV)
+        dout = _bf(torch.randn(B * Sq, H, generator=g)).to(DEV)
+        fm = (torch.rand(B, Sk, generator=g) < 0.4).float().to(DEV)
+        mask = K.KitAttnMask()
+        bias = None
+        if flags:
+            mask.frame_mask = fm.data_ptr()
+            mask.frame_mask_stride = Sk
+            mask.flags = flags
+            bias = _mask_bias(fm, flags, Sq, Sk)[:, None]
+        out = torch.empty(B * Sq, H, dtype=torch.bfloat16, device=DEV)
+        lse = torch.empty(B, NH, Sq, device=DEV)
+        lib = K.lib()
+        k, v = kv[:, :H], kv[:, H:]
+        K.check(lib.kit_attention_fwd(K.ptr(q), H, K.ptr(k), 2 * H, K.ptr(v), 2 * H, K.ptr(out), H, K.ptr(lse), B, NH, Sq, Sk, d,
+                                      C.byref(mask), _sp()))
+        dq = torch.empty(B * Sq, H, dtype=torch.bfloat16, device=DEV)
+        dkv = torch.empty(B * Sk, 2 * H, dtype=torch.bfloat16, device=DEV)
+        dq_acc = torch.empty(B * Sq * H + B * NH * Sq, device=DEV)
+        K.check(lib.kit_attention_bwd(K.ptr(q), H, K.ptr(k), 2 * H, K.ptr(v), 2 * H, K.ptr(out), H, K.ptr(dout), H, K.ptr(lse),
+                                      K.ptr(dq), H, K.ptr(dkv[:, :H]), 2 * H, K.ptr(dkv[:, H:]), 2 * H, K.ptr(dq_acc), B, NH, Sq, Sk, d,
+                                      C.byref(mask), _sp()))
+        torch.cuda.synchronize()
+
+        def heads(x, S):
+            return x.float().view(B, S, NH, d).transpose(1, 2)
+        qf = heads(q, Sq).detach().requires_grad_(True)
+        kf, vf = (heads(t, Sk).detach().requires_grad_(True) for t in (k, v))
+        ref = _attn_ref(qf, kf, vf, bias)
+        ref.backward(heads(dout, Sq))
+        assert _rel(heads(out, Sq), ref) < 1e-2, tc
+        assert _rel(heads(dq, Sq), qf.grad) < 2e-2, tc
+        assert _rel(heads(dkv[:, :H], Sk), kf.grad) < 2e-2, tc
+        assert _rel(heads(dkv[:, H:], Sk), vf.grad) < 2e-2, tc
+
+
 # ------------------------------------------------------------------------------- LayerNorm
 @pytest.mark.parametrize("M,H", [(1000, 256), (333, 64), (512, 512), (64, 1024), (16384, 256), (40000, 256)])
 def test_add_layernorm_fwd_bwd(M, H):
