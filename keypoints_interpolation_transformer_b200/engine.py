@@ -70,6 +70,12 @@ class StepEngine:
 
     def __init__(self, layout: ModelLayout, batch, seq_len, params, grads, training=True):
         assert params.is_cuda and params.dtype == torch.float32 and params.numel() >= layout.total
+        # The library keeps its one-time state (shared-memory attributes, SM count) for the device the process uses and launches
+        # on the CURRENT device's stream (one process per GPU, as under torchrun): a model on another device is an error, not a
+        # silent launch on the wrong stream.
+        if params.device.index is not None and params.device.index != torch.cuda.current_device():
+            raise K.KitError(f"the model lives on cuda:{params.device.index} but the current device is cuda:{torch.cuda.current_device()}: "
+                             "call torch.cuda.set_device() first (one process per GPU)")
         self.layout = layout
         self.batch, self.seq_len, self.training = batch, seq_len, training
         self._h = C.c_void_p()
