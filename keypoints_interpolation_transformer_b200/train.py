@@ -338,7 +338,7 @@ class RawTrainStep(TrainStep):
                 self.reducer.finish()
         else:
             eng.backward(dpred)
-        self.last_launches = eng.fwd_launches + eng.bwd_launches + 3 + 5      # + policy (3) and pre-pass (2) launches
+        self.last_launches = eng.fwd_launches + eng.bwd_launches + 3 + 2 + (1 if B <= 512 else 2)   # + policy (2) and pre-pass (1; 2 beyond 512 sequences) launches
         return loss
 
 
