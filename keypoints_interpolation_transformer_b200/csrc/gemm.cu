@@ -179,6 +179,16 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
   const size_t esize = (out_kind == OUT_BF16) ? 2 : 4;
   int epi = EPI_GENERIC;
   const bool c_ok = aligned16(C, ldc, esize) && (bias == nullptr || (N % 8) == 0);
+  // fp32 rows of an even number of floats that TMA cannot address (row starts only 8-byte aligned, e.g. N = ldc = 142): the staged
+  // EPI_F32 epilogue with a coalesced copy-out by the warp instead of the per-lane scalar path
+  const bool manual_ok = !c_ok && out_kind != OUT_BF16 && act == ACT_NONE && addend == nullptr && (ldc % 2) == 0 &&
+                         (reinterpret_cast<uintptr_t>(C) & 7) == 0 && (bias == nullptr || aligned16(bias, 0, 4)) && bias_grad == nullptr &&
+                         getenv("KIT_GEMM_NO_MANUAL_OUT") == nullptr;
+  p.manual_out = 0;
+  if (manual_ok) {
+    epi = EPI_F32;
+    p.manual_out = 1;
+  }
   if (c_ok) {
     if (out_kind != OUT_BF16) {
       if (act == ACT_NONE && addend == nullptr) epi = EPI_F32;
@@ -212,7 +222,9 @@ int gemm_plan(GemmPlan* plan, int mode, const bf16* A, int64_t lda, const bf16* 
   }
   plan->tmC = plan->tmA;
   plan->tmAux = plan->tmA;
-  if (epi == EPI_F32) {
+  if (epi == EPI_F32 && p.manual_out) {
+    // no tensor map for C: the warp copies the staged tile out itself
+  } else if (epi == EPI_F32) {
     if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   } else if (epi != EPI_GENERIC) {
     if ((rc = make_tensor_map_2d_typed(&plan->tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, C, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;

@@ -72,6 +72,9 @@ struct GemmParams {
   float ln_eps;
   LnBwdArgs lnb;      // EPI_ADD_LNBWD
   float* bias_grad;   // MODE 1, BG kernels: bias_grad[m] += sum_k A[k, m] (column sums of dy), else null
+  int manual_out;     // EPI_F32 over fp32 rows a tensor map cannot describe (pitch a multiple of 8 but not of 16 bytes: the 142-wide
+                      // prediction and embedding gradients; TMA needs 16-byte aligned row starts): the staged [32 x 32] tile leaves
+                      // by coalesced 8-byte stores / vector reductions, two rows of 128 bytes per warp instruction
   long long* trace;   // experiments only (KIT_GEMM_TRACE): clock64 marks of CTA 0, see kit_gemm_trace_read
 };
 
@@ -237,11 +240,17 @@ __device__ __forceinline__ void gemm_epilogue_sub(const GemmParams& p, int col0,
     float v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[8 * i + u]);
-    if (p.bias != nullptr && col0 + 8 * i < p.N) {   // TMA kinds with a bias have N % 8 == 0 (planner)
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * i));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * i + 4));
-      add_pair(v[0], v[1], b0.x, b0.y); add_pair(v[2], v[3], b0.z, b0.w);
-      add_pair(v[4], v[5], b1.x, b1.y); add_pair(v[6], v[7], b1.z, b1.w);
+    if (p.bias != nullptr && col0 + 8 * i < p.N) {   // TMA kinds with a bias have N % 8 == 0 (planner); manual_out may end mid-chunk
+      if (EPI != EPI_F32 || col0 + 8 * i + 8 <= p.N) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * i));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * i + 4));
+        add_pair(v[0], v[1], b0.x, b0.y); add_pair(v[2], v[3], b0.z, b0.w);
+        add_pair(v[4], v[5], b1.x, b1.y); add_pair(v[6], v[7], b1.z, b1.w);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (col0 + 8 * i + u < p.N) v[u] += __ldg(p.bias + col0 + 8 * i + u);
+      }
     }
     if (EPI == EPI_F32) {
       const uint32_t row128 = t_out + lane * 128, sw128 = lane & 7;
@@ -870,9 +879,37 @@ __global__ void __launch_bounds__(gemm_threads<BN>(), 1) gemm_tcgen05_kernel(con
             tma_store_2d_a(&tmAux, t_aux[sub], col0, row0);
             tma_store_commit();
           }
-          if (EPI == EPI_F32 && p.out_kind == OUT_F32_ATOMIC) tma_reduce_add_2d_a(&tmC, t_sub[sub], col0, row0);
-          else tma_store_2d_a(&tmC, t_sub[sub], col0, row0);
-          tma_store_commit();
+          if (EPI == EPI_F32 && p.manual_out) {
+            // (copied out below by the whole warp)
+          } else {
+            if (EPI == EPI_F32 && p.out_kind == OUT_F32_ATOMIC) tma_reduce_add_2d_a(&tmC, t_sub[sub], col0, row0);
+            else tma_store_2d_a(&tmC, t_sub[sub], col0, row0);
+            tma_store_commit();
+          }
+        }
+        if (EPI == EPI_F32 && p.manual_out) {
+          // lanes 0..15: row r, lanes 16..31: row r + 1; lane l: columns col0 + 2 (l & 15) .. + 1 of the staged tile (SWIZZLE_128B
+          // layout: 16-byte chunk c of row r at chunk c ^ (r & 7))
+          const int half = lane >> 4, l2 = (lane & 15) * 2, col = col0 + l2;
+          float* cbase = reinterpret_cast<float*>(p.C);
+#pragma unroll 4
+          for (int r = 0; r < 32; r += 2) {
+            const int rr = r + half, row = row0 + rr;
+            const uint32_t addr = t_sub[sub] + rr * 128 + ((uint32_t(l2 >> 2) ^ uint32_t(rr & 7)) << 4) + (l2 & 3) * 4;
+            float2 val;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(val.x), "=f"(val.y) : "r"(addr));
+            if (row < p.M && col < p.N) {
+              float* dst = cbase + (int64_t)row * p.ldc + col;
+              if (col + 1 < p.N) {
+                if (p.out_kind == OUT_F32_ATOMIC) asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(val.x), "f"(val.y) : "memory");
+                else *reinterpret_cast<float2*>(dst) = val;
+              } else {
+                if (p.out_kind == OUT_F32_ATOMIC) atomicAdd(dst, val.x);
+                else *dst = val.x;
+              }
+            }
+          }
+          __syncwarp();   // the tile is free for the next half
         }
         if (it == 0 && warp == 2 && sub == 0) mark(8);
       }

@@ -30,7 +30,9 @@ def _bf(x):
 
 # ------------------------------------------------------------------------------- GEMM (tcgen05)
 @pytest.mark.parametrize("M,N,Kd", [(128, 128, 64), (256, 128, 256), (300, 200, 144), (1000, 768, 256),
-                                    (16384, 256, 256), (2048, 256, 2048), (1024, 2048, 256), (515, 142, 256)])
+                                    (16384, 256, 256), (2048, 256, 2048), (1024, 2048, 256), (515, 142, 256),
+                                    # fp32 rows of 142 floats (pitch 568 B): even M takes the row-pair TMA epilogue, odd M the scalar one
+                                    (512, 142, 256), (16384, 142, 256), (130, 70, 64)])
 def test_gemm_tn_bias(M, N, Kd):
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
     a = _bf(torch.randn(M, Kd, generator=g)).to(DEV)
