@@ -652,15 +652,16 @@ static int swiglu_fwd(KitEngine* e, const bf16* x, const SwiW& s, bf16* x12, bf1
   KIT_TRY(swiglu_gate_fwd(x12, g, e->M, H, e->st));
   return linear_fwd(e, g, H, s.fc3, 0, H, out, H, nullptr, 0);
 }
-// dout -> dx (into dx_out); uses g2h / a scratch [M,H]
+// dout -> dx (into dx_out); uses g2h / a scratch [M,H].  The two weight gradients are QUEUED (pend): the caller flushes them as one
+// grouped launch while dout and g2h are still intact (each was a single 9.5 us launch on the critical path of the step).
 static int swiglu_bwd(KitEngine* e, const bf16* dout, const bf16* x, const SwiW& s, const bf16* x12, const bf16* g,
-                      bf16* scratch, bf16* dx_out) {
+                      bf16* scratch, bf16* dx_out, std::vector<PendingW>& pend) {
   const int H = e->L.cfg.hidden;
-  KIT_TRY(linear_wgrad(e, dout, H, g, H, s.fc3, 0, H));
+  pend.push_back({dout, H, g, H, &s.fc3, 0, H, false});
   KIT_TRY(linear_dgrad(e, dout, H, s.fc3, 0, H, scratch, H, nullptr, 0));
   e->launches++;
   KIT_TRY(swiglu_gate_bwd(scratch, x12, e->g2h, e->M, H, e->st));
-  KIT_TRY(linear_wgrad(e, e->g2h, 2 * H, x, H, s.fc12, 0, 2 * H));
+  pend.push_back({e->g2h, 2 * H, x, H, &s.fc12, 0, 2 * H, false});
   return linear_dgrad(e, e->g2h, 2 * H, s.fc12, 0, 2 * H, dx_out, H, nullptr, 0);
 }
 
@@ -758,12 +759,13 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
   // ---- output head
   e->launches++;
   KIT_TRY(cast_pad(dpred, M, IN, IN, e->dp, e->K2p, e->st));
-  KIT_TRY(linear_wgrad(e, e->dp, e->K2p, e->sf, H, L.fc_final, 0, IN));
+  pend.push_back({e->dp, e->K2p, e->sf, H, &L.fc_final, 0, IN, false});
   KIT_TRY(eg(e, 0, e->dp, e->K2p, e->wb + L.fc_final.wbT, L.fc_final.ldT, e->g0, H, (int)M, H, e->K2p, nullptr, nullptr, 0,
              OUT_BF16, ACT_NONE, nullptr, 0));
   e->launches++;
   KIT_TRY(final_norm_silu_bwd(e->g0, e->zf, e->g3, M, H, e->st));  // g3 = d(zf): kept for the embedding residual
-  KIT_TRY(swiglu_bwd(e, e->g3, e->dec_out, L.swi_d, e->sd12, e->sdg, e->g0, e->g1));  // g1 = d dec_out
+  KIT_TRY(swiglu_bwd(e, e->g3, e->dec_out, L.swi_d, e->sd12, e->sdg, e->g0, e->g1, pend));  // g1 = d dec_out
+  KIT_TRY(flush_wgrads(e, pend));   // fc_final + the head's SwiGLU: dp, g3 and g2h are intact
   e->launches++;
   KIT_TRY(ln_bwd(e->g1, e->da[nl - 1].y3, e->st_decn, e->st_decn + M, e->params + L.dec_norm.g, nullptr, e->g0,
                  e->grads + L.dec_norm.g, e->grads + L.dec_norm.b, nullptr, M, H, e->st));
@@ -816,7 +818,8 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
   }
   done();  // decoder finished
   // filled branch: SwiGLU, token-norm/PE, embedding  (g3 = residual gradient from the head)
-  KIT_TRY(swiglu_bwd(e, dy, e->ef, L.swi_f, e->sf12, e->sfg, e->g1, e->g2));  // g2 = d ef
+  KIT_TRY(swiglu_bwd(e, dy, e->ef, L.swi_f, e->sf12, e->sfg, e->g1, e->g2, pend));  // g2 = d ef
+  KIT_TRY(flush_wgrads(e, pend));   // (dy = g0 and g2h are intact)
   e->launches++;
   const float ns = L.cfg.variant == KIT_MODEL_CYCLE ? 2.f : 1.f;
   KIT_TRY(embed_post_bwd(e->g2, e->ef_raw, e->g3, e->g1, e->grads + L.learned_f, M, H, ns, e->st));  // g1 = d ef_raw
@@ -863,7 +866,8 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
     if (L.enc_cut[l]) done();
   }
   // input branch
-  KIT_TRY(swiglu_bwd(e, dx, e->ei, L.swi_i, e->si12, e->sig, e->g1, e->g2));
+  KIT_TRY(swiglu_bwd(e, dx, e->ei, L.swi_i, e->si12, e->sig, e->g1, e->g2, pend));
+  KIT_TRY(flush_wgrads(e, pend));
   e->launches++;
   KIT_TRY(embed_post_bwd(e->g2, e->ei_raw, nullptr, e->g1, e->grads + L.learned_i, M, H, ns, e->st));
   KIT_TRY(eg(e, 1, e->g1, H, e->xe, e->K2p, e->grads + L.emb_i.w, IN, H, IN, (int)M, nullptr, nullptr, 0, OUT_F32_ATOMIC,
