@@ -21,6 +21,7 @@ Rank 0 prints ONE JSON line.  Beside the kit numbers the line carries
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -278,6 +279,56 @@ def dp_grad_check(rank, world, dev, c):
 # --------------------------------------------------------------------------------------------
 # GPU leg
 # --------------------------------------------------------------------------------------------
+def in_graph_timeline(run, batches, replays=4):
+    """Critical-path attribution of ONE replayed step from CUPTI kernel activity records (torch.profiler; no serialisation or
+    cache flush as under ncu, no launch gaps as in the kernel-by-kernel leg): with programmatic dependent launch every kernel of
+    the chain starts early and waits for its predecessor, so a kernel's contribution to the step is its END minus the previous
+    END; the contributions add up to the span of the replay.  Returns None when CUPTI is not available."""
+    try:
+        import torch
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(replays):
+                run(batches[i % len(batches)])
+            torch.cuda.synchronize()
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start
+               and "memcpy" not in e.name.lower() and "memset" not in e.name.lower()]
+        if len(evs) < replays or len(evs) % replays:
+            return None
+        evs.sort(key=lambda e: e.time_range.start)
+        n_per = len(evs) // replays
+        one = sorted(evs[(replays - 2) * n_per:(replays - 1) * n_per], key=lambda e: e.time_range.end)
+        prev = min(e.time_range.start for e in one)
+        t0, agg = prev, {}
+        for e in one:
+            name = re.sub(r"\(.*", "", e.name).replace("void kit::", "").replace("kit::", "")[:64]
+            a = agg.setdefault(name, [0, 0.0])
+            a[0] += 1
+            a[1] += max(0.0, e.time_range.end - prev)
+            prev = max(prev, e.time_range.end)
+        span = prev - t0
+        return {"span_us": span, "kernels": n_per,
+                "by_kernel": {k: {"launches": v[0], "us": round(v[1], 1), "share": round(v[1] / span, 4)}
+                              for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
+                "method": "CUPTI kernel records of one CUDA-graph replay; per kernel: end - previous end (sums to span_us)"}
+    except Exception as exc:   # noqa: BLE001 -- a supplementary leg must not cost the bench line
+        return {"unavailable": repr(exc)[:200]}
+
+
+def in_graph_roofline(timeline, flops_per_launch, peak_tf):
+    """The dominant kernel's rate INSIDE the replayed step (in_graph_timeline: end - previous end per launch, so neither the launch
+    gaps of the kernel-by-kernel leg nor the cold caches of ncu): supplementary to `achieved`, which keeps the CUDA-event figure."""
+    if not timeline or "by_kernel" not in timeline or not flops_per_launch:
+        return None
+    us = sum(v["us"] for k, v in timeline["by_kernel"].items() if k.startswith("ffn_kernel"))
+    n = sum(v["launches"] for k, v in timeline["by_kernel"].items() if k.startswith("ffn_kernel"))
+    if n == 0 or us <= 0:
+        return None
+    tf = flops_per_launch / (us / n * 1e-6) / 1e12
+    return {"avg_launch_us": us / n, "launches": n, "achieved": tf, "frac": tf / peak_tf if peak_tf else None,
+            "share_of_step": us / timeline["span_us"]}
+
+
 def gpu_run(args, c):
     import torch
     import torch.distributed as dist
@@ -408,6 +459,8 @@ def gpu_run(args, c):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
 
+    timeline = in_graph_timeline(run, devb) if (is_train and use_graph and world == 1 and rank == 0) else None
+
     # ---- per-kernel-class timing: CUDA events around every launch of the engine, kernel by kernel on one stream (no graph, no
     # overlap between consecutive kernels), plus events around the whole eager step so that the shares add up
     eng.set_profiling(True)
@@ -521,11 +574,13 @@ def gpu_run(args, c):
                      "ms_per_step": dom_ms / prof_steps, "share_of_eager_step": (dom_ms / prof_steps) / eager_ms if eager_ms else None,
                      "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst: the step is a few ms at full clocks; "
                                      "frac_of_sustained_peak beside it)") if peaks else "fallback",
+                     "in_graph": in_graph_roofline(timeline, dom_fl / dom_n if dom_n else None, burst_tf) if ffn[1] > 0 else None,
                      "tensor_family": {"what": "plain GEMMs + grouped weight gradients + ffn_kernel (attention listed in breakdown)",
                                        "achieved": family_tf, "frac": family_tf / burst_tf if burst_tf else None,
                                        "launches_per_step": gemm_n // prof_steps, "ms_per_step": gemm_ms / prof_steps,
                                        "share_of_eager_step": (gemm_ms / prof_steps) / eager_ms if eager_ms else None}},
         "breakdown": breakdown,
+        "in_graph": timeline,
         "framepass_roofline": frame,
         "gpu_baseline": gpu_base,
         "cpu_baseline": None if cpu is None else {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
