@@ -17,6 +17,15 @@ except Exception as e:
     print(open(f"gpurun_out/dp_{name}.err").read()[-1500:])
 PY
 }
+if [ "$2" = "nvls" ]; then
+run nvls_r4 NCCL_ALGO=NVLS KIT_COLLECTIVE_SMS=4
+run nvls_r8 NCCL_ALGO=NVLS KIT_COLLECTIVE_SMS=8
+exit 0
+fi
+if [ "$2" = "train" ]; then
+run train_n$N
+exit 0
+fi
 if [ "$2" = "final" ]; then
 run final_r8 KIT_COLLECTIVE_SMS=8
 run final_r16 KIT_COLLECTIVE_SMS=16
