@@ -49,6 +49,7 @@ __device__ __forceinline__ void pdl_grid_sync() {
 }
 bool pdl_enabled();   // errors.cu: KIT_PDL=0 turns the attribute off (A/B measurements)
 int sm_reserve();     // errors.cu: SMs the persistent kernels leave free for concurrent collectives (kit_set_sm_reserve)
+void set_sm_reserve_active(bool on);   // engine.cu: off while no collective can be in flight (forward, backward before its first bucket)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};

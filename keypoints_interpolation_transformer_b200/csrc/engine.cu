@@ -665,6 +665,13 @@ static int swiglu_bwd(KitEngine* e, const bf16* dout, const bf16* x, const SwiW&
   return linear_dgrad(e, e->g2h, 2 * H, s.fc12, 0, 2 * H, dx_out, H, nullptr, 0);
 }
 
+// Scope during which no collective can be in flight: the persistent kernels planned / launched inside keep every SM.
+struct ReserveOff {
+  ReserveOff() { set_sm_reserve_active(false); }
+  ~ReserveOff() { set_sm_reserve_active(true); }
+  void end() { set_sm_reserve_active(true); }
+};
+
 static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const float* x_dec, int64_t xds,
                           const KitAttnMask* em, const KitAttnMask* dm, int zero_masked, float* pred) {
   const Layout& L = e->L;
@@ -676,6 +683,7 @@ static int engine_forward(KitEngine* e, const float* x_enc, int64_t xes, const f
   e->ffn_cursor = 0;
   e->launches = 0;
   prof_reset(e);
+  ReserveOff no_collective_in_flight;   // every all-reduce of the previous step was waited for by its optimiser step
   e->enc_mask = em ? *em : KitAttnMask{};
   e->dec_mask = dm ? *dm : KitAttnMask{};
   if (x_enc != nullptr) {   // else: the pre-pass wrote the bf16 operands straight into xe / xd (kit_engine_operands)
@@ -752,8 +760,10 @@ static int engine_backward(KitEngine* e, const float* dpred, KitBucketCallback c
   e->launches = 0;
   std::vector<PendingW> pend;
   int bucket = 0;
+  ReserveOff before_first_bucket;   // the first all-reduce starts at the first bucket callback: until then the kernels keep every SM
   auto done = [&]() {
     if (cb) cb(bucket, user);
+    before_first_bucket.end();
     ++bucket;
   };
   // ---- output head
