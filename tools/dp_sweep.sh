@@ -22,6 +22,10 @@ run nvls_r4 NCCL_ALGO=NVLS KIT_COLLECTIVE_SMS=4
 run nvls_r8 NCCL_ALGO=NVLS KIT_COLLECTIVE_SMS=8
 exit 0
 fi
+if [ "$2" = "b3" ]; then
+run b3_n$N KIT_BUCKET_LAYERS=3
+exit 0
+fi
 if [ "$2" = "train" ]; then
 run train_n$N
 exit 0
